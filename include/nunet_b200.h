@@ -1,0 +1,103 @@
+/* nunet_b200.h — C ABI of the B200-native UNet++ hot path (libnunet_b200.so).
+ *
+ * The reference (husheng876/pytorch_nested-unet) has no FFI/plugin interface: its boundary is the Python module
+ * surface (archs.NestedUNet / archs.UNet, losses.BCEDiceLoss, metrics.iou_score).  The entry
+ * points below are what that surface binds to in this build; each comment cites the reference lines whose GPU
+ * work the entry point replaces.  Conventions (all functions):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller unless stated otherwise
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises, allocates or frees device memory
+ *   - return 0 on success; NUNET_E_* (>0) for an invalid descriptor, 1000+cudaError_t for a CUDA launch error
+ *   - re-entrant across streams/devices (no mutable global state)
+ */
+#ifndef NUNET_B200_H
+#define NUNET_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUNET_ABI_VERSION 1
+#define NUNET_MAX_SRC 5
+
+enum { NUNET_OK = 0, NUNET_E_BADARG = 1, NUNET_E_UNSUPPORTED = 2, NUNET_E_SMEM = 3, NUNET_E_CUDA = 1000 };
+
+/* How one concatenated source enters the consuming 3x3 convolution's loader. */
+enum {
+    NUNET_SRC_INPUT = 0, /* network input, fp32 NCHW [N,C,H,W], C <= 16 (zero-padded to 16 channels)            */
+    NUNET_SRC_SAME = 1,  /* relu(scale*y+shift) of a raw conv output y at the same resolution (bf16 NHWC)       */
+    NUNET_SRC_POOL = 2,  /* 2x2 max-pool of relu(scale*y+shift), y at (2H,2W)   — finished/archs1.py:82        */
+    NUNET_SRC_UP = 3,    /* bilinear 2x (align_corners=True) of relu(scale*y+shift), y at (H/2,W/2) — :83       */
+    NUNET_SRC_GRAD = 4   /* backward operand: scale*gz + k2*y + shift (BatchNorm backward folded into loader)   */
+};
+
+typedef struct {
+    const void* data;   /* see kind */
+    const void* data2;  /* GRAD: raw conv output y (bf16 NHWC); else NULL */
+    const float* scale; /* [C] per-channel; INPUT: unused */
+    const float* shift; /* [C] */
+    const float* k2;    /* [C] GRAD only */
+    int32_t C;          /* channels contributed (multiple of 32; INPUT: real channel count <= 16) */
+    int32_t kind;
+} nunet_src_t;
+
+/* One fused 3x3 convolution:  out[n,y,x,co] = sum_{src, ci, r, s} T_src(a_src)[n,y+r-1,x+s-1,ci] * W[co,ci,r,s]
+ * (zero padding applied AFTER the per-source transform, as torch.cat + nn.Conv2d(padding=1) does).
+ * Replaces, for one VGGBlock conv: nn.Conv2d (finished/archs1.py:18,20,24,28) and — via the source kinds — the
+ * preceding nn.BatchNorm2d + ReLU apply (:25-26,29-30), nn.MaxPool2d (:82), nn.Upsample (:83) and torch.cat (:117-132).
+ * With stat_part != NULL the epilogue also emits per-CTA per-channel [sum, sum of squares] of the fp32 accumulators
+ * (the batch statistics nn.BatchNorm2d computes in train mode).  The same entry point runs dgrad (source kind GRAD,
+ * weights packed with NUNET_PACK_DGRAD). */
+typedef struct {
+    int32_t N, H, W; /* output resolution */
+    int32_t num_src;
+    nunet_src_t src[NUNET_MAX_SRC];
+    int32_t Cout;      /* output channels (row pitch of `out`) */
+    const void* wpack; /* from nunet_pack_weights with the plan of this descriptor */
+    void* out;         /* bf16 NHWC [N,H,W,Cout] */
+    float* stat_part;  /* [plan.grid_m][2][Cout] fp32 or NULL */
+} nunet_conv_desc_t;
+
+typedef struct {
+    int32_t T, NT, CK, S, P; /* M-tiles per CTA, N tile, channels per K chunk, pipeline stages, staged positions */
+    int32_t nchunks, n_tiles, grid_m, cin_pad;
+    int32_t smem_bytes, tmem_cols;
+    int64_t wpack_elems; /* bf16 elements the packed weights occupy */
+} nunet_conv_plan_t;
+
+int nunet_version(void);
+/* Tiling decision for a conv of this shape (pure host function, no CUDA calls). */
+int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* plan);
+int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream);
+
+enum { NUNET_PACK_FWD = 0, NUNET_PACK_DGRAD = 1 };
+/* fp32 OIHW master weights [Cout,Cin,3,3] -> bf16 tile images consumed by cp.async.bulk (one contiguous block per
+ * (N tile, K chunk)).  FWD: GEMM-N = Cout, GEMM-K = Cin (padded to cin_pad).  DGRAD: GEMM-N = Cin, GEMM-K = Cout,
+ * taps flipped (transposed convolution).  `plan` is the plan of the conv that will consume the pack. */
+int nunet_pack_weights(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t mode, const nunet_conv_plan_t* plan,
+                       void* wpack, void* stream);
+
+/* Reduce the per-CTA partial statistics and emit the BN apply coefficients (nn.BatchNorm2d train-mode forward,
+ * finished/archs1.py:19,21): mean/var over count = N*H*W, scale = gamma*rsqrt(var+eps), shift = beta - mean*scale,
+ * running_mean/var momentum update (unbiased var), conv bias folded into running_mean (the bias itself cancels in
+ * train-mode BN and is never added to y).  save_mean / save_invstd are kept for the backward pass.
+ * scratch: nunet_bn_workspace_bytes(C) bytes; counters: C/32 uint32, zero-initialised once (self-resetting).
+ * sums_out (optional): [2][C] fp64 [sum, sum of squares] — with gamma == NULL only the sums are produced, which is
+ * the SyncBN path: all-reduce sums_out across ranks, then nunet_bn_finalize_from_sums with the GLOBAL count. */
+int nunet_bn_workspace_bytes(int32_t C);
+int nunet_bn_finalize_train(const float* stat_part, int32_t rows, int32_t C, double count, const float* gamma,
+                            const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                            float momentum, float eps, float* scale, float* shift, float* save_mean,
+                            float* save_invstd, double* scratch, uint32_t* counters, double* sums_out, void* stream);
+int nunet_bn_finalize_from_sums(const double* sums, int32_t C, double count, const float* gamma, const float* beta,
+                                const float* conv_bias, float* running_mean, float* running_var, float momentum,
+                                float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                                void* stream);
+/* Eval mode: scale = gamma*rsqrt(running_var+eps), shift = beta + (conv_bias - running_mean)*scale. */
+int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
+                       const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,75 @@
+"""ctypes binding of libnunet_b200.so (the C ABI declared in include/nunet_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnunet_b200.so")
+
+MAX_SRC = 5
+SRC_INPUT, SRC_SAME, SRC_POOL, SRC_UP, SRC_GRAD = 0, 1, 2, 3, 4
+PACK_FWD, PACK_DGRAD = 0, 1
+
+
+class Src(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data2", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("k2", C.c_void_p), ("C", C.c_int32), ("kind", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_src", C.c_int32), ("src", Src * MAX_SRC),
+                ("Cout", C.c_int32), ("wpack", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p)]
+
+
+class ConvPlan(C.Structure):
+    _fields_ = [("T", C.c_int32), ("NT", C.c_int32), ("CK", C.c_int32), ("S", C.c_int32), ("P", C.c_int32),
+                ("nchunks", C.c_int32), ("n_tiles", C.c_int32), ("grid_m", C.c_int32), ("cin_pad", C.c_int32),
+                ("smem_bytes", C.c_int32), ("tmem_cols", C.c_int32), ("wpack_elems", C.c_int64)]
+
+
+class NunetError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    "nunet_version": ([], C.c_int),
+    "nunet_conv3x3_plan": ([C.c_int32] * 5 + [C.POINTER(ConvPlan)], C.c_int),
+    "nunet_conv3x3_fwd": ([C.POINTER(ConvDesc), C.c_void_p], C.c_int),
+    "nunet_pack_weights": ([C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ConvPlan), C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_bn_workspace_bytes": ([C.c_int32], C.c_int),
+    "nunet_bn_finalize_train": ([C.c_void_p, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 5 + [C.c_float, C.c_float]
+                                + [C.c_void_p] * 8, C.c_int),
+    "nunet_bn_finalize_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 5 + [C.c_float, C.c_float]
+                                    + [C.c_void_p] * 5, C.c_int),
+    "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
+}
+
+
+def lib():
+    """Loads the shared library once; raises if it is not built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NunetError("libnunet_b200.so is not built: run `python pytorch_nested-unet_b200/build.py` "
+                             "(or __graft_entry__.build()). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc >= 1000:
+            raise NunetError("%s: CUDA error %d" % (what, rc - 1000))
+        raise NunetError("%s: error %d (%s)" % (what, rc, {1: "bad argument", 2: "unsupported shape", 3: "shared memory"}.get(rc, "?")))

@@ -1,0 +1,142 @@
+// BatchNorm statistics: reduction of the conv epilogue's per-CTA partials and emission of the apply coefficients
+// consumed by the NEXT conv's loader (train mode), running-stat update, eval-mode folding, and the backward
+// coefficient kernel.  All HBM-trivial (C <= 512 channels); latency matters, so one launch does reduce + finalize via
+// the last-block-done pattern (deterministic: the last block sums the fixed RS slices in a fixed order, in fp64).
+#include "conv_common.cuh"
+
+namespace nunet {
+
+constexpr int kRS = 32;  // row slices per channel group
+
+struct BnFinalizeArgs {
+    double count;
+    const float* gamma;
+    const float* beta;
+    const float* conv_bias;
+    float* running_mean;
+    float* running_var;
+    float momentum, eps;
+    float* scale;
+    float* shift;
+    float* save_mean;
+    float* save_invstd;
+};
+
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS) {
+    const double mean = S / a.count;
+    double var = SS / a.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.scale[c] = sc;
+    a.shift[c] = a.beta[c] - (float)mean * sc;
+    if (a.save_mean) a.save_mean[c] = (float)mean;
+    if (a.save_invstd) a.save_invstd[c] = invstd;
+    if (a.running_mean) {
+        const double b = a.conv_bias ? (double)a.conv_bias[c] : 0.0;  // the dropped conv bias only shifts the mean
+        a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * (mean + b));
+        const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+        a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
+    }
+}
+
+// grid (C/32, kRS), block 256 = 32 channels x 8 row lanes.  part: [rows][2][C].
+// sums_out (optional): [2][C] fp64 — the cross-rank SyncBN exchange buffer.  fin.gamma == nullptr -> reduce only.
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ part, int rows, int C, double* scratch,
+                                                        unsigned* counters, double* sums_out, BnFinalizeArgs fin) {
+    __shared__ float sh[2][8][32];
+    __shared__ bool last;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int per = (rows + kRS - 1) / kRS;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    float s = 0.f, ss = 0.f;
+    for (int r = r0 + rl; r < r1; r += 8) {
+        s += part[(size_t)r * 2 * C + c];
+        ss += part[(size_t)r * 2 * C + C + c];
+    }
+    sh[0][rl][cl] = s;
+    sh[1][rl][cl] = ss;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int which = threadIdx.x >> 5;
+        double acc = 0.0;
+        for (int i = 0; i < 8; ++i) acc += (double)sh[which][i][cl];
+        scratch[((size_t)blockIdx.y * 2 + which) * C + c] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&counters[blockIdx.x], 1u);
+        last = (prev == kRS - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double S = 0.0, SS = 0.0;
+        for (int i = 0; i < kRS; ++i) {
+            S += scratch[((size_t)i * 2 + 0) * C + c];
+            SS += scratch[((size_t)i * 2 + 1) * C + c];
+        }
+        if (sums_out) { sums_out[c] = S; sums_out[C + c] = SS; }
+        if (fin.gamma) bn_finalize_channel(fin, c, S, SS);
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;  // self-resetting for the next launch
+}
+
+__global__ void bn_finalize_from_sums_kernel(const double* __restrict__ sums, int C, BnFinalizeArgs fin) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) bn_finalize_channel(fin, c, sums[c], sums[C + c]);
+}
+
+__global__ void bn_fold_eval_kernel(int C, const float* gamma, const float* beta, const float* bias, const float* rm,
+                                    const float* rv, float eps, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] * (1.0f / sqrtf(rv[c] + eps));
+    scale[c] = sc;
+    shift[c] = beta[c] + ((bias ? bias[c] : 0.f) - rm[c]) * sc;
+}
+
+}  // namespace nunet
+
+using namespace nunet;
+
+static inline int cuda_rc() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+}
+
+extern "C" int nunet_bn_workspace_bytes(int32_t C) { return (int)(sizeof(double) * kRS * 2 * C); }
+
+extern "C" int nunet_bn_finalize_train(const float* stat_part, int32_t rows, int32_t C, double count, const float* gamma,
+                                       const float* beta, const float* conv_bias, float* running_mean, float* running_var,
+                                       float momentum, float eps, float* scale, float* shift, float* save_mean,
+                                       float* save_invstd, double* scratch, uint32_t* counters, double* sums_out,
+                                       void* stream) {
+    if (!stat_part || rows <= 0 || C <= 0 || C % 32 != 0 || !scratch || !counters) return NUNET_E_BADARG;
+    if (gamma && (!beta || !scale || !shift || count <= 0)) return NUNET_E_BADARG;
+    BnFinalizeArgs f{count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
+    bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(stat_part, rows, C, scratch, counters, sums_out, f);
+    return cuda_rc();
+}
+
+extern "C" int nunet_bn_finalize_from_sums(const double* sums, int32_t C, double count, const float* gamma, const float* beta,
+                                           const float* conv_bias, float* running_mean, float* running_var, float momentum,
+                                           float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                                           void* stream) {
+    if (!sums || C <= 0 || !gamma || !beta || !scale || !shift || count <= 0) return NUNET_E_BADARG;
+    BnFinalizeArgs f{count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
+    bn_finalize_from_sums_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, f);
+    return cuda_rc();
+}
+
+extern "C" int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
+                                  const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
+                                  void* stream) {
+    if (C <= 0 || !gamma || !beta || !running_mean || !running_var || !scale || !shift) return NUNET_E_BADARG;
+    bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, conv_bias, running_mean, running_var,
+                                                                           eps, scale, shift);
+    return cuda_rc();
+}

@@ -1,0 +1,29 @@
+// Shared declarations of the conv kernels (kernel parameter blocks mirror include/nunet_b200.h descriptors).
+#pragma once
+#include "ptx.cuh"
+#include "../../include/nunet_b200.h"
+
+namespace nunet {
+
+struct ConvSrc {
+    const void* data;
+    const void* data2;
+    const float* scale;
+    const float* shift;
+    const float* k2;
+    int C;
+    int kind;
+};
+
+struct ConvParams {
+    int N, H, W;
+    int Wp, Hp1;  // W+2, H+1
+    int Q;        // padded positions: (N*(H+1)+1)*(W+2)
+    int T, NT, CK, S, P, nchunks, cin_pad, Cout, num_src, tmem_cols;
+    ConvSrc src[NUNET_MAX_SRC];
+    const void* wpack;
+    void* out;
+    float* stat_part;
+};
+
+}  // namespace nunet

@@ -1,0 +1,131 @@
+"""Parity of the fused implicit-GEMM conv (forward + BN statistics) against a torch fp32 reference on the device."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_src(kind, N, H, W, C, gen, dev):
+    """Random raw producer output at the resolution the kind implies + random BN coefficients (both signs)."""
+    import _lib as L
+    import ops
+    hs, ws = {"same": (H, W), "pool": (2 * H, 2 * W), "up": (H // 2, W // 2)}[kind]
+    y = (torch.randn(N, hs, ws, C, generator=gen, device=dev) * 1.5).to(torch.bfloat16)
+    scale = torch.randn(C, generator=gen, device=dev)
+    shift = torch.randn(C, generator=gen, device=dev) * 0.5
+    k = {"same": L.SRC_SAME, "pool": L.SRC_POOL, "up": L.SRC_UP}[kind]
+    return ops.Source(k, y, C, scale, shift), (kind, y, scale, shift)
+
+
+CASES = [
+    # (N, H, W, [(kind, C), ...], Cout)
+    (2, 32, 32, [("same", 32)], 32),
+    (3, 16, 16, [("same", 64)], 64),
+    (4, 8, 8, [("same", 128)], 128),
+    (5, 6, 6, [("same", 256)], 256),
+    (3, 6, 6, [("same", 512)], 512),
+    (2, 16, 16, [("pool", 32)], 64),
+    (2, 6, 6, [("pool", 256)], 512),
+    (2, 32, 32, [("same", 32), ("up", 64)], 32),
+    (2, 32, 32, [("same", 32), ("same", 32), ("same", 32), ("same", 32), ("up", 64)], 32),
+    (2, 12, 12, [("same", 256), ("up", 512)], 256),
+    (2, 16, 16, [("same", 64), ("same", 64), ("same", 64), ("up", 128)], 64),
+    (3, 48, 80, [("same", 32), ("up", 64)], 32),
+    (16, 96, 96, [("same", 32)], 32),
+    (16, 48, 48, [("same", 64), ("up", 128)], 64),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%d_%dx%d_%s_%d" % (c[0], c[1], c[2], "+".join("%s%d" % s for s in c[3]), c[4]))
+def test_conv_fwd_sources(case):
+    import _lib as L
+    import ops
+    from refops import conv_ref, source_tensor
+    N, H, W, srcs, Cout = case
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(1234 + N + H + Cout)
+    sources, refs = [], []
+    for kind, Cc in srcs:
+        s, r = _mk_src(kind, N, H, W, Cc, gen, dev)
+        sources.append(s)
+        refs.append(r)
+    cin = sum(c for _, c in srcs)
+    w = torch.randn(Cout, cin, 3, 3, generator=gen, device=dev) * (2.0 / (9 * cin)) ** 0.5
+    plan = ops.conv_plan(N, H, W, cin, Cout)
+    wp = ops.pack_weights(w, L.PACK_FWD, plan)
+    out, part = ops.conv3x3(N, H, W, sources, Cout, wp, want_stats=True)
+    torch.cuda.synchronize()
+    x = torch.cat([source_tensor(*r) for r in refs], 1)
+    ref = conv_ref(x, w)
+    got = out.float().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    tol = 0.008 * ref.abs() + 2e-3 * ref.abs().max()
+    assert bool((err <= tol).all()), "max err %g (ref max %g), T=%d NT=%d CK=%d S=%d" % (err.max(), ref.abs().max(), plan.T, plan.NT, plan.CK, plan.S)
+    # statistics come from the fp32 accumulators
+    s = part[:, 0, :].double().sum(0)
+    ss = part[:, 1, :].double().sum(0)
+    rs = ref.double().sum((0, 2, 3))
+    rss = (ref.double() ** 2).sum((0, 2, 3))
+    assert torch.allclose(s, rs, rtol=2e-3, atol=2e-3 * float(rss.max().sqrt())), (s - rs).abs().max()
+    assert torch.allclose(ss, rss, rtol=2e-3), ((ss - rss) / rss).abs().max()
+
+
+@pytest.mark.parametrize("cin_real", [3, 1, 4])
+def test_conv_fwd_stem_input(cin_real):
+    import _lib as L
+    import ops
+    from refops import conv_ref
+    N, H, W, Cout = 3, 32, 48, 32
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(N, cin_real, H, W, generator=gen, device=dev)
+    w = torch.randn(Cout, cin_real, 3, 3, generator=gen, device=dev) * 0.2
+    plan = ops.conv_plan(N, H, W, 16, Cout)
+    wp = ops.pack_weights(w, L.PACK_FWD, plan)
+    out, part = ops.conv3x3(N, H, W, [ops.Source(L.SRC_INPUT, x, cin_real)], Cout, wp, want_stats=True)
+    torch.cuda.synchronize()
+    ref = conv_ref(x, w)
+    got = out.float().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    assert bool((err <= 0.008 * ref.abs() + 2e-3 * ref.abs().max()).all()), err.max()
+
+
+def test_bn_finalize_matches_batchnorm():
+    import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    Cc, rows = 64, 77
+    part = torch.rand(rows, 2, Cc, generator=gen, device=dev)
+    part[:, 1, :] += 3.0
+    count = 1000.0
+    gamma = torch.randn(Cc, generator=gen, device=dev)
+    beta = torch.randn(Cc, generator=gen, device=dev)
+    bias = torch.randn(Cc, generator=gen, device=dev)
+    rm = torch.randn(Cc, generator=gen, device=dev)
+    rv = torch.rand(Cc, generator=gen, device=dev) + 0.5
+    rm0, rv0 = rm.clone(), rv.clone()
+    ws = ops.BnWorkspace(dev)
+    scale, shift, mean, invstd = (torch.empty(Cc, device=dev) for _ in range(4))
+    sums = torch.empty(2, Cc, dtype=torch.float64, device=dev)
+    for _ in range(2):  # twice: the counters must self-reset
+        rm.copy_(rm0)
+        rv.copy_(rv0)
+        ops.bn_finalize_train(part, count, gamma, beta, bias, rm, rv, 0.1, 1e-5, ws, scale, shift, mean, invstd, sums_out=sums)
+    torch.cuda.synchronize()
+    S = part[:, 0].double().sum(0)
+    SS = part[:, 1].double().sum(0)
+    m = S / count
+    v = SS / count - m * m
+    assert torch.allclose(sums[0], S, rtol=1e-6) and torch.allclose(sums[1], SS, rtol=1e-6)
+    assert torch.allclose(mean.double(), m, rtol=1e-5, atol=1e-6)
+    inv = 1.0 / torch.sqrt(v + 1e-5)
+    assert torch.allclose(invstd.double(), inv, rtol=1e-5)
+    assert torch.allclose(scale.double(), gamma.double() * inv, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(shift.double(), beta.double() - m * gamma.double() * inv, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm.double(), 0.9 * rm0.double() + 0.1 * (m + bias.double()), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv.double(), 0.9 * rv0.double() + 0.1 * v * count / (count - 1), rtol=1e-5, atol=1e-6)
+    # SyncBN path: sums -> finalize
+    scale2, shift2 = torch.empty_like(scale), torch.empty_like(shift)
+    ops.bn_finalize_from_sums(sums, count, gamma, beta, None, None, None, 0.1, 1e-5, scale2, shift2, None, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(scale2, scale) and torch.allclose(shift2, shift)
