@@ -97,6 +97,79 @@ int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* beta, const f
                        const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
                        void* stream);
 
+/* ---- 1x1 heads, loss, metric (finished/archs1.py:106-111,135-142; losses.py:107-117; metrics.py:6-18) ---------------
+ * head_fwd: logits[n,k,y,x] (fp32 NCHW) = sum_c relu(scale*y+shift)[n,y,x,c]*wh[k,c] + bh[k]; y bf16 NHWC with 32 ch. */
+int nunet_head_fwd(const void* y, const float* scale, const float* shift, const float* wh, const float* bh, int32_t N,
+                   int32_t H, int32_t W, int32_t K, float* logits, void* stream);
+/* One pass over (logits, target) [N][E = K*H*W] fp32: BCE-with-logits + per-sample dice sums + integer IoU counts.
+ * part: [N][bps][4] fp32, cnt: [N][bps][2] int32 with bps = nunet_loss_blocks_per_sample(N,E);
+ * sums: [N][3] fp64 (sum p*t, sum p, sum t — kept for loss_bwd); loss: fp32 scalar (0.5*bce + 1 - mean dice);
+ * counts: [2] int64 (intersection, union over the whole batch and all classes). loss / counts may be NULL. */
+int nunet_loss_blocks_per_sample(int32_t N, int32_t E);
+int nunet_loss_iou_fwd(const float* logits, const float* target, int32_t N, int32_t E, float* part, int32_t* cnt,
+                       double* sums, float* loss, long long* counts, void* stream);
+/* metrics.iou_score counts only: counts[0] = |o & t|, counts[1] = |o | t| with o = sigmoid(logit) > 0.5, t = target > 0.5. */
+int nunet_iou_counts(const float* logits, const float* target, long long total, unsigned long long* counts, void* stream);
+/* dlogits = (gscale ? *gscale : 1) * gmul * d(loss)/d(logits). */
+int nunet_loss_bwd(const float* logits, const float* target, const double* sums, const float* gscale, float gmul, int32_t N,
+                   int32_t E, float* dlogits, void* stream);
+/* Head parameter gradients: dwh[k][c] = sum dlogit*a, dbh[k] = sum dlogit. part: [nunet_head_bwd_params_rows()][K][33]. */
+int nunet_head_bwd_params_rows(void);
+int nunet_head_bwd_params(const void* y, const float* scale, const float* shift, const float* dlogits, int32_t N, int32_t H,
+                          int32_t W, int32_t K, float* part, float* dwh, float* dbh, int32_t accumulate, void* stream);
+
+/* ---- backward of the skip pathway + BatchNorm/ReLU (autograd of finished/archs1.py:23-32,82-83,117-142) ---------------
+ * One consumer of this conv output's activation: the consumer's dgrad buffer (bf16 NHWC at the consumer's resolution,
+ * `pitch` channels per pixel) holds our slice at channel offset `coff`; kind says how the consumer read us. */
+typedef struct {
+    const void* dx;
+    int32_t pitch, coff, kind; /* NUNET_SRC_SAME | NUNET_SRC_POOL | NUNET_SRC_UP */
+} nunet_grad_cons_t;
+
+typedef struct {
+    int32_t N, H, W, C; /* this conv output */
+    const void* y;      /* raw conv output, bf16 NHWC */
+    const float *scale, *shift, *mean, *invstd;
+    int32_t num_cons;
+    nunet_grad_cons_t cons[6];
+    const float* dlogits; /* optional head consumer: fp32 NCHW [N,K,H,W] */
+    const float* wh;      /* [K][C] */
+    int32_t K;
+    void* gz;    /* out: g_z = g_a * [a>0], bf16 NHWC */
+    float* part; /* out: [nunet_grad_router_rows()][2][C]: sum g_z, sum g_z*yhat */
+} nunet_router_desc_t;
+int nunet_grad_router_rows(int32_t N, int32_t H, int32_t W, int32_t C);
+int nunet_grad_router(const nunet_router_desc_t* d, void* stream);
+/* Finishes BatchNorm backward: dbeta = S1, dgamma = S2 and the loader coefficients of g_y = k1*g_z + k2*y + k3.
+ * gamma == NULL: only sums_out ([2][C] fp64) is produced (SyncBN: all-reduce, then nunet_bn_backward_from_sums). */
+int nunet_bn_backward_reduce(const float* part, int32_t rows, int32_t C, double count, const float* gamma,
+                             const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
+                             float* k2, float* k3, double* scratch, uint32_t* counters, double* sums_out, void* stream);
+int nunet_bn_backward_from_sums(const double* sums, int32_t C, double count, const float* gamma, const float* save_mean,
+                                const float* save_invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
+                                void* stream);
+
+/* ---- weight gradient (autograd of nn.Conv2d, finished/archs1.py:18,20) --------------------------------------------------
+ * dw[co][ci][3][3] (fp32 OIHW, overwritten) = sum over pixels of g_y (x) X, with X read through the same fused loaders
+ * as the forward conv (src[]) and g_y = k1*gz + k2*y + k3.  part: plan.part_elems fp32 of scratch. */
+typedef struct {
+    int32_t KP, S, Pg, cpc, nchunks_total, splits, m_tiles, n_tiles, cin_pad, smem_bytes;
+    int64_t part_elems;
+} nunet_wgrad_plan_t;
+typedef struct {
+    int32_t N, H, W;
+    int32_t num_src;
+    nunet_src_t src[NUNET_MAX_SRC];
+    int32_t Cout;
+    const void* gz; /* bf16 NHWC [N,H,W,Cout] */
+    const void* y;  /* raw conv output, bf16 NHWC */
+    const float *k1, *k2, *k3;
+    float* part;
+    float* dw;
+} nunet_wgrad_desc_t;
+int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* plan);
+int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,28 @@ class ConvPlan(C.Structure):
                 ("smem_bytes", C.c_int32), ("tmem_cols", C.c_int32), ("wpack_elems", C.c_int64)]
 
 
+class GradCons(C.Structure):
+    _fields_ = [("dx", C.c_void_p), ("pitch", C.c_int32), ("coff", C.c_int32), ("kind", C.c_int32)]
+
+
+class RouterDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("y", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("num_cons", C.c_int32), ("cons", GradCons * 6), ("dlogits", C.c_void_p), ("wh", C.c_void_p),
+                ("K", C.c_int32), ("gz", C.c_void_p), ("part", C.c_void_p)]
+
+
+class WgradPlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("KP", "S", "Pg", "cpc", "nchunks_total", "splits", "m_tiles", "n_tiles", "cin_pad",
+                                         "smem_bytes")] + [("part_elems", C.c_int64)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_src", C.c_int32), ("src", Src * MAX_SRC),
+                ("Cout", C.c_int32), ("gz", C.c_void_p), ("y", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p),
+                ("k3", C.c_void_p), ("part", C.c_void_p), ("dw", C.c_void_p)]
+
+
 class NunetError(RuntimeError):
     pass
 
@@ -44,6 +66,19 @@ _SIGS = {
                                 + [C.c_void_p] * 8, C.c_int),
     "nunet_bn_finalize_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 5 + [C.c_float, C.c_float]
                                     + [C.c_void_p] * 5, C.c_int),
+    "nunet_head_fwd": ([C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_loss_blocks_per_sample": ([C.c_int32, C.c_int32], C.c_int),
+    "nunet_loss_iou_fwd": ([C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6, C.c_int),
+    "nunet_iou_counts": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_loss_bwd": ([C.c_void_p] * 4 + [C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_head_bwd_params_rows": ([], C.c_int),
+    "nunet_head_bwd_params": ([C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p], C.c_int),
+    "nunet_grad_router_rows": ([C.c_int32] * 4, C.c_int),
+    "nunet_grad_router": ([C.POINTER(RouterDesc), C.c_void_p], C.c_int),
+    "nunet_bn_backward_reduce": ([C.c_void_p, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 12, C.c_int),
+    "nunet_bn_backward_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 9, C.c_int),
+    "nunet_conv3x3_wgrad_plan": ([C.c_int32] * 5 + [C.POINTER(WgradPlan)], C.c_int),
+    "nunet_conv3x3_wgrad": ([C.POINTER(WgradDesc), C.c_void_p], C.c_int),
     "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
 }
 

@@ -9,6 +9,7 @@ namespace nunet {
 constexpr int kRS = 32;  // row slices per channel group
 
 struct BnFinalizeArgs {
+    int mode;  // 0: forward statistics -> apply coefficients ; 1: backward sums -> dgamma/dbeta + loader coefficients
     double count;
     const float* gamma;
     const float* beta;
@@ -20,9 +21,27 @@ struct BnFinalizeArgs {
     float* shift;
     float* save_mean;
     float* save_invstd;
+    // mode 1 (inputs: gamma, save_mean, save_invstd ; sums S1 = sum g_z, S2 = sum g_z*yhat)
+    float* dgamma;
+    float* dbeta;
+    float* k1;
+    float* k2;
+    float* k3;
 };
 
+// BatchNorm backward (nn.BatchNorm2d, train): dbeta = S1, dgamma = S2,
+//   g_y = gamma*r*(g_z - S1/M - yhat*S2/M),  yhat = (y-mean)*r   =>   g_y = k1*g_z + k2*y + k3.
+__device__ __forceinline__ void bn_backward_channel(const BnFinalizeArgs& a, int c, double S1, double S2) {
+    const double g = a.gamma[c], r = a.save_invstd[c], mu = a.save_mean[c], M = a.count;
+    a.dbeta[c] = (float)S1;
+    a.dgamma[c] = (float)S2;
+    a.k1[c] = (float)(g * r);
+    a.k2[c] = (float)(-g * r * r * S2 / M);
+    a.k3[c] = (float)(-g * r * S1 / M + g * r * r * mu * S2 / M);
+}
+
 __device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS) {
+    if (a.mode == 1) { bn_backward_channel(a, c, S, SS); return; }
     const double mean = S / a.count;
     double var = SS / a.count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -117,7 +136,7 @@ extern "C" int nunet_bn_finalize_train(const float* stat_part, int32_t rows, int
                                        void* stream) {
     if (!stat_part || rows <= 0 || C <= 0 || C % 32 != 0 || !scratch || !counters) return NUNET_E_BADARG;
     if (gamma && (!beta || !scale || !shift || count <= 0)) return NUNET_E_BADARG;
-    BnFinalizeArgs f{count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
+    BnFinalizeArgs f{0, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
     bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(stat_part, rows, C, scratch, counters, sums_out, f);
     return cuda_rc();
 }
@@ -127,7 +146,7 @@ extern "C" int nunet_bn_finalize_from_sums(const double* sums, int32_t C, double
                                            float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                                            void* stream) {
     if (!sums || C <= 0 || !gamma || !beta || !scale || !shift || count <= 0) return NUNET_E_BADARG;
-    BnFinalizeArgs f{count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
+    BnFinalizeArgs f{0, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
     bn_finalize_from_sums_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, f);
     return cuda_rc();
 }
@@ -138,5 +157,28 @@ extern "C" int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* be
     if (C <= 0 || !gamma || !beta || !running_mean || !running_var || !scale || !shift) return NUNET_E_BADARG;
     bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, conv_bias, running_mean, running_var,
                                                                            eps, scale, shift);
+    return cuda_rc();
+}
+
+extern "C" int nunet_bn_backward_reduce(const float* part, int32_t rows, int32_t C, double count, const float* gamma,
+                                        const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
+                                        float* k2, float* k3, double* scratch, uint32_t* counters, double* sums_out, void* stream) {
+    if (!part || rows <= 0 || C <= 0 || C % 32 != 0 || !scratch || !counters) return NUNET_E_BADARG;
+    if (gamma && (!save_mean || !save_invstd || !dgamma || !dbeta || !k1 || !k2 || !k3 || count <= 0)) return NUNET_E_BADARG;
+    BnFinalizeArgs f{};
+    f.mode = 1; f.count = count; f.gamma = gamma; f.save_mean = const_cast<float*>(save_mean);
+    f.save_invstd = const_cast<float*>(save_invstd); f.dgamma = dgamma; f.dbeta = dbeta; f.k1 = k1; f.k2 = k2; f.k3 = k3;
+    bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(part, rows, C, scratch, counters, sums_out, f);
+    return cuda_rc();
+}
+
+extern "C" int nunet_bn_backward_from_sums(const double* sums, int32_t C, double count, const float* gamma, const float* save_mean,
+                                           const float* save_invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
+                                           void* stream) {
+    if (!sums || C <= 0 || !gamma || !save_mean || !save_invstd || !dgamma || !dbeta || !k1 || !k2 || !k3 || count <= 0) return NUNET_E_BADARG;
+    BnFinalizeArgs f{};
+    f.mode = 1; f.count = count; f.gamma = gamma; f.save_mean = const_cast<float*>(save_mean);
+    f.save_invstd = const_cast<float*>(save_invstd); f.dgamma = dgamma; f.dbeta = dbeta; f.k1 = k1; f.k2 = k2; f.k3 = k3;
+    bn_finalize_from_sums_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, f);
     return cuda_rc();
 }

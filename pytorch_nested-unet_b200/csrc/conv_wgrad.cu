@@ -1,0 +1,298 @@
+// Weight gradient of the fused 3x3 convolution on tcgen05 tensor cores (sm_100a), split-K over positions.
+//
+//   dW[co][ci][tap] = sum_q gy[q][co] * X[q + off(tap)][ci] = sum_q' X[q'][ci] * gy[q' - off(tap)][co]
+// over the flattened padded positions of conv_igemm.cu.  The reduction index (GEMM K) is the POSITION, so both
+// operands are MN-major for the tensor core; the producers stage, per chunk of KP positions,
+//   X  [cgroup(16)][KP][8 ci]        — the conv's virtual input through the FORWARD loaders (BN+ReLU, pool, upsample,
+//                                      concat), unshifted
+//   gy [cgroup(4)][KP + 2Wp + 2][8 co] — k1*g_z + k2*y + k3 (BatchNorm backward folded in), with the halo, so that the
+//                                      nine taps are nine start-address shifts of the SMALL operand.
+// A CTA owns a (128 ci) x (32 co) x (9 taps) accumulator block = 288 TMEM columns and a contiguous range of chunks;
+// partial blocks are written as fp32 and summed in a fixed order by wgrad_reduce_kernel (deterministic).
+#include "conv_common.cuh"
+#include "loaders.cuh"
+
+namespace nunet {
+
+struct WgradParams {
+    int N, H, W, Wp, Hp1;
+    long long Q;
+    int KP, S, Pg, cpc, nchunks_total;
+    int cin_pad, Cout, num_src;
+    ConvSrc src[NUNET_MAX_SRC];
+    ConvSrc gsrc;  // GRAD: data = g_z, data2 = y, scale = k1, k2, shift = k3 ; C = Cout
+    float* part;   // [splits][Cout/32][9][cin_pad][32]
+};
+
+constexpr int kWThreads = 320;
+constexpr int kWProducerWarps = 8;
+
+__global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const WgradParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t x_bytes = 16u * p.KP * 16u;
+    const uint32_t g_bytes = 4u * p.Pg * 16u;
+    uint8_t* sX = smem;
+    uint8_t* sG = sX + (size_t)p.S * x_bytes;
+    PixInfo* tabs = reinterpret_cast<PixInfo*>(sG + (size_t)p.S * g_bytes);  // [S][Pg]
+    float* s_scale = reinterpret_cast<float*>(tabs + (size_t)p.S * p.Pg);    // [cin_pad]
+    float* s_shift = s_scale + p.cin_pad;
+    float* s_g = s_shift + p.cin_pad;  // [3][32]: k1, k2, k3 of this CTA's 32 output channels
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_g + 96);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.S;
+    uint64_t* accum = bars + 2 * p.S;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * p.S + 1);
+
+    const int split = blockIdx.x, m_tile = blockIdx.y, n_tile = blockIdx.z;
+    const int chunk0 = split * p.cpc;
+    const int nchunks = min(p.cpc, p.nchunks_total - chunk0);
+    const int ci0 = m_tile * 128;
+    const int mcg = min(16, (p.cin_pad - ci0) >> 3);  // staged channel groups of this M tile
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < p.S; ++s) {
+                mbar_init(&full[s], kWProducerWarps);
+                mbar_init(&empty[s], 1);
+            }
+            mbar_init(accum, 1);
+            mbar_init_fence();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_ptr);
+    }
+    {
+        int cbase = 0;
+        for (int si = 0; si < p.num_src; ++si) {
+            const ConvSrc& s = p.src[si];
+            const int cpad = (s.kind == NUNET_SRC_INPUT) ? 16 : s.C;
+            for (int c = threadIdx.x; c < cpad; c += kWThreads) {
+                const bool has = (s.kind != NUNET_SRC_INPUT);
+                s_scale[cbase + c] = has ? s.scale[c] : 1.f;
+                s_shift[cbase + c] = has ? s.shift[c] : 0.f;
+            }
+            cbase += cpad;
+        }
+        if (threadIdx.x < 32) {
+            s_g[threadIdx.x] = p.gsrc.scale[n_tile * 32 + threadIdx.x];
+            s_g[32 + threadIdx.x] = p.gsrc.k2[n_tile * 32 + threadIdx.x];
+            s_g[64 + threadIdx.x] = p.gsrc.shift[n_tile * 32 + threadIdx.x];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < kWProducerWarps) {
+        const int pl = lane & 7, r = lane >> 3;
+        const int tid = threadIdx.x;  // 0..255
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            const int s = chunk % p.S;
+            const uint32_t ph = (chunk / p.S) & 1;
+            const long long k0 = (long long)(chunk0 + chunk) * p.KP;  // first position of the chunk
+            PixInfo* tab = tabs + (size_t)s * p.Pg;
+            mbar_wait(&empty[s], ph ^ 1);
+            for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position(k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- gy with halo: 4 channel groups x Pg positions
+            {
+                float k1[8], k2[8], k3[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { k1[i] = s_g[r * 8 + i]; k2[i] = s_g[32 + r * 8 + i]; k3[i] = s_g[64 + r * 8 + i]; }
+                uint8_t* dst = sG + (size_t)s * g_bytes + (size_t)r * p.Pg * 16;
+                const int nblk = (p.Pg + 7) >> 3;
+                for (int blk = warp; blk < nblk; blk += kWProducerWarps) {
+                    const int pp = blk * 8 + pl;
+                    if (pp < p.Pg) {
+                        const PixInfo pi = tab[pp];
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (pi.pix >= 0) v = load_transform(p.gsrc, p.H, p.W, pi, n_tile * 32 + r * 8, k1, k3, k2);
+                        *reinterpret_cast<uint4*>(dst + (size_t)pp * 16) = v;
+                    }
+                }
+            }
+            // ---- X: mcg channel groups x KP positions (positions [Wp+1, Wp+1+KP) of the table)
+            {
+                const int nquads = (mcg + 3) >> 2;
+                const int nblk = (p.KP >> 3) * nquads;
+                for (int blk = warp; blk < nblk; blk += kWProducerWarps) {
+                    const int quad = blk % nquads, pb = blk / nquads;
+                    const int cg = quad * 4 + r;
+                    if (cg < mcg) {
+                        const int pp = pb * 8 + pl;
+                        const int cglob = ci0 + cg * 8;
+                        int si = 0, c0 = 0;
+                        while (true) {
+                            const int cpad = (p.src[si].kind == NUNET_SRC_INPUT) ? 16 : p.src[si].C;
+                            if (cglob < c0 + cpad) break;
+                            c0 += cpad;
+                            ++si;
+                        }
+                        const PixInfo pi = tab[pp + p.Wp + 1];
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (pi.pix >= 0) {
+                            float sc[8], sh[8], zz[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { sc[i] = s_scale[cglob + i]; sh[i] = s_shift[cglob + i]; zz[i] = 0.f; }
+                            v = load_transform(p.src[si], p.H, p.W, pi, cglob - c0, sc, sh, zz);
+                        }
+                        *reinterpret_cast<uint4*>(sX + (size_t)s * x_bytes + ((size_t)cg * p.KP + pp) * 16) = v;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        // ---- epilogue: TMEM -> fp32 partial block
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        const int lq = warp & 3, half = warp >> 2;
+        const int ci = ci0 + lq * 32 + lane;
+        float* dst_base = p.part + ((size_t)(split * (p.Cout >> 5) + n_tile) * 9) * p.cin_pad * 32;
+        for (int tap = half; tap < 9; tap += 2) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(tap * 32), v);
+            tmem_ld_wait();
+            if (ci < p.cin_pad) {
+                uint4* d = reinterpret_cast<uint4*>(dst_base + ((size_t)tap * p.cin_pad + ci) * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 32, kMajorMN, kMajorMN);
+            const uint32_t a_sbo = (uint32_t)p.KP * 16u, b_sbo = (uint32_t)p.Pg * 16u;
+            const int ksteps = p.KP >> 4;
+            for (int chunk = 0; chunk < nchunks; ++chunk) {
+                const int s = chunk % p.S;
+                const uint32_t ph = (chunk / p.S) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sX + (size_t)s * x_bytes);
+                const uint32_t b_base = smem_u32(sG + (size_t)s * g_bytes);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dr = tap / 3, dc = tap - 3 * dr;
+                    const uint32_t b_tap = b_base + (uint32_t)((2 - dr) * p.Wp + (2 - dc)) * 16u;
+                    const uint32_t d_addr = tmem_base + (uint32_t)(tap * 32);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t ad = umma_desc_nosw(a_base + (uint32_t)ks * 256u, 128u, a_sbo);
+                        const uint64_t bd = umma_desc_nosw(b_tap + (uint32_t)ks * 256u, 128u, b_sbo);
+                        umma_bf16(d_addr, ad, bd, idesc, (chunk | ks) != 0);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(accum);
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+// dW[co][ci][tap] (fp32 OIHW, ci < Cin real) = sum over splits, fixed order.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Cout, int cin_pad, int Cin, float* __restrict__ dw) {
+    const size_t block_elems = (size_t)(Cout >> 5) * 9 * cin_pad * 32;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < block_elems; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int col = (int)(r & 31); r >>= 5;
+        const int ci = (int)(r % cin_pad); r /= cin_pad;
+        const int tap = (int)(r % 9); r /= 9;
+        const int nt = (int)r;
+        if (ci >= Cin) continue;
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += part[(size_t)k * block_elems + i];
+        dw[((size_t)(nt * 32 + col) * Cin + ci) * 9 + tap] = s;
+    }
+}
+
+}  // namespace nunet
+
+using namespace nunet;
+
+static size_t wgrad_smem_bytes(int KP, int S, int Pg, int cin_pad) {
+    return (size_t)S * (256ull * KP + 64ull * Pg + 8ull * Pg) + (size_t)cin_pad * 8 + 96 * 4 + (2 * S + 1) * 8 + 16 + 128;
+}
+
+extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* pl) {
+    if (!pl || N <= 0 || H <= 0 || W <= 0 || cin_total <= 0 || Cout <= 0 || Cout % 32 != 0) return NUNET_E_BADARG;
+    if (H >= 65536 || W >= 65536) return NUNET_E_UNSUPPORTED;
+    const int cin_pad = cin_total <= 16 ? 16 : cin_total;
+    if (cin_pad % 16 != 0) return NUNET_E_UNSUPPORTED;
+    const long long Q = ((long long)N * (H + 1) + 1) * (W + 2);
+    if (Q >= (1LL << 31) - 4096) return NUNET_E_UNSUPPORTED;
+    const size_t budget = 220 * 1024;
+    int KP = 0, S = 0;
+    for (int kp = 256; kp >= 64 && !KP; kp >>= 1) {
+        const int Pg = kp + 2 * (W + 2) + 2;
+        if ((size_t)Pg * 16 >= (1u << 18)) continue;
+        for (int s = 3; s >= 2; --s)
+            if (wgrad_smem_bytes(kp, s, Pg, cin_pad) <= budget) { KP = kp; S = s; break; }
+    }
+    if (!KP) return NUNET_E_SMEM;
+    const int nchunks_total = (int)((Q + KP - 1) / KP);
+    const int m_tiles = (cin_pad + 127) / 128, n_tiles = Cout / 32;
+    // enough CTAs for ~2 waves, but at least 4 chunks per CTA to amortise prologue + epilogue
+    int splits = (2 * 148 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+    int max_splits = nchunks_total / 4;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int cpc = (nchunks_total + splits - 1) / splits;
+    splits = (nchunks_total + cpc - 1) / cpc;
+    if (S > cpc) S = cpc < 1 ? 1 : cpc;
+    pl->KP = KP; pl->S = S; pl->Pg = KP + 2 * (W + 2) + 2; pl->cpc = cpc; pl->nchunks_total = nchunks_total;
+    pl->splits = splits; pl->m_tiles = m_tiles; pl->n_tiles = n_tiles; pl->cin_pad = cin_pad;
+    pl->smem_bytes = (int)wgrad_smem_bytes(KP, S, pl->Pg, cin_pad);
+    pl->part_elems = (int64_t)splits * n_tiles * 9 * cin_pad * 32;
+    return NUNET_OK;
+}
+
+extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
+    if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->part || !d->dw) return NUNET_E_BADARG;
+    if (!d->gz || !d->y || !d->k1 || !d->k2 || !d->k3) return NUNET_E_BADARG;
+    int cin = 0, cin_real = 0;
+    for (int i = 0; i < d->num_src; ++i) {
+        const nunet_src_t& s = d->src[i];
+        if (!s.data) return NUNET_E_BADARG;
+        if (s.kind == NUNET_SRC_INPUT) {
+            if (s.C < 1 || s.C > 16 || d->num_src != 1) return NUNET_E_UNSUPPORTED;
+            cin += 16; cin_real += s.C;
+        } else {
+            if (s.kind == NUNET_SRC_GRAD || s.C % 32 != 0 || !s.scale || !s.shift) return NUNET_E_BADARG;
+            cin += s.C; cin_real += s.C;
+        }
+    }
+    nunet_wgrad_plan_t pl;
+    int rc = nunet_conv3x3_wgrad_plan(d->N, d->H, d->W, cin, d->Cout, &pl);
+    if (rc) return rc;
+    WgradParams p{};
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
+    p.Q = ((long long)d->N * (d->H + 1) + 1) * (d->W + 2);
+    p.KP = pl.KP; p.S = pl.S; p.Pg = pl.Pg; p.cpc = pl.cpc; p.nchunks_total = pl.nchunks_total;
+    p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src;
+    for (int i = 0; i < d->num_src; ++i) {
+        p.src[i].data = d->src[i].data; p.src[i].data2 = nullptr; p.src[i].scale = d->src[i].scale;
+        p.src[i].shift = d->src[i].shift; p.src[i].k2 = nullptr; p.src[i].C = d->src[i].C; p.src[i].kind = d->src[i].kind;
+    }
+    p.gsrc.data = d->gz; p.gsrc.data2 = d->y; p.gsrc.scale = d->k1; p.gsrc.k2 = d->k2; p.gsrc.shift = d->k3;
+    p.gsrc.C = d->Cout; p.gsrc.kind = NUNET_SRC_GRAD;
+    p.part = d->part;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    conv3x3_wgrad_kernel<<<dim3(pl.splits, pl.m_tiles, pl.n_tiles), kWThreads, pl.smem_bytes, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    const size_t block_elems = (size_t)pl.n_tiles * 9 * pl.cin_pad * 32;
+    int blocks = (int)((block_elems + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d->part, pl.splits, d->Cout, pl.cin_pad, cin_real, d->dw);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+}

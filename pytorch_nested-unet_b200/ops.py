@@ -108,3 +108,121 @@ def bn_finalize_from_sums(sums, count, gamma, beta, conv_bias, running_mean, run
 def bn_fold_eval(gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift):
     L.check(L.lib().nunet_bn_fold_eval(gamma.numel(), _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
                                        _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), _stream()), "nunet_bn_fold_eval")
+
+
+# ------------------------------------------------------------------------------------------------ heads / loss / metric
+def head_fwd(y, scale, shift, wh, bh, N, H, W, logits=None):
+    K = wh.shape[0]
+    if logits is None:
+        logits = torch.empty((N, K, H, W), dtype=torch.float32, device=y.device)
+    L.check(L.lib().nunet_head_fwd(_ptr(y), _ptr(scale), _ptr(shift), _ptr(wh), _ptr(bh), N, H, W, K, _ptr(logits), _stream()), "nunet_head_fwd")
+    return logits
+
+
+def loss_iou_fwd(logits, target, want_counts=True):
+    """Returns (loss 0-dim fp32 tensor, sums [N,3] fp64, counts [2] int64 or None). No host sync."""
+    N = logits.shape[0]
+    E = logits.numel() // N
+    bps = L.lib().nunet_loss_blocks_per_sample(N, E)
+    dev = logits.device
+    part = torch.empty((N, bps, 4), dtype=torch.float32, device=dev)
+    cnt = torch.empty((N, bps, 2), dtype=torch.int32, device=dev)
+    sums = torch.empty((N, 3), dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev) if want_counts else None
+    L.check(L.lib().nunet_loss_iou_fwd(_ptr(logits), _ptr(target), N, E, _ptr(part), _ptr(cnt), _ptr(sums), _ptr(loss), _ptr(counts),
+                                       _stream()), "nunet_loss_iou_fwd")
+    return loss, sums, counts
+
+
+def iou_counts(logits, target):
+    counts = torch.empty(2, dtype=torch.int64, device=logits.device)
+    L.check(L.lib().nunet_iou_counts(_ptr(logits), _ptr(target), logits.numel(), _ptr(counts), _stream()), "nunet_iou_counts")
+    return counts
+
+
+def loss_bwd(logits, target, sums, gscale, gmul=1.0, dlogits=None):
+    N = logits.shape[0]
+    E = logits.numel() // N
+    if dlogits is None:
+        dlogits = torch.empty_like(logits)
+    L.check(L.lib().nunet_loss_bwd(_ptr(logits), _ptr(target), _ptr(sums), _ptr(gscale), float(gmul), N, E, _ptr(dlogits), _stream()), "nunet_loss_bwd")
+    return dlogits
+
+
+def head_bwd_params(y, scale, shift, dlogits, N, H, W, K):
+    dev = y.device
+    rows = L.lib().nunet_head_bwd_params_rows()
+    part = torch.empty((rows, K, 33), dtype=torch.float32, device=dev)
+    dwh = torch.empty((K, 32), dtype=torch.float32, device=dev)
+    dbh = torch.empty((K,), dtype=torch.float32, device=dev)
+    L.check(L.lib().nunet_head_bwd_params(_ptr(y), _ptr(scale), _ptr(shift), _ptr(dlogits), N, H, W, K, _ptr(part), _ptr(dwh), _ptr(dbh), 0,
+                                          _stream()), "nunet_head_bwd_params")
+    return dwh, dbh
+
+
+# ------------------------------------------------------------------------------------------------ backward
+class Consumer(object):
+    __slots__ = ("dx", "pitch", "coff", "kind")
+
+    def __init__(self, dx, pitch, coff, kind):
+        self.dx, self.pitch, self.coff, self.kind = dx, pitch, coff, kind
+
+
+def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, part=None, dlogits=None, wh=None):
+    dev = y.device
+    rows = L.lib().nunet_grad_router_rows(N, H, W, Cc)
+    if gz is None:
+        gz = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=dev)
+    if part is None:
+        part = torch.empty((rows, 2, Cc), dtype=torch.float32, device=dev)
+    d = L.RouterDesc()
+    d.N, d.H, d.W, d.C = N, H, W, Cc
+    d.y, d.scale, d.shift, d.mean, d.invstd = y.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr()
+    d.num_cons = len(consumers)
+    for i, c in enumerate(consumers):
+        d.cons[i].dx, d.cons[i].pitch, d.cons[i].coff, d.cons[i].kind = c.dx.data_ptr(), c.pitch, c.coff, c.kind
+    if dlogits is not None:
+        d.dlogits, d.wh, d.K = dlogits.data_ptr(), wh.data_ptr(), wh.shape[0]
+    d.gz, d.part = gz.data_ptr(), part.data_ptr()
+    L.check(L.lib().nunet_grad_router(C.byref(d), _stream()), "nunet_grad_router")
+    return gz, part
+
+
+def bn_backward_reduce(part, count, gamma, mean, invstd, ws, dgamma, dbeta, k1, k2, k3, sums_out=None, finalize=True):
+    rows, _, Cc = part.shape
+    L.check(L.lib().nunet_bn_backward_reduce(_ptr(part), rows, Cc, float(count), _ptr(gamma if finalize else None), _ptr(mean), _ptr(invstd),
+                                             _ptr(dgamma), _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), _ptr(ws.scratch), _ptr(ws.counters),
+                                             _ptr(sums_out), _stream()), "nunet_bn_backward_reduce")
+
+
+def bn_backward_from_sums(sums, count, gamma, mean, invstd, dgamma, dbeta, k1, k2, k3):
+    L.check(L.lib().nunet_bn_backward_from_sums(_ptr(sums), gamma.numel(), float(count), _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(dgamma),
+                                                _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), _stream()), "nunet_bn_backward_from_sums")
+
+
+@functools.lru_cache(maxsize=None)
+def wgrad_plan(N, H, W, cin_total, Cout):
+    pl = L.WgradPlan()
+    L.check(L.lib().nunet_conv3x3_wgrad_plan(N, H, W, cin_total, Cout, C.byref(pl)), "nunet_conv3x3_wgrad_plan")
+    return pl
+
+
+def conv3x3_wgrad(N, H, W, sources, Cout, gz, y, k1, k2, k3, dw, part=None):
+    """dw: fp32 [Cout, Cin_real, 3, 3] (overwritten)."""
+    cin = sum(s.cpad for s in sources)
+    plan = wgrad_plan(N, H, W, cin, Cout)
+    if part is None:
+        part = torch.empty(plan.part_elems, dtype=torch.float32, device=gz.device)
+    d = L.WgradDesc()
+    d.N, d.H, d.W, d.num_src, d.Cout = N, H, W, len(sources), Cout
+    for i, s in enumerate(sources):
+        d.src[i].data = s.data.data_ptr()
+        d.src[i].scale = s.scale.data_ptr() if s.scale is not None else None
+        d.src[i].shift = s.shift.data_ptr() if s.shift is not None else None
+        d.src[i].C = s.C
+        d.src[i].kind = s.kind
+    d.gz, d.y, d.k1, d.k2, d.k3 = gz.data_ptr(), y.data_ptr(), k1.data_ptr(), k2.data_ptr(), k3.data_ptr()
+    d.part, d.dw = part.data_ptr(), dw.data_ptr()
+    L.check(L.lib().nunet_conv3x3_wgrad(C.byref(d), _stream()), "nunet_conv3x3_wgrad")
+    return dw

@@ -94,7 +94,7 @@ def loss_case(losses, metrics, seed, shape, soft):
     flat = x.view(-1)
     flat[::7] = 0.0                      # exact zeros: sigmoid(0) = 0.5 is NOT > 0.5
     flat[1::11] = 5e-8                   # below the fp32 sigmoid threshold (~8.94e-8): still False
-    flat[2::13] = 2e-7                   # above it: True
+    flat[2::13] = 1e-6                   # above it: True
     t = torch.rand(shape, generator=g)
     if not soft:
         t = (t > 0.5).float()

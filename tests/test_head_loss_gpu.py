@@ -1,0 +1,71 @@
+"""Heads, BCE+Dice loss, IoU counts: CUDA kernels vs the committed reference goldens and vs torch on the device."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["hard_1c", "soft_1c", "hard_4c"])
+def test_loss_iou_against_reference_golden(name):
+    import ops
+    g = torch.load(os.path.join(GOLD, "loss_iou.pt"))[name]
+    x, t = g["logits"].to(DEV), g["target"].to(DEV)
+    loss, sums, counts = ops.loss_iou_fwd(x, t)
+    gs = torch.tensor(1.0, device=DEV)
+    dl = ops.loss_bwd(x, t, sums, gs)
+    c2 = ops.iou_counts(x, t)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - g["loss"]) <= 2e-6 * max(1.0, abs(g["loss"]))
+    assert counts.tolist() == [g["I"], g["U"]]          # bit-exact integer counts (incl. logit == 0 -> False)
+    assert c2.tolist() == [g["I"], g["U"]]
+    assert (c2[0].item() + 1e-5) / (c2[1].item() + 1e-5) == g["iou"]
+    ref = g["dlogits"].to(DEV)
+    assert torch.allclose(dl, ref, rtol=1e-4, atol=1e-7 + 1e-5 * float(ref.abs().max()))
+
+
+def test_loss_bwd_scale_pointer_and_mul():
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(4, 1, 96, 96, generator=gen, device=DEV)
+    t = (torch.rand(4, 1, 96, 96, generator=gen, device=DEV) > 0.5).float()
+    loss, sums, counts = ops.loss_iou_fwd(x, t)
+    d1 = ops.loss_bwd(x, t, sums, torch.tensor(0.5, device=DEV), 0.25)
+    xr = x.clone().requires_grad_(True)
+    bce = F.binary_cross_entropy_with_logits(xr, t)
+    p = torch.sigmoid(xr).view(4, -1)
+    tt = t.view(4, -1)
+    dice = (2 * (p * tt).sum(1) + 1e-5) / (p.sum(1) + tt.sum(1) + 1e-5)
+    ref_loss = 0.5 * bce + 1 - dice.sum() / 4
+    ref_loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref_loss)) < 2e-6
+    assert torch.allclose(d1, xr.grad * 0.125, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("K", [1, 4])
+def test_head_fwd_and_param_grads(K):
+    import ops
+    N, H, W = 3, 16, 24
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    y = torch.randn(N, H, W, 32, generator=gen, device=DEV).to(torch.bfloat16)
+    scale = torch.randn(32, generator=gen, device=DEV)
+    shift = torch.randn(32, generator=gen, device=DEV) * 0.2
+    wh = torch.randn(K, 32, generator=gen, device=DEV) * 0.3
+    bh = torch.randn(K, generator=gen, device=DEV)
+    logits = ops.head_fwd(y, scale, shift, wh, bh, N, H, W)
+    a = torch.relu(y.float().permute(0, 3, 1, 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    ref = F.conv2d(a, wh.view(K, 32, 1, 1), bh)
+    torch.cuda.synchronize()
+    assert torch.allclose(logits, ref, rtol=1e-5, atol=1e-5)
+    dl = torch.randn(N, K, H, W, generator=gen, device=DEV)
+    dwh, dbh = ops.head_bwd_params(y, scale, shift, dl, N, H, W, K)
+    torch.cuda.synchronize()
+    rw = torch.einsum("nkhw,nchw->kc", dl, a)
+    rb = dl.sum((0, 2, 3))
+    assert torch.allclose(dwh, rw, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(dbh, rb, rtol=1e-4, atol=1e-3)
