@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
     float* s_scale = reinterpret_cast<float*>(pixtab + p.P);
     float* s_shift = s_scale + p.cin_pad;
     float* s_k2 = s_shift + p.cin_pad;
-    float* s_stat = s_k2 + p.cin_pad;  // [2][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 512);
+    float* s_stat = s_k2 + p.cin_pad;  // [8 warps][2][NT]: per-warp partials, summed in a fixed order (deterministic)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 16 * p.NT);
     uint64_t* full = bars;
     uint64_t* empty = bars + p.S;
     uint64_t* accum = bars + 2 * p.S;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             }
             cbase += cpad;
         }
-        for (int i = threadIdx.x; i < 512; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < 16 * p.NT; i += kThreads) s_stat[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -190,16 +190,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                         ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
                     }
                 }
-                atomicAdd(&s_stat[cs * 32 + lane], ssum[0]);
-                atomicAdd(&s_stat[256 + cs * 32 + lane], ssq[0]);
+                s_stat[(warp * 2 + 0) * p.NT + cs * 32 + lane] = ssum[0];  // each (warp, cs) slot is written at most once
+                s_stat[(warp * 2 + 1) * p.NT + cs * 32 + lane] = ssq[0];
             }
         }
         if (p.stat_part != nullptr) {
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
             float* dst = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n_tile * p.NT;
             for (int c = threadIdx.x; c < p.NT; c += 256) {
-                dst[c] = s_stat[c];
-                dst[p.Cout + c] = s_stat[256 + c];
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) {
+                    a += s_stat[(w8 * 2 + 0) * p.NT + c];
+                    b += s_stat[(w8 * 2 + 1) * p.NT + c];
+                }
+                dst[c] = a;
+                dst[p.Cout + c] = b;
             }
         }
     } else if (warp == 8) {
@@ -306,7 +312,7 @@ static int pick_nt(int C) {
 
 static size_t conv_smem_bytes(int T, int NT, int CK, int S, int P, int cin_pad) {
     size_t a = (size_t)(CK / 8) * P * 16, b = (size_t)9 * CK * NT * 2;
-    return S * (a + b) + (size_t)P * 8 + (size_t)cin_pad * 12 + 512 * 4 + (2 * S + 1) * 8 + 16 + 128;
+    return S * (a + b) + (size_t)P * 8 + (size_t)cin_pad * 12 + (size_t)16 * NT * 4 + (2 * S + 1) * 8 + 16 + 128;
 }
 
 extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* pl) {

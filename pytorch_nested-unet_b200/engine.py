@@ -1,0 +1,312 @@
+"""Host-side schedule of the fused UNet++ / U-Net step on one B200.
+
+`run_model(model, x)` walks the reference's node graph (finished/archs1.py:58-71 / :114-143) in its topological
+order and issues, per VGGBlock conv, ONE fused implicit-GEMM launch (ops.conv3x3: the producers' BatchNorm+ReLU, the
+2x2 max-pool / bilinear 2x upsample of the skip pathway and the channel concat all happen in its loader; train-mode
+batch statistics come out of its epilogue) followed by one tiny BN finalize launch.  Activations exist in HBM only as
+raw bf16 NHWC conv outputs.  The backward pass (an autograd.Function so that `loss.backward()` and torch.optim keep
+working on the fp32 master parameters) runs, per conv in reverse order: gradient router + BN/ReLU backward reduction,
+split-K wgrad, dgrad — all CUDA kernels behind the C ABI; nothing here calls an ATen compute op on activations.
+"""
+import torch
+
+import _lib as L
+import ops
+
+NB_FILTER = (32, 64, 128, 256, 512)
+
+
+# --------------------------------------------------------------------------------------------- graphs
+def nested_graph():
+    """[(node, [(source node | 'input', kind)])] in the execution order of NestedUNet.forward (finished/archs1.py:115-132);
+    concat order = same-level nodes in increasing j, the upsampled lower node last."""
+    g = [("0_0", [("input", "input")])]
+    for name in ("1_0", "0_1", "2_0", "1_1", "0_2", "3_0", "2_1", "1_2", "0_3", "4_0", "3_1", "2_2", "1_3", "0_4"):
+        i, j = int(name[0]), int(name[2])
+        if j == 0:
+            g.append((name, [("%d_0" % (i - 1), "pool")]))
+        else:
+            g.append((name, [("%d_%d" % (i, jj), "same") for jj in range(j)] + [("%d_%d" % (i + 1, j - 1), "up")]))
+    return g
+
+
+def unet_graph():
+    """UNet.forward (finished/archs1.py:59-68)."""
+    g = [("0_0", [("input", "input")])]
+    for i in range(1, 5):
+        g.append(("%d_0" % i, [("%d_0" % (i - 1), "pool")]))
+    for name, same, up in (("3_1", "3_0", "4_0"), ("2_2", "2_0", "3_1"), ("1_3", "1_0", "2_2"), ("0_4", "0_0", "1_3")):
+        g.append((name, [(same, "same"), (up, "up")]))
+    return g
+
+
+_KIND = {"input": L.SRC_INPUT, "same": L.SRC_SAME, "pool": L.SRC_POOL, "up": L.SRC_UP}
+
+
+class LayerSpec(object):
+    """One 3x3 conv (+ its BatchNorm) of the network."""
+    __slots__ = ("idx", "node", "which", "level", "conv", "bn", "cin_real", "cin_pad", "cout", "sources", "consumers", "head")
+
+    def __init__(self):
+        self.sources = []    # [(producer layer idx | -1, kind, C)]
+        self.consumers = []  # [(consumer layer idx, channel offset in its concatenated input, kind)]
+        self.head = None     # nn.Conv2d 1x1 reading this layer's activation
+
+
+def build_specs(model):
+    specs, node_out = [], {}
+    for node, srcs in model._graph:
+        block = getattr(model, "conv" + node)
+        level = int(node[0])
+        for which in (1, 2):
+            s = LayerSpec()
+            s.idx, s.node, s.which, s.level = len(specs), node, which, level
+            s.conv = getattr(block, "conv%d" % which)
+            s.bn = getattr(block, "bn%d" % which)
+            s.cout = s.conv.out_channels
+            s.cin_real = s.conv.in_channels
+            if which == 1:
+                for src, kind in srcs:
+                    if kind == "input":
+                        s.sources.append((-1, L.SRC_INPUT, s.cin_real))
+                    else:
+                        pi = node_out[src]
+                        s.sources.append((pi, _KIND[kind], specs[pi].cout))
+            else:
+                s.sources.append((s.idx - 1, L.SRC_SAME, specs[s.idx - 1].cout))
+            s.cin_pad = 16 if s.sources[0][1] == L.SRC_INPUT else sum(c for _, _, c in s.sources)
+            if s.sources[0][1] == L.SRC_INPUT and s.cin_real > 16:
+                raise L.NunetError("input_channels > 16 is not supported by the stem loader")
+            if s.sources[0][1] != L.SRC_INPUT and s.cin_pad != s.cin_real:
+                raise L.NunetError("channel bookkeeping mismatch in %s" % node)
+            specs.append(s)
+        node_out[node] = specs[-1].idx
+    for s in specs:
+        off = 0
+        for pi, kind, c in s.sources:
+            if pi >= 0:
+                specs[pi].consumers.append((s.idx, off, kind))
+            off += c
+    for head_name, node in model._heads:
+        specs[node_out[node]].head = getattr(model, head_name)
+    return specs
+
+
+class _State(object):
+    """Per-model engine state: layer specs, packed-weight cache, BN scratch."""
+
+    def __init__(self, model):
+        self.specs = build_specs(model)
+        self.packs = {}
+        self.ws = None
+        self.device = None
+
+    def workspace(self, device):
+        if self.ws is None or self.device != device:
+            self.ws = ops.BnWorkspace(device)
+            self.device = device
+            self.packs = {}
+        return self.ws
+
+    def pack(self, spec, plan, mode):
+        w = spec.conv.weight
+        key = (spec.idx, mode)
+        tag = (w._version, w.data_ptr(), plan.NT, plan.CK)
+        hit = self.packs.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        out = hit[1] if (hit is not None and hit[1].numel() == plan.wpack_elems and hit[1].device == w.device) else None
+        out = ops.pack_weights(w, mode, plan, out)
+        self.packs[key] = (tag, out)
+        return out
+
+
+def _state(model):
+    st = model.__dict__.get("_nunet_state")
+    if st is None:
+        st = _State(model)
+        model.__dict__["_nunet_state"] = st
+    return st
+
+
+# SyncBN / data-parallel hooks (set by dist.DataParallel): callables that all-reduce an fp64 [2,C] tensor in place.
+def _world(model):
+    return model.__dict__.get("_nunet_dp")
+
+
+class _Record(object):
+    __slots__ = ("y", "scale", "shift", "mean", "invstd", "h", "w")
+
+
+def _forward(model, x, train):
+    st = _state(model)
+    specs = st.specs
+    if x.dim() != 4:
+        raise ValueError("expected NCHW input")
+    ops.require_cuda(x, "input")
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    N, Cin, H, W = x.shape
+    if Cin != specs[0].cin_real:
+        raise ValueError("expected %d input channels, got %d" % (specs[0].cin_real, Cin))
+    if H % 16 or W % 16:
+        raise ValueError("input height/width must be multiples of 16 (four 2x2 poolings), got %dx%d" % (H, W))
+    dev = x.device
+    ws = st.workspace(dev)
+    dp = _world(model)
+    recs = []
+    for s in specs:
+        h, w = H >> s.level, W >> s.level
+        srcs = []
+        for pi, kind, c in s.sources:
+            if pi < 0:
+                srcs.append(ops.Source(kind, x, c))
+            else:
+                r = recs[pi]
+                srcs.append(ops.Source(kind, r.y, c, r.scale, r.shift))
+        plan = ops.conv_plan(N, h, w, s.cin_pad, s.cout)
+        wp = st.pack(s, plan, L.PACK_FWD)
+        y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
+        r = _Record()
+        r.y, r.h, r.w = y, h, w
+        r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        bn = s.bn
+        if train:
+            r.mean = torch.empty(s.cout, dtype=torch.float32, device=dev)
+            r.invstd = torch.empty(s.cout, dtype=torch.float32, device=dev)
+            momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+            track = bn.track_running_stats and bn.running_mean is not None
+            rm = bn.running_mean if track else None
+            rv = bn.running_var if track else None
+            count = float(N * h * w)
+            if dp is None or not dp.sync_bn:
+                ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
+                                      r.mean, r.invstd)
+            else:
+                sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
+                ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
+                                      r.mean, r.invstd, sums_out=sums, finalize=False)
+                dp.all_reduce_sum(sums)
+                ops.bn_finalize_from_sums(sums, count * dp.world_size, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps,
+                                          r.scale, r.shift, r.mean, r.invstd)
+        else:
+            r.mean = r.invstd = None
+            ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
+        recs.append(r)
+    if train:
+        nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]
+        if nbt:
+            torch._foreach_add_(nbt, 1)
+    logits = []
+    for s in specs:
+        if s.head is not None:
+            r = recs[s.idx]
+            K = s.head.out_channels
+            logits.append((s.idx, ops.head_fwd(r.y, r.scale, r.shift, s.head.weight.detach().view(K, -1), s.head.bias.detach(), N, r.h, r.w)))
+    return x, recs, logits
+
+
+def _backward(model, x, recs, grad_logits):
+    """grad_logits: {layer idx: dlogits fp32 NCHW}. Returns {id(param): grad}."""
+    st = _state(model)
+    specs = st.specs
+    N, _, H, W = x.shape
+    dev = x.device
+    ws = st.workspace(dev)
+    dp = _world(model)
+    grads, dxs = {}, {}
+    for s in reversed(specs):
+        r = recs[s.idx]
+        h, w = r.h, r.w
+        cons = [ops.Consumer(dxs[m], specs[m].cin_pad, off, kind) for (m, off, kind) in s.consumers]
+        dl = wh = None
+        if s.head is not None:
+            dl = grad_logits.get(s.idx)
+            if dl is not None:
+                K = s.head.out_channels
+                wh = s.head.weight.detach().view(K, -1)
+                dwh, dbh = ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K)
+                grads[id(s.head.weight)] = dwh.view_as(s.head.weight)
+                grads[id(s.head.bias)] = dbh
+        if not cons and dl is None:
+            dl = torch.zeros((N, 1, h, w), dtype=torch.float32, device=dev)
+            wh = torch.zeros((1, s.cout), dtype=torch.float32, device=dev)
+        gz, rpart = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh)
+        dgamma = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
+        count = float(N * h * w)
+        if dp is None or not dp.sync_bn:
+            ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, ws, dgamma, dbeta, k1, k2, k3)
+        else:
+            sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
+            ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, ws, dgamma, dbeta, k1, k2, k3, sums_out=sums, finalize=False)
+            dp.all_reduce_sum(sums)
+            ops.bn_backward_from_sums(sums, count * dp.world_size, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3)
+            # dgamma / dbeta now hold GLOBAL sums; the gradient all-reduce averages, so pre-divide to keep them global
+            dp.mark_global(dgamma, dbeta)
+        grads[id(s.bn.weight)] = dgamma
+        grads[id(s.bn.bias)] = dbeta
+        srcs = []
+        for pi, kind, c in s.sources:
+            if pi < 0:
+                srcs.append(ops.Source(kind, x, c))
+            else:
+                pr = recs[pi]
+                srcs.append(ops.Source(kind, pr.y, c, pr.scale, pr.shift))
+        dw = torch.empty_like(s.conv.weight, dtype=torch.float32)
+        ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gz, r.y, k1, k2, k3, dw)
+        grads[id(s.conv.weight)] = dw
+        if s.conv.bias is not None:
+            # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
+            grads[id(s.conv.bias)] = torch.zeros_like(s.conv.bias)
+        if s.sources[0][0] >= 0:
+            plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
+            wpd = st.pack(s, plan, L.PACK_DGRAD)
+            gsrc = ops.Source(L.SRC_GRAD, gz, s.cout, k1, k3, data2=r.y, k2=k2)
+            dxs[s.idx], _ = ops.conv3x3(N, h, w, [gsrc], s.cin_pad, wpd)
+        for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
+            if specs[m].sources[0][0] == s.idx:
+                dxs.pop(m, None)
+    return grads
+
+
+class _NetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        x, recs, logits = _forward(model, x, True)
+        ctx.model, ctx.x, ctx.recs = model, x, recs
+        ctx.head_layers = [i for i, _ in logits]
+        ctx.params = params
+        return tuple(t for _, t in logits)
+
+    @staticmethod
+    def backward(ctx, *grad_logits):
+        gl = {}
+        for i, g in zip(ctx.head_layers, grad_logits):
+            if g is not None:
+                gl[i] = g.contiguous().float()
+        grads = _backward(ctx.model, ctx.x, ctx.recs, gl)
+        ctx.recs = None
+        out = []
+        for p in ctx.params:
+            g = grads.get(id(p)) if p.requires_grad else None
+            out.append(g)
+        return (None, None) + tuple(out)
+
+
+def run_model(model, x):
+    """model(input) of the reference (trains.py:117-125, val.py:92-95)."""
+    L.lib()  # fail loudly if the CUDA library is missing
+    params = [p for p in model.parameters()]
+    need_grad = model.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if need_grad:
+        outs = _NetFunction.apply(model, x, *params)
+    else:
+        with torch.no_grad():
+            _, _, logits = _forward(model, x, model.training)
+        outs = tuple(t for _, t in logits)
+    if model._returns_list:
+        return list(outs)
+    return outs[0]

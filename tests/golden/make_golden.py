@@ -112,7 +112,7 @@ def main():
     out = {}
     out["nested_ds_n2_32"] = train_case(archs, losses, metrics, "NestedUNet", 1, True, 2, 32, 32, "normal")
     out["nested_wods_n2_32_dsb"] = train_case(archs, losses, metrics, "NestedUNet", 1, False, 2, 32, 32, "dsb")
-    out["unet_n2_32"] = train_case(archs, losses, metrics, "UNet", 1, False, 2, 32, 32, "normal")
+    out["unet_n4_64"] = train_case(archs, losses, metrics, "UNet", 1, False, 4, 64, 64, "normal")
     out["nested_ds_c4_n2_32"] = train_case(archs, losses, metrics, "NestedUNet", 4, True, 2, 32, 32, "normal")
     out["nested_wods_n4_96"] = train_case(archs, losses, metrics, "NestedUNet", 1, False, 4, 96, 96, "normal")
     out["nested_ds_n3_48x80"] = train_case(archs, losses, metrics, "NestedUNet", 1, True, 3, 48, 80, "normal", weight_seed=3, data_seed=7)

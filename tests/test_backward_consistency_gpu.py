@@ -1,0 +1,112 @@
+"""Backward-pass correctness with the forward held fixed ("teacher forcing").
+
+Comparing the gradients of a bf16 forward with those of an fp32 forward at random init is dominated by ReLU gates and
+max-pool winners that flip where |pre-activation| ~ rounding error (a few % of pixels per layer, each an O(1) change of
+that pixel's gradient; ~0.15 rel-L2 per layer, ~0.5 after 15 blocks — measured in tools/diag_grads.py), which says
+nothing about the backward kernels.  Here a torch fp32 autograd graph of the SAME network is evaluated with every raw
+conv output replaced (straight-through) by the value the CUDA engine produced, so both backward passes see identical
+gates / winners / statistics inputs, and the gradients must agree to bf16-operand accuracy."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ste_bf16(t):
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def _torch_forced_forward(model, x, recs):
+    import engine
+    import _lib as L
+    specs = engine._state(model).specs
+    acts = {}
+    for s in specs:
+        parts = []
+        for pi, kind, c in s.sources:
+            if pi < 0:
+                parts.append(x)
+                continue
+            a = acts[pi]
+            if kind == L.SRC_POOL:
+                a = F.max_pool2d(a, 2, 2)
+            elif kind == L.SRC_UP:
+                a = F.interpolate(a, scale_factor=2, mode="bilinear", align_corners=True)
+            parts.append(a)
+        X = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
+        y = F.conv2d(_ste_bf16(X), _ste_bf16(s.conv.weight), s.conv.bias, padding=1)
+        y_eng = recs[s.idx].y.float().permute(0, 3, 1, 2) + s.conv.bias.detach().view(1, -1, 1, 1)
+        y = y + (y_eng - y).detach()
+        z = F.batch_norm(y, None, None, s.bn.weight, s.bn.bias, True, 0.0, s.bn.eps)
+        acts[s.idx] = torch.relu(z)
+    outs = []
+    for s in specs:
+        if s.head is not None:
+            outs.append(F.conv2d(acts[s.idx], s.head.weight, s.head.bias))
+    return outs
+
+
+@pytest.mark.parametrize("arch,ds,K,n,h,w", [("NestedUNet", True, 1, 2, 32, 32), ("NestedUNet", False, 1, 3, 48, 80),
+                                              ("UNet", False, 1, 2, 32, 32), ("NestedUNet", True, 3, 4, 96, 96)])
+def test_backward_matches_autograd_with_forced_forward(arch, ds, K, n, h, w):
+    import archs
+    import engine
+    import losses
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = getattr(archs, arch)(K, 3, ds).to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(n, 3, h, w, generator=gen, device=DEV)
+    t = (torch.rand(n, K, h, w, generator=gen, device=DEV) > 0.5).float()
+    crit = losses.BCEDiceLoss()
+    model.train()
+    # engine step (keep the raw conv outputs of THIS forward)
+    keep = {}
+    orig_forward = engine._forward
+
+    def _capturing_forward(m, xx, tr):
+        res = orig_forward(m, xx, tr)
+        keep["recs"] = res[1]
+        return res
+
+    engine._forward = _capturing_forward
+    try:
+        out = model(x)
+    finally:
+        engine._forward = orig_forward
+    outs = out if isinstance(out, list) else [out]
+    loss = sum(crit(o, t) for o in outs) / len(outs)
+    loss.backward()
+    got = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    # torch autograd on the forced forward
+    recs = keep["recs"]
+    routs = _torch_forced_forward(model, x, recs)
+
+    def ref_loss(o):
+        bce = F.binary_cross_entropy_with_logits(o, t)
+        p = torch.sigmoid(o).view(n, -1)
+        tt = t.view(n, -1)
+        dice = (2 * (p * tt).sum(1) + 1e-5) / (p.sum(1) + tt.sum(1) + 1e-5)
+        return 0.5 * bce + 1 - dice.sum() / n
+
+    rloss = sum(ref_loss(o) for o in routs) / len(routs)
+    rloss.backward()
+    assert abs(float(loss.detach()) - float(rloss.detach())) < 2e-4
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        r = p.grad
+        if k.endswith("conv1.bias") or k.endswith("conv2.bias"):
+            assert float(got[k].abs().max()) == 0.0 and float(r.abs().max()) < 1e-6
+            continue
+        rel = float((got[k] - r).norm() / (r.norm() + 1e-20))
+        if rel > worst[1]:
+            worst = (k, rel)
+        import os
+        if os.environ.get("NUNET_VERBOSE"):
+            print("%-24s rel %.3e ratio %.3f" % (k, rel, float(got[k].norm() / (r.norm() + 1e-20))))
+    print(arch, ds, "worst grad rel-L2 vs forced-forward autograd: %s %.3e" % worst)
+    assert worst[1] <= 6e-2, worst
