@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — NestedUNet (deep supervision) train images/sec @96x96 bf16 on N B200s (BASELINE.json metric, config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B] [--size S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one full iteration of the reference's training loop body (trains.py:113-136): forward, BCEDice loss (mean
+over the four deep-supervision heads), iou_score on the last head, zero_grad, backward, SGD(momentum, weight decay)
+step.  `value` times it with the batch already resident in HBM; `e2e` includes the pinned-host -> device copy of
+every step's batch and the device -> host read of loss and IoU.  `--impl reference` times the reference's CPU path
+(the oracle port of it; /root/reference does not exist on the GPU box) on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pytorch_nested-unet_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "NestedUNet(deep_supervision) train images/sec @96x96"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--size", type=int, default=96)
+    ap.add_argument("--arch", default="NestedUNet")
+    ap.add_argument("--no-ds", action="store_true")
+    ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-layers", action="store_true", help="also write profiles/layers_latest.json")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "tc_burst": float(p["bf16_tflops"]), "tc_sustained": float(p["bf16_tflops_sustained"]),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm": 6650.0, "tc_burst": 1590.0, "tc_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic work
+def conv_flops_per_image(arch, size, input_channels=3):
+    """2*M*Cout*9*Cin per conv; train = 3x forward except 2x for the stem conv (no dgrad). SURVEY.md 8d."""
+    import engine
+    graph = engine.nested_graph() if arch == "NestedUNet" else engine.unet_graph()
+    nb = engine.NB_FILTER
+    fwd = train = 0.0
+    for node, srcs in graph:
+        lvl = int(node[0])
+        m = (size >> lvl) ** 2
+        cout = nb[lvl]
+        cin = 0
+        for s, kind in srcs:
+            cin += input_channels if kind == "input" else nb[int(s[0])]
+        f1 = 2.0 * m * cout * 9 * cin
+        f2 = 2.0 * m * cout * 9 * cout
+        fwd += f1 + f2
+        train += (2 * f1 if srcs[0][1] == "input" else 3 * f1) + 3 * f2
+    return fwd, train
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_step_rate(arch, ds, n, size, steps, warmup):
+    """Times the oracle port of the reference's train step (trains.py:113-136) on the host cores."""
+    from oracle import nunet_oracle as O
+    import archs
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = getattr(archs, arch)(1, 3, ds)          # parameter container only (CPU): same init as the reference
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x, t = O.synthetic_batch(n, size, size, 1, 3, 1, "dsb")
+    bufs = {}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        sd, loss, iou, _, _ = O.train_step(sd, x, t, arch, ds, bufs=bufs)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return n / med, med, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 16
+    steps = max(1, min(args.steps, 5))
+    warm = 1
+    ds = not args.no_ds
+    rate, med, cores = cpu_reference_step_rate(args.arch, ds, n, args.size, steps, warm)
+    sample = "oracle port of trains.py:113-136, %s ds=%s, batch %d @%dx%d fp32 on CPU, median of %d steps after %d warm-up" % (
+        args.arch, ds, n, args.size, args.size, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+        "data": "synthetic", "config": {"workload": "NestedUNet-DS 96x96 train step (BASELINE config 2 shape), CPU sample batch %d" % n},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import archs
+    import losses
+    import metrics
+    import ops
+    ds = not args.no_ds
+    torch.manual_seed(0)
+    model = getattr(archs, args.arch)(1, 3, ds).to(dev)
+    crit = losses.BCEDiceLoss().to(dev)
+    if world > 1:
+        import dist as nunet_dist
+        model = nunet_dist.DataParallel(model, sync_bn=not args.no_sync_bn)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    B, S = args.batch, args.size
+    IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)  # albumentations Normalize(), trains.py:266
+    g = torch.Generator().manual_seed(1 + rank)
+    u8 = torch.randint(0, 256, (B, 3, S, S), generator=g).float()
+    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    x_host = (((u8 / 255.0 - mean) / std) / 255.0).pin_memory()
+    t_host = (torch.rand(B, 1, S, S, generator=g) > 0.5).float().pin_memory()
+    x_dev, t_dev = x_host.to(dev), t_host.to(dev)
+
+    def step(x, t):
+        outputs = model(x)
+        if isinstance(outputs, list):
+            loss = 0
+            for o in outputs:
+                loss = loss + crit(o, t)
+            loss = loss / len(outputs)
+            last = outputs[-1]
+        else:
+            loss = crit(outputs, t)
+            last = outputs
+        counts = metrics_counts(last, t)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss, counts
+
+    def metrics_counts(last, t):
+        # device-side integer counts (metrics.iou_score without the host read, which the e2e loop does explicitly)
+        cached = last.__dict__.get("_nunet_iou")
+        return cached[3] if cached is not None else ops.iou_counts(last.detach(), t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model.train()
+    for _ in range(args.warmup):
+        step(x_dev, t_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, counts = step(x_dev, t_dev)
+    e1.record()
+    barrier()
+    launches = ops.launch_count()
+    ms = e0.elapsed_time(e1)
+    # ---- end-to-end: pinned host batch -> device every step, loss + IoU read back every step
+    for _ in range(2):
+        step(x_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        xb = x_host.to(dev, non_blocking=True)
+        tb = t_host.to(dev, non_blocking=True)
+        loss, counts = step(xb, tb)
+        lv = loss.item()
+        i_, u_ = counts.tolist()
+        iou = (i_ + 1e-5) / (u_ + 1e-5)
+    f1.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_e2e = f0.elapsed_time(f1)
+    tm = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tm.tolist()
+    imgs = B * world * args.steps
+    value = imgs / (ms * 1e-3)
+    e2e = imgs / (ms_e2e * 1e-3)
+    # ---- roofline of the dominant kernel class (implicit-GEMM conv: forward + dgrad + wgrad launches), timed per launch
+    pk = peaks()
+    raw = model.module if hasattr(model, "module") else model
+    roof = None
+    layer_rows = []
+    if rank == 0:
+        ops.enable_kernel_timing(True)
+        step(x_dev, t_dev)
+        torch.cuda.synchronize()
+        timing = ops.collect_kernel_timing()
+        ops.enable_kernel_timing(False)
+        conv_ms = sum(v for k, v in timing["by_class"].items() if k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
+        total_ms = sum(timing["by_class"].values())
+        _, train_fl = conv_flops_per_image(args.arch, S)
+        tflops = train_fl * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tflops / pk["tc_sustained"],
+                "traffic": None, "kernel": "conv3x3_igemm_kernel + conv3x3_wgrad_kernel (all 89 conv launches of one step)",
+                "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "kernel_ms_per_step": conv_ms, "all_kernels_ms_per_step": total_ms,
+                "class_ms": {k: round(v, 4) for k, v in sorted(timing["by_class"].items())}}
+        layer_rows = timing["launches"]
+        if args.profile_layers:
+            os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+            with open(os.path.join(ROOT, "profiles", "layers_latest.json"), "w") as f:
+                json.dump({"batch": B, "size": S, "arch": args.arch, "launches": layer_rows}, f, indent=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, med, cores = cpu_reference_step_rate(args.arch, ds, 16, S, 3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle port of the reference train step, %s ds=%s batch 16 @%dx%d fp32, median of 3 steps (%.2f s/step)" % (args.arch, ds, S, S, med)}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "%s(num_classes=1, input_channels=3, deep_supervision=%s) %dx%d, batch %d per GPU, full train step "
+                                   "(fwd + BCEDice + IoU + bwd + SGD)" % (args.arch, ds, S, S, B),
+                       "global_batch": B * world, "parallelism": "dp%d%s" % (world, "" if world == 1 else ("+syncbn" if not args.no_sync_bn else "")),
+                       "l2": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4) * world,
+                    "d2h_bytes_per_step": (4 + 16) * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "last_loss": float(lv), "last_iou": float(iou),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

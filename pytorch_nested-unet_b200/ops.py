@@ -18,6 +18,51 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---------------------------------------------------------------------------------------------- launch accounting
+_LAUNCHES = 0
+_TIMING = None  # list of (class, meta, start_event, end_event) while enabled
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def launch_count():
+    """Number of CUDA kernels of this library launched since reset_launch_count()."""
+    return _LAUNCHES
+
+
+def enable_kernel_timing(on):
+    """Per-launch CUDA-event timing on the launching (current) stream; used by bench.py for the roofline figures."""
+    global _TIMING
+    _TIMING = [] if on else None
+
+
+def collect_kernel_timing():
+    torch.cuda.synchronize()
+    by_class, launches = {}, []
+    for cls, meta, e0, e1 in (_TIMING or []):
+        ms = e0.elapsed_time(e1)
+        by_class[cls] = by_class.get(cls, 0.0) + ms
+        launches.append({"class": cls, "meta": meta, "ms": ms})
+    return {"by_class": by_class, "launches": launches}
+
+
+def _call(cls, nkernels, meta, what, fn, *args):
+    global _LAUNCHES
+    if _TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _TIMING.append((cls, meta, e0, e1))
+    else:
+        rc = fn(*args)
+    L.check(rc, what)
+    _LAUNCHES += nkernels
+
+
 def require_cuda(t, what):
     if not t.is_cuda:
         raise L.NunetError("%s must be a CUDA tensor: the B200 path has no CPU fallback" % what)
@@ -50,7 +95,7 @@ def pack_weights(w_oihw, mode, plan, out=None):
         w = w.float().contiguous()
     if out is None:
         out = torch.empty(plan.wpack_elems, dtype=torch.bfloat16, device=w.device)
-    L.check(L.lib().nunet_pack_weights(_ptr(w), w.shape[0], w.shape[1], mode, C.byref(plan), _ptr(out), _stream()), "nunet_pack_weights")
+    _call("pack", 1, None, "nunet_pack_weights", L.lib().nunet_pack_weights, _ptr(w), w.shape[0], w.shape[1], mode, C.byref(plan), _ptr(out), _stream())
     return out
 
 
@@ -76,7 +121,8 @@ def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=
     d.wpack = wpack.data_ptr()
     d.out = out.data_ptr()
     d.stat_part = stat_part.data_ptr() if stat_part is not None else None
-    L.check(L.lib().nunet_conv3x3_fwd(C.byref(d), _stream()), "nunet_conv3x3_fwd")
+    cls = "conv_dgrad" if sources[0].kind == L.SRC_GRAD else "conv_fwd"
+    _call(cls, 1, (N, H, W, cin, Cout), "nunet_conv3x3_fwd", L.lib().nunet_conv3x3_fwd, C.byref(d), _stream())
     return out, stat_part
 
 
@@ -91,23 +137,23 @@ class BnWorkspace(object):
 def bn_finalize_train(stat_part, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, ws,
                       scale, shift, save_mean, save_invstd, sums_out=None, finalize=True):
     rows, _, Cc = stat_part.shape
-    L.check(L.lib().nunet_bn_finalize_train(
+    _call("bn_finalize", 1, None, "nunet_bn_finalize_train", L.lib().nunet_bn_finalize_train, 
         _ptr(stat_part), rows, Cc, float(count), _ptr(gamma if finalize else None), _ptr(beta), _ptr(conv_bias),
         _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), _ptr(scale), _ptr(shift), _ptr(save_mean),
-        _ptr(save_invstd), _ptr(ws.scratch), _ptr(ws.counters), _ptr(sums_out), _stream()), "nunet_bn_finalize_train")
+        _ptr(save_invstd), _ptr(ws.scratch), _ptr(ws.counters), _ptr(sums_out), _stream())
 
 
 def bn_finalize_from_sums(sums, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift,
                           save_mean, save_invstd):
-    L.check(L.lib().nunet_bn_finalize_from_sums(
+    _call("bn_finalize", 1, None, "nunet_bn_finalize_from_sums", L.lib().nunet_bn_finalize_from_sums, 
         _ptr(sums), gamma.numel(), float(count), _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
         _ptr(running_var), float(momentum), float(eps), _ptr(scale), _ptr(shift), _ptr(save_mean), _ptr(save_invstd),
-        _stream()), "nunet_bn_finalize_from_sums")
+        _stream())
 
 
 def bn_fold_eval(gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift):
-    L.check(L.lib().nunet_bn_fold_eval(gamma.numel(), _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
-                                       _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), _stream()), "nunet_bn_fold_eval")
+    _call("bn_fold", 1, None, "nunet_bn_fold_eval", L.lib().nunet_bn_fold_eval, gamma.numel(), _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
+                                       _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ heads / loss / metric
@@ -115,7 +161,7 @@ def head_fwd(y, scale, shift, wh, bh, N, H, W, logits=None):
     K = wh.shape[0]
     if logits is None:
         logits = torch.empty((N, K, H, W), dtype=torch.float32, device=y.device)
-    L.check(L.lib().nunet_head_fwd(_ptr(y), _ptr(scale), _ptr(shift), _ptr(wh), _ptr(bh), N, H, W, K, _ptr(logits), _stream()), "nunet_head_fwd")
+    _call("head_fwd", 1, None, "nunet_head_fwd", L.lib().nunet_head_fwd, _ptr(y), _ptr(scale), _ptr(shift), _ptr(wh), _ptr(bh), N, H, W, K, _ptr(logits), _stream())
     return logits
 
 
@@ -130,14 +176,14 @@ def loss_iou_fwd(logits, target, want_counts=True):
     sums = torch.empty((N, 3), dtype=torch.float64, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     counts = torch.empty(2, dtype=torch.int64, device=dev) if want_counts else None
-    L.check(L.lib().nunet_loss_iou_fwd(_ptr(logits), _ptr(target), N, E, _ptr(part), _ptr(cnt), _ptr(sums), _ptr(loss), _ptr(counts),
-                                       _stream()), "nunet_loss_iou_fwd")
+    _call("loss_fwd", 2, None, "nunet_loss_iou_fwd", L.lib().nunet_loss_iou_fwd, _ptr(logits), _ptr(target), N, E, _ptr(part), _ptr(cnt), _ptr(sums), _ptr(loss), _ptr(counts),
+                                       _stream())
     return loss, sums, counts
 
 
 def iou_counts(logits, target):
     counts = torch.empty(2, dtype=torch.int64, device=logits.device)
-    L.check(L.lib().nunet_iou_counts(_ptr(logits), _ptr(target), logits.numel(), _ptr(counts), _stream()), "nunet_iou_counts")
+    _call("iou", 1, None, "nunet_iou_counts", L.lib().nunet_iou_counts, _ptr(logits), _ptr(target), logits.numel(), _ptr(counts), _stream())
     return counts
 
 
@@ -146,7 +192,7 @@ def loss_bwd(logits, target, sums, gscale, gmul=1.0, dlogits=None):
     E = logits.numel() // N
     if dlogits is None:
         dlogits = torch.empty_like(logits)
-    L.check(L.lib().nunet_loss_bwd(_ptr(logits), _ptr(target), _ptr(sums), _ptr(gscale), float(gmul), N, E, _ptr(dlogits), _stream()), "nunet_loss_bwd")
+    _call("loss_bwd", 1, None, "nunet_loss_bwd", L.lib().nunet_loss_bwd, _ptr(logits), _ptr(target), _ptr(sums), _ptr(gscale), float(gmul), N, E, _ptr(dlogits), _stream())
     return dlogits
 
 
@@ -156,8 +202,8 @@ def head_bwd_params(y, scale, shift, dlogits, N, H, W, K):
     part = torch.empty((rows, K, 33), dtype=torch.float32, device=dev)
     dwh = torch.empty((K, 32), dtype=torch.float32, device=dev)
     dbh = torch.empty((K,), dtype=torch.float32, device=dev)
-    L.check(L.lib().nunet_head_bwd_params(_ptr(y), _ptr(scale), _ptr(shift), _ptr(dlogits), N, H, W, K, _ptr(part), _ptr(dwh), _ptr(dbh), 0,
-                                          _stream()), "nunet_head_bwd_params")
+    _call("head_bwd", 2, None, "nunet_head_bwd_params", L.lib().nunet_head_bwd_params, _ptr(y), _ptr(scale), _ptr(shift), _ptr(dlogits), N, H, W, K, _ptr(part), _ptr(dwh), _ptr(dbh), 0,
+                                          _stream())
     return dwh, dbh
 
 
@@ -185,20 +231,20 @@ def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, 
     if dlogits is not None:
         d.dlogits, d.wh, d.K = dlogits.data_ptr(), wh.data_ptr(), wh.shape[0]
     d.gz, d.part = gz.data_ptr(), part.data_ptr()
-    L.check(L.lib().nunet_grad_router(C.byref(d), _stream()), "nunet_grad_router")
+    _call("router", 1, (N, H, W, Cc, len(consumers)), "nunet_grad_router", L.lib().nunet_grad_router, C.byref(d), _stream())
     return gz, part
 
 
 def bn_backward_reduce(part, count, gamma, mean, invstd, ws, dgamma, dbeta, k1, k2, k3, sums_out=None, finalize=True):
     rows, _, Cc = part.shape
-    L.check(L.lib().nunet_bn_backward_reduce(_ptr(part), rows, Cc, float(count), _ptr(gamma if finalize else None), _ptr(mean), _ptr(invstd),
+    _call("bn_bwd", 1, None, "nunet_bn_backward_reduce", L.lib().nunet_bn_backward_reduce, _ptr(part), rows, Cc, float(count), _ptr(gamma if finalize else None), _ptr(mean), _ptr(invstd),
                                              _ptr(dgamma), _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), _ptr(ws.scratch), _ptr(ws.counters),
-                                             _ptr(sums_out), _stream()), "nunet_bn_backward_reduce")
+                                             _ptr(sums_out), _stream())
 
 
 def bn_backward_from_sums(sums, count, gamma, mean, invstd, dgamma, dbeta, k1, k2, k3):
-    L.check(L.lib().nunet_bn_backward_from_sums(_ptr(sums), gamma.numel(), float(count), _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(dgamma),
-                                                _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), _stream()), "nunet_bn_backward_from_sums")
+    _call("bn_bwd", 1, None, "nunet_bn_backward_from_sums", L.lib().nunet_bn_backward_from_sums, _ptr(sums), gamma.numel(), float(count), _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(dgamma),
+                                                _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), _stream())
 
 
 @functools.lru_cache(maxsize=None)
@@ -224,5 +270,5 @@ def conv3x3_wgrad(N, H, W, sources, Cout, gz, y, k1, k2, k3, dw, part=None):
         d.src[i].kind = s.kind
     d.gz, d.y, d.k1, d.k2, d.k3 = gz.data_ptr(), y.data_ptr(), k1.data_ptr(), k2.data_ptr(), k3.data_ptr()
     d.part, d.dw = part.data_ptr(), dw.data_ptr()
-    L.check(L.lib().nunet_conv3x3_wgrad(C.byref(d), _stream()), "nunet_conv3x3_wgrad")
+    _call("conv_wgrad", 2, (N, H, W, cin, Cout), "nunet_conv3x3_wgrad", L.lib().nunet_conv3x3_wgrad, C.byref(d), _stream())
     return dw
