@@ -59,8 +59,8 @@ typedef struct {
 
 typedef struct {
     int32_t T, NT, CK, S, P; /* M-tiles per CTA, N tile, channels per K chunk, pipeline stages, staged positions */
-    int32_t nchunks, n_tiles, grid_m, cin_pad;
-    int32_t smem_bytes, tmem_cols;
+    int32_t nchunks, n_tiles, grid_m, cin_pad; /* grid_m = CTAs along x = rows of stat_part (persistent kernel) */
+    int32_t smem_bytes, tmem_cols, ntg;       /* ntg = tile groups of 128*T positions */
     int64_t wpack_elems; /* bf16 elements the packed weights occupy */
 } nunet_conv_plan_t;
 

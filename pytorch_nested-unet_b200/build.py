@@ -34,6 +34,9 @@ def needs_build():
 
 
 def build(force=False, verbose=True):
+    extra = os.environ.get("NUNET_NVCC_EXTRA", "").split()
+    if extra:
+        force = True
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, "build")
@@ -42,7 +45,7 @@ def build(force=False, verbose=True):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        procs.append((src, subprocess.Popen([_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
+        procs.append((src, subprocess.Popen([_nvcc()] + NVCC_FLAGS + extra + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
                                             stderr=subprocess.STDOUT)))
     for src, p in procs:
         out, _ = p.communicate()
@@ -50,7 +53,7 @@ def build(force=False, verbose=True):
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out.decode()))
         if verbose and out.strip():
             print(out.decode())
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs)
+    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs)
     return LIB
 
 

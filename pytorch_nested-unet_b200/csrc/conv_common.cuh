@@ -19,7 +19,7 @@ struct ConvParams {
     int N, H, W;
     int Wp, Hp1;  // W+2, H+1
     int Q;        // padded positions: (N*(H+1)+1)*(W+2)
-    int T, NT, CK, S, P, nchunks, cin_pad, Cout, num_src, tmem_cols;
+    int T, NT, CK, S, P, nchunks, cin_pad, Cout, num_src, tmem_cols, ntg;
     ConvSrc src[NUNET_MAX_SRC];
     const void* wpack;
     void* out;

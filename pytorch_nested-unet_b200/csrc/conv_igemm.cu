@@ -23,9 +23,15 @@
 namespace nunet {
 
 // ------------------------------------------------------------------------------------------------ kernel
-constexpr int kProducerWarps = 8;
-constexpr int kThreads = 320;
+constexpr int kProducerWarps = 8;                 // warps 0-7 : stage the transformed input halo
+constexpr int kEpilogueWarp0 = 8;                 // warps 8-11: TMEM -> bf16 NHWC + BN statistics (warp % 4 = TMEM lane quadrant)
+constexpr int kMmaWarp = 12;                      // warp 12   : tcgen05.mma issuer (one lane) + TMEM owner
+constexpr int kFetchWarp = 13;                    // warp 13   : weight fetcher (cp.async.bulk, one lane)
+constexpr int kThreads = 14 * 32;
 
+// Persistent: CTA (x, n_tile) processes tile groups x, x+gridDim.x, ... of 128*T positions each.  Accumulators and the
+// position table are double-buffered so the producers / tensor core work on group i+1 while the epilogue drains group i.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -35,29 +41,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
 
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)p.S * a_bytes;
-    PixInfo* pixtab = reinterpret_cast<PixInfo*>(sB + (size_t)p.S * b_bytes);
-    float* s_scale = reinterpret_cast<float*>(pixtab + p.P);
+    PixInfo* pixtab = reinterpret_cast<PixInfo*>(sB + (size_t)p.S * b_bytes);  // [2][P]
+    float* s_scale = reinterpret_cast<float*>(pixtab + 2 * p.P);
     float* s_shift = s_scale + p.cin_pad;
     float* s_k2 = s_shift + p.cin_pad;
-    float* s_stat = s_k2 + p.cin_pad;  // [8 warps][2][NT]: per-warp partials, summed in a fixed order (deterministic)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 16 * p.NT);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + p.S;
-    uint64_t* accum = bars + 2 * p.S;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * p.S + 1);
+    float* s_stat = s_k2 + p.cin_pad;  // [4 quadrant warps][2][NT], each slot owned by one thread (deterministic)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 8 * p.NT);
+    uint64_t* full = bars;                 // [S]  producers + fetcher -> MMA
+    uint64_t* empty = bars + p.S;          // [S]  MMA -> producers + fetcher
+    uint64_t* acc_full = bars + 2 * p.S;   // [2]  MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;    // [2]  epilogue -> MMA + producers (accumulator AND table buffer are free)
+    uint64_t* tab_full = acc_empty + 2;    // [2]  producers -> epilogue (position table of the group is written)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tab_full + 2);
 
-    const int q0 = blockIdx.x * (128 * p.T);
-    const int qbase = q0 - p.Wp - 1;
     const int n_tile = blockIdx.y;
+    const int group_positions = 128 * p.T;
 
     // ---- one-time setup
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int s = 0; s < p.S; ++s) {
                 mbar_init(&full[s], kProducerWarps + 1);
                 mbar_init(&empty[s], 1);
             }
-            mbar_init(accum, 1);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&acc_full[b], 1);
+                mbar_init(&acc_empty[b], 4);
+                mbar_init(&tab_full[b], kProducerWarps);
+            }
             mbar_init_fence();
         }
         __syncwarp();
@@ -68,10 +79,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             case 256: tmem_alloc<256>(tmem_ptr); break;
             default: tmem_alloc<512>(tmem_ptr); break;
         }
-    }
-    for (int i = threadIdx.x; i < p.P; i += kThreads) {
-        const PixInfo pi = decode_position((long long)qbase + i, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q);
-        pixtab[i] = pi;
     }
     {
         int cbase = 0;
@@ -86,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             }
             cbase += cpad;
         }
-        for (int i = threadIdx.x; i < 16 * p.NT; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < 8 * p.NT; i += kThreads) s_stat[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -94,161 +101,200 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp < kProducerWarps) {
-        // =============================== producers: stage the transformed input halo, chunk by chunk
-        const int ppi = 8 * (4 / cgs);  // positions per warp iteration: 8 (CK=32) or 16 (CK=16)
-        const int nblk = (p.P + ppi - 1) / ppi;
+        // =============================== producers
+        const int nblk = (p.P + 7) >> 3;
         const int pl = lane & 7, r = lane >> 3;
-        const int cg = r % cgs, psub = pl + 8 * (r / cgs);
-        int si = 0, src_c0 = 0;  // current source and its first concatenated channel
-        for (int chunk = 0; chunk < p.nchunks; ++chunk) {
-            const int s = chunk % p.S;
-            const uint32_t ph = (chunk / p.S) & 1;
-            const int cglob = chunk * p.CK;  // first concatenated channel of this chunk
-            while (true) {
-                const int cpad = (p.src[si].kind == NUNET_SRC_INPUT) ? 16 : p.src[si].C;
-                if (cglob < src_c0 + cpad) break;
-                src_c0 += cpad;
-                ++si;
-            }
-            const ConvSrc& src = p.src[si];
-            const int ch = cglob - src_c0 + cg * 8;  // channel inside the source
-            float sc[8], sh[8], k2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                sc[i] = s_scale[cglob + cg * 8 + i];
-                sh[i] = s_shift[cglob + cg * 8 + i];
-                k2[i] = s_k2[cglob + cg * 8 + i];
-            }
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* dstA = sA + (size_t)s * a_bytes + (size_t)cg * p.P * 16;
-            for (int blk = warp; blk < nblk; blk += kProducerWarps) {
-                const int pp = blk * ppi + psub;
-                if (pp < p.P) {
-                    const PixInfo pi = pixtab[pp];
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (pi.pix >= 0) v = load_transform(src, p.H, p.W, pi, ch, sc, sh, k2);
-                    *reinterpret_cast<uint4*>(dstA + (size_t)pp * 16) = v;
+        // CK=32: the four lane groups of a warp take the four channel groups of one 8-position block;
+        // CK=16: two channel groups, the lane-group pairs take two different blocks
+        const int cg = r % cgs;
+        const int first_blk = (cgs == 4) ? warp : (warp * 2 + (r >> 1));
+        const int blk_stride = (cgs == 4) ? kProducerWarps : 2 * kProducerWarps;
+        int cc = 0;  // running chunk counter across tile groups
+        int it = 0;
+        for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t k = (uint32_t)(it >> 1);
+            PixInfo* tab = pixtab + (size_t)b * p.P;
+            const int qbase = tg * group_positions - p.Wp - 1;
+            mbar_wait(&acc_empty[b], (k & 1) ^ 1);  // the epilogue of group it-2 no longer reads table b
+            for (int i = threadIdx.x; i < p.P; i += kProducerWarps * 32) tab[i] = decode_position(qbase + i, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (lane == 0) mbar_arrive(&tab_full[b]);
+            int si = 0, src_c0 = 0;  // current source and its first concatenated channel
+            for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
+                const int s = cc % p.S;
+                const uint32_t ph = (uint32_t)(cc / p.S) & 1;
+                const int cglob = chunk * p.CK;  // first concatenated channel of this chunk
+                while (true) {
+                    const int cpad = (p.src[si].kind == NUNET_SRC_INPUT) ? 16 : p.src[si].C;
+                    if (cglob < src_c0 + cpad) break;
+                    src_c0 += cpad;
+                    ++si;
                 }
+                const int ch = cglob - src_c0 + cg * 8;  // channel inside the source
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* dstA = sA + (size_t)s * a_bytes + (size_t)cg * p.P * 16;
+                stage_blocks_mode<MODE>(p.src[si], p.H, p.W, tab, 0, p.P, first_blk, nblk, blk_stride, pl, ch, s_scale + cglob + cg * 8,
+                                      s_shift + cglob + cg * 8, s_k2 + cglob + cg * 8, dstA);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
         }
-
-        // =============================== epilogue
-        mbar_wait(accum, 0);
-        tc_fence_after();
-        const int lq = warp & 3, half = warp >> 2;
-        const int nslab = p.NT >> 5;
+    } else if (warp < kMmaWarp) {
+        // =============================== epilogue (4 warps, one TMEM lane quadrant each)
+        const int lq = warp & 3;
+        const int nslab = p.NT >> 4;  // 16-channel slabs
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-        for (int cs = 0; cs < nslab; ++cs) {
-            float ssum[32], ssq[32];
+        const bool want_stats = p.stat_part != nullptr;
+        float* my_stat = s_stat + (size_t)lq * 2 * p.NT;
+        int it = 0;
+        for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t k = (uint32_t)(it >> 1);
+            const PixInfo* tab = pixtab + (size_t)b * p.P;
+            mbar_wait(&tab_full[b], k & 1);
+            mbar_wait(&acc_full[b], k & 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);
+            for (int cs = 0; cs < nslab; ++cs) {
+                float ssum[16], ssq[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
-            bool any = false;
-            for (int t = 0; t < p.T; ++t) {
-                if (((cs * p.T + t) & 1) != half) continue;
-                any = true;
-                const int m = lq * 32 + lane;
-                const PixInfo pi = pixtab[t * 128 + m + p.Wp + 1];
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * p.NT + cs * 32), v);
-                tmem_ld_wait();
-                if (pi.pix >= 0) {
-                    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pi.pix * p.Cout + n_tile * p.NT + cs * 32);
+                for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+                for (int t = 0; t < p.T; ++t) {
+                    const PixInfo pi = tab[t * 128 + lq * 32 + lane + p.Wp + 1];
+                    uint32_t v[16];
+                    tmem_ld16(acc + (uint32_t)(t * p.NT + cs * 16), v);
+                    tmem_ld_wait();
+                    if (pi.pix >= 0) {
+                        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pi.pix * p.Cout + n_tile * p.NT + cs * 16);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                        dst[j] = o;
-                    }
-                    if (p.stat_part != nullptr) {
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 o;
+                            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                            dst[j] = o;
+                        }
+                        if (want_stats) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float f = __uint_as_float(v[i]);
-                            ssum[i] += f;
-                            ssq[i] = fmaf(f, f, ssq[i]);
+                            for (int i = 0; i < 16; ++i) {
+                                const float f = __uint_as_float(v[i]);
+                                ssum[i] += f;
+                                ssq[i] = fmaf(f, f, ssq[i]);
+                            }
                         }
                     }
                 }
-            }
-            if (p.stat_part != nullptr && any) {
-                // transposing butterfly: afterwards lane L holds the warp total of channel L
+                if (want_stats) {
+                    // fold the two half-warps, then a transposing butterfly: lane L ends with the total of channel L & 15
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
+                    for (int i = 0; i < 16; ++i) {
+                        ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
+                        ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
+                    }
 #pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float sa = up ? ssum[i] : ssum[i + off];
-                        const float ka = up ? ssum[i + off] : ssum[i];
-                        ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-                        const float sb = up ? ssq[i] : ssq[i + off];
-                        const float kb = up ? ssq[i + off] : ssq[i];
-                        ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+                    for (int off = 8; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float sa = up ? ssum[i] : ssum[i + off];
+                            const float ka = up ? ssum[i + off] : ssum[i];
+                            ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+                            const float sb = up ? ssq[i] : ssq[i + off];
+                            const float kb = up ? ssq[i + off] : ssq[i];
+                            ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+                        }
+                    }
+                    if (lane < 16) {  // this thread is the only writer of these two slots, groups are visited in a fixed order
+                        my_stat[cs * 16 + lane] += ssum[0];
+                        my_stat[p.NT + cs * 16 + lane] += ssq[0];
                     }
                 }
-                s_stat[(warp * 2 + 0) * p.NT + cs * 32 + lane] = ssum[0];  // each (warp, cs) slot is written at most once
-                s_stat[(warp * 2 + 1) * p.NT + cs * 32 + lane] = ssq[0];
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[b]);
         }
-        if (p.stat_part != nullptr) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+        if (want_stats) {
+            asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps only
             float* dst = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n_tile * p.NT;
-            for (int c = threadIdx.x; c < p.NT; c += 256) {
-                float a = 0.f, b = 0.f;
+            for (int c = threadIdx.x - kEpilogueWarp0 * 32; c < p.NT; c += 128) {
+                float a = 0.f, bb = 0.f;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) {
-                    a += s_stat[(w8 * 2 + 0) * p.NT + c];
-                    b += s_stat[(w8 * 2 + 1) * p.NT + c];
+                for (int q = 0; q < 4; ++q) {
+                    a += s_stat[(q * 2 + 0) * p.NT + c];
+                    bb += s_stat[(q * 2 + 1) * p.NT + c];
                 }
                 dst[c] = a;
-                dst[p.Cout + c] = b;
+                dst[p.Cout + c] = bb;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // =============================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.NT, kMajorK, kMajorK);
             const uint32_t a_lbo = (uint32_t)p.P * 16u, b_lbo = (uint32_t)p.NT * 16u;
-            const int ksteps = p.CK >> 4;
-            for (int chunk = 0; chunk < p.nchunks; ++chunk) {
-                const int s = chunk % p.S;
-                const uint32_t ph = (chunk / p.S) & 1;
-                mbar_wait(&full[s], ph);
+            const uint32_t hi = umma_desc_hi(128u);          // SBO = 128 B for both operands
+            const uint32_t a_kstep = 2u * (uint32_t)p.P;     // address-field units (16 B): two channel groups
+            const uint32_t b_step = 2u * (uint32_t)p.NT;
+            uint32_t tapoff[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3));
+            int cc = 0, it = 0;
+            for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
+                const int b = it & 1;
+                const uint32_t k = (uint32_t)(it >> 1);
+                mbar_wait(&acc_empty[b], (k & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(sA + (size_t)s * a_bytes);
-                const uint32_t b_base = smem_u32(sB + (size_t)s * b_bytes);
-                for (int t = 0; t < p.T; ++t) {
-                    const uint32_t d_addr = tmem_base + (uint32_t)(t * p.NT);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int dr = tap / 3, dc = tap - 3 * dr;
-                        const uint32_t a_tap = a_base + (uint32_t)(t * 128 + dr * p.Wp + dc) * 16u;
-                        const uint32_t b_tap = b_base + (uint32_t)(tap * cgs) * b_lbo;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t ad = umma_desc_nosw(a_tap + (uint32_t)(2 * ks) * a_lbo, a_lbo, 128u);
-                            const uint64_t bd = umma_desc_nosw(b_tap + (uint32_t)(2 * ks) * b_lbo, b_lbo, 128u);
-                            umma_bf16(d_addr, ad, bd, idesc, (chunk | tap | ks) != 0);
+                const uint32_t acc = tmem_base + (uint32_t)(b * p.T * p.NT);
+                for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
+                    const int s = cc % p.S;
+                    const uint32_t ph = (uint32_t)(cc / p.S) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA + (size_t)s * a_bytes), a_lbo);
+                    const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB + (size_t)s * b_bytes), b_lbo);
+                    for (int t = 0; t < p.T; ++t) {
+                        const uint32_t d_addr = acc + (uint32_t)(t * p.NT);
+                        const uint32_t a_t = a_lo0 + (uint32_t)(t * 128);
+                        uint32_t b_lo = b_lo0;
+                        if (cgs == 4) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t a_lo = a_t + tapoff[tap];
+                                umma_bf16_lohi(d_addr, a_lo, hi, b_lo, hi, idesc, (uint32_t)((chunk | tap) != 0));
+                                umma_bf16_lohi(d_addr, a_lo + a_kstep, hi, b_lo + b_step, hi, idesc, 1u);
+                                b_lo += 2 * b_step;
+                            }
+                        } else {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                umma_bf16_lohi(d_addr, a_t + tapoff[tap], hi, b_lo, hi, idesc, (uint32_t)((chunk | tap) != 0));
+                                b_lo += b_step;
+                            }
                         }
                     }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&acc_full[b]);
             }
-            umma_commit(accum);
         }
         __syncwarp();
     } else {
         // =============================== weight fetcher (bulk async copy engine)
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)n_tile * p.nchunks * b_bytes;
-            for (int chunk = 0; chunk < p.nchunks; ++chunk) {
-                const int s = chunk % p.S;
-                const uint32_t ph = (chunk / p.S) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], b_bytes);
-                bulk_g2s(sB + (size_t)s * b_bytes, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
+            int cc = 0;
+            for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x) {
+                for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
+                    const int s = cc % p.S;
+                    const uint32_t ph = (uint32_t)(cc / p.S) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], b_bytes);
+                    bulk_g2s(sB + (size_t)s * b_bytes, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
+                }
             }
         }
         __syncwarp();
@@ -256,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         switch (p.tmem_cols) {
             case 32: tmem_dealloc<32>(tmem_base); break;
             case 64: tmem_dealloc<64>(tmem_base); break;
@@ -312,7 +358,7 @@ static int pick_nt(int C) {
 
 static size_t conv_smem_bytes(int T, int NT, int CK, int S, int P, int cin_pad) {
     size_t a = (size_t)(CK / 8) * P * 16, b = (size_t)9 * CK * NT * 2;
-    return S * (a + b) + (size_t)P * 8 + (size_t)cin_pad * 12 + (size_t)16 * NT * 4 + (2 * S + 1) * 8 + 16 + 128;
+    return S * (a + b) + (size_t)2 * P * 8 + (size_t)cin_pad * 12 + (size_t)8 * NT * 4 + (2 * S + 6) * 8 + 16 + 128;
 }
 
 extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* pl) {
@@ -330,10 +376,10 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     const size_t budget = 220 * 1024;
     int bestT = 0, bestCK = 0, bestS = 0;
     // prefer: large T (halo amortisation) while keeping >= 2 waves of CTAs, CK=32, 2 stages
-    for (int T = (512 / NT < 4 ? 512 / NT : 4); T >= 1 && !bestT; --T) {
+    for (int T = (256 / NT < 4 ? 256 / NT : 4); T >= 1 && !bestT; --T) {
         if (T == 3) continue;
-        const long long ctas = ((Q + 128LL * T - 1) / (128LL * T)) * n_tiles;
-        if (T > 1 && ctas < 2 * 148) continue;
+        const long long groups = ((Q + 128LL * T - 1) / (128LL * T)) * n_tiles;
+        if (T > 1 && groups < 4 * 148) continue;  // keep >= 4 tile groups per SM for balance and pipelining
         for (int CK = 32; CK >= 16 && !bestT; CK -= 16) {
             if (cin_pad % CK != 0) continue;
             const int nch = cin_pad / CK;
@@ -349,14 +395,28 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     pl->P = 128 * bestT + 2 * (W + 2) + 2;
     pl->nchunks = cin_pad / bestCK;
     pl->n_tiles = n_tiles;
-    pl->grid_m = (int)((Q + 128LL * bestT - 1) / (128LL * bestT));
+    pl->ntg = (int)((Q + 128LL * bestT - 1) / (128LL * bestT));
+    {
+        int ctas_x = 148 / n_tiles;  // persistent: one CTA per SM in total
+        if (ctas_x < 1) ctas_x = 1;
+        pl->grid_m = pl->ntg < ctas_x ? pl->ntg : ctas_x;
+    }
     pl->cin_pad = cin_pad;
     pl->smem_bytes = (int)conv_smem_bytes(bestT, NT, bestCK, bestS, pl->P, cin_pad);
-    int cols = bestT * NT, tc = 32;
+    int cols = 2 * bestT * NT, tc = 32;
     while (tc < cols) tc <<= 1;
     pl->tmem_cols = tc;
     pl->wpack_elems = (int64_t)n_tiles * pl->nchunks * 9 * bestCK * NT;
     return NUNET_OK;
+}
+
+template <int MODE>
+static int launch_conv(const ConvParams& p, const nunet_conv_plan_t& pl, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    conv3x3_igemm_kernel<MODE><<<dim3(pl.grid_m, pl.n_tiles), kThreads, pl.smem_bytes, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
 }
 
 extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
@@ -382,18 +442,24 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
     p.Q = (d->N * (d->H + 1) + 1) * (d->W + 2);
     p.T = pl.T; p.NT = pl.NT; p.CK = pl.CK; p.S = pl.S; p.P = pl.P; p.nchunks = pl.nchunks;
-    p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src; p.tmem_cols = pl.tmem_cols;
+    p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src; p.tmem_cols = pl.tmem_cols; p.ntg = pl.ntg;
     for (int i = 0; i < d->num_src; ++i) {
         p.src[i].data = d->src[i].data; p.src[i].data2 = d->src[i].data2;
         p.src[i].scale = d->src[i].scale; p.src[i].shift = d->src[i].shift; p.src[i].k2 = d->src[i].k2;
         p.src[i].C = d->src[i].C; p.src[i].kind = d->src[i].kind;
     }
     p.wpack = d->wpack; p.out = d->out; p.stat_part = d->stat_part;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
-    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
-    conv3x3_igemm_kernel<<<dim3(pl.grid_m, pl.n_tiles), kThreads, pl.smem_bytes, (cudaStream_t)stream>>>(p);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+    int kinds[NUNET_MAX_SRC];
+    for (int i = 0; i < d->num_src; ++i) kinds[i] = d->src[i].kind;
+    const int mode = sources_mode(kinds, d->num_src);
+    switch (mode) {
+        case MODE_INPUT: return launch_conv<MODE_INPUT>(p, pl, (cudaStream_t)stream);
+        case MODE_SAME: return launch_conv<MODE_SAME>(p, pl, (cudaStream_t)stream);
+        case MODE_POOL: return launch_conv<MODE_POOL>(p, pl, (cudaStream_t)stream);
+        case MODE_SAME_UP: return launch_conv<MODE_SAME_UP>(p, pl, (cudaStream_t)stream);
+        case MODE_GRAD: return launch_conv<MODE_GRAD>(p, pl, (cudaStream_t)stream);
+    }
+    return NUNET_E_UNSUPPORTED;  // source-kind combination outside {input | same* | pool | same*+up | grad}
 }
 
 extern "C" int nunet_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t mode, const nunet_conv_plan_t* pl,

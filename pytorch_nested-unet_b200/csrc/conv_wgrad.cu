@@ -27,6 +27,7 @@ struct WgradParams {
 constexpr int kWThreads = 320;
 constexpr int kWProducerWarps = 8;
 
+template <int MODE>
 __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const WgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,52 +95,32 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             const long long k0 = (long long)(chunk0 + chunk) * p.KP;  // first position of the chunk
             PixInfo* tab = tabs + (size_t)s * p.Pg;
             mbar_wait(&empty[s], ph ^ 1);
-            for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position(k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q);
+            for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position((int)k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, (int)p.Q);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // ---- gy with halo: 4 channel groups x Pg positions
+            // ---- gy with halo: 4 channel groups x Pg positions (lane group r = channel group)
             {
-                float k1[8], k2[8], k3[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { k1[i] = s_g[r * 8 + i]; k2[i] = s_g[32 + r * 8 + i]; k3[i] = s_g[64 + r * 8 + i]; }
                 uint8_t* dst = sG + (size_t)s * g_bytes + (size_t)r * p.Pg * 16;
-                const int nblk = (p.Pg + 7) >> 3;
-                for (int blk = warp; blk < nblk; blk += kWProducerWarps) {
-                    const int pp = blk * 8 + pl;
-                    if (pp < p.Pg) {
-                        const PixInfo pi = tab[pp];
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (pi.pix >= 0) v = load_transform(p.gsrc, p.H, p.W, pi, n_tile * 32 + r * 8, k1, k3, k2);
-                        *reinterpret_cast<uint4*>(dst + (size_t)pp * 16) = v;
-                    }
-                }
+                stage_blocks<NUNET_SRC_GRAD, 4>(p.gsrc, p.H, p.W, tab, 0, p.Pg, warp, (p.Pg + 7) >> 3, kWProducerWarps, pl, n_tile * 32 + r * 8,
+                                                s_g + r * 8, s_g + 64 + r * 8, s_g + 32 + r * 8, dst);
             }
-            // ---- X: mcg channel groups x KP positions (positions [Wp+1, Wp+1+KP) of the table)
+            // ---- X: mcg channel groups x KP positions (positions [Wp+1, Wp+1+KP) of the table), one quad of channel
+            //      groups (= 32 channels, never straddling a source) per pass
             {
                 const int nquads = (mcg + 3) >> 2;
-                const int nblk = (p.KP >> 3) * nquads;
-                for (int blk = warp; blk < nblk; blk += kWProducerWarps) {
-                    const int quad = blk % nquads, pb = blk / nquads;
+                for (int quad = 0; quad < nquads; ++quad) {
                     const int cg = quad * 4 + r;
-                    if (cg < mcg) {
-                        const int pp = pb * 8 + pl;
-                        const int cglob = ci0 + cg * 8;
-                        int si = 0, c0 = 0;
-                        while (true) {
-                            const int cpad = (p.src[si].kind == NUNET_SRC_INPUT) ? 16 : p.src[si].C;
-                            if (cglob < c0 + cpad) break;
-                            c0 += cpad;
-                            ++si;
-                        }
-                        const PixInfo pi = tab[pp + p.Wp + 1];
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (pi.pix >= 0) {
-                            float sc[8], sh[8], zz[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { sc[i] = s_scale[cglob + i]; sh[i] = s_shift[cglob + i]; zz[i] = 0.f; }
-                            v = load_transform(p.src[si], p.H, p.W, pi, cglob - c0, sc, sh, zz);
-                        }
-                        *reinterpret_cast<uint4*>(sX + (size_t)s * x_bytes + ((size_t)cg * p.KP + pp) * 16) = v;
+                    if (cg >= mcg) continue;
+                    const int cglob = ci0 + cg * 8;
+                    int si = 0, c0 = 0;
+                    while (true) {
+                        const int cpad = (p.src[si].kind == NUNET_SRC_INPUT) ? 16 : p.src[si].C;
+                        if (cglob < c0 + cpad) break;
+                        c0 += cpad;
+                        ++si;
                     }
+                    uint8_t* dst = sX + (size_t)s * x_bytes + (size_t)cg * p.KP * 16;
+                    stage_blocks_mode<MODE>(p.src[si], p.H, p.W, tab, p.Wp + 1, p.KP, warp, p.KP >> 3, kWProducerWarps, pl, cglob - c0, s_scale + cglob,
+                                          s_shift + cglob, s_scale + cglob, dst);
                 }
             }
             fence_proxy_async_smem();
@@ -165,24 +146,26 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
     } else if (warp == 8) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, 32, kMajorMN, kMajorMN);
-            const uint32_t a_sbo = (uint32_t)p.KP * 16u, b_sbo = (uint32_t)p.Pg * 16u;
+            const uint32_t a_hi = umma_desc_hi((uint32_t)p.KP * 16u), b_hi = umma_desc_hi((uint32_t)p.Pg * 16u);
             const int ksteps = p.KP >> 4;
+            uint32_t tapoff[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((2 - tap / 3) * p.Wp + (2 - tap % 3));
             for (int chunk = 0; chunk < nchunks; ++chunk) {
                 const int s = chunk % p.S;
                 const uint32_t ph = (chunk / p.S) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(sX + (size_t)s * x_bytes);
-                const uint32_t b_base = smem_u32(sG + (size_t)s * g_bytes);
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int dr = tap / 3, dc = tap - 3 * dr;
-                    const uint32_t b_tap = b_base + (uint32_t)((2 - dr) * p.Wp + (2 - dc)) * 16u;
-                    const uint32_t d_addr = tmem_base + (uint32_t)(tap * 32);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t ad = umma_desc_nosw(a_base + (uint32_t)ks * 256u, 128u, a_sbo);
-                        const uint64_t bd = umma_desc_nosw(b_tap + (uint32_t)ks * 256u, 128u, b_sbo);
-                        umma_bf16(d_addr, ad, bd, idesc, (chunk | ks) != 0);
-                    }
+                uint32_t a_lo = umma_desc_lo(smem_u32(sX + (size_t)s * x_bytes), 128u);
+                uint32_t b_lo = umma_desc_lo(smem_u32(sG + (size_t)s * g_bytes), 128u);
+                // K-step outer, taps inner: each K step (16 positions = 16 address units) feeds nine accumulators
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t accf = (uint32_t)((chunk | ks) != 0);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+                        umma_bf16_lohi(tmem_base + (uint32_t)(tap * 32), a_lo, a_hi, b_lo + tapoff[tap], b_hi, idesc, accf);
+                    a_lo += 16u;
+                    b_lo += 16u;
                 }
                 umma_commit(&empty[s]);
             }
@@ -254,6 +237,15 @@ extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t
     return NUNET_OK;
 }
 
+template <int MODE>
+static int launch_wgrad(const WgradParams& p, const nunet_wgrad_plan_t& pl, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    conv3x3_wgrad_kernel<MODE><<<dim3(pl.splits, pl.m_tiles, pl.n_tiles), kWThreads, pl.smem_bytes, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+}
+
 extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
     if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->part || !d->dw) return NUNET_E_BADARG;
     if (!d->gz || !d->y || !d->k1 || !d->k2 || !d->k3) return NUNET_E_BADARG;
@@ -284,11 +276,18 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
     p.gsrc.data = d->gz; p.gsrc.data2 = d->y; p.gsrc.scale = d->k1; p.gsrc.k2 = d->k2; p.gsrc.shift = d->k3;
     p.gsrc.C = d->Cout; p.gsrc.kind = NUNET_SRC_GRAD;
     p.part = d->part;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
-    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
-    conv3x3_wgrad_kernel<<<dim3(pl.splits, pl.m_tiles, pl.n_tiles), kWThreads, pl.smem_bytes, (cudaStream_t)stream>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    int kinds[NUNET_MAX_SRC];
+    for (int i = 0; i < d->num_src; ++i) kinds[i] = d->src[i].kind;
+    int lrc;
+    switch (sources_mode(kinds, d->num_src)) {
+        case MODE_INPUT: lrc = launch_wgrad<MODE_INPUT>(p, pl, (cudaStream_t)stream); break;
+        case MODE_SAME: lrc = launch_wgrad<MODE_SAME>(p, pl, (cudaStream_t)stream); break;
+        case MODE_POOL: lrc = launch_wgrad<MODE_POOL>(p, pl, (cudaStream_t)stream); break;
+        case MODE_SAME_UP: lrc = launch_wgrad<MODE_SAME_UP>(p, pl, (cudaStream_t)stream); break;
+        default: return NUNET_E_UNSUPPORTED;
+    }
+    if (lrc) return lrc;
+    cudaError_t e;
     const size_t block_elems = (size_t)pl.n_tiles * 9 * pl.cin_pad * 32;
     int blocks = (int)((block_elems + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
