@@ -59,112 +59,130 @@ __device__ __forceinline__ float up_weight(int D, int s, int h, float r) {
     return (i0 == s ? 1.f - l1 : 0.f) + (i1 == s ? l1 : 0.f);
 }
 
-__global__ void __launch_bounds__(256) grad_router_kernel(const RouterParams p) {
+// Consumers are ordered by the host: cons[0..n_same) are SAME, then (HAS_POOL) one POOL, then (HAS_UP) one UP.
+template <bool HAS_POOL, bool HAS_UP, bool HAS_HEAD>
+__global__ void __launch_bounds__(256, 2) grad_router_kernel(const RouterParams p) {
     const int cgs = p.C >> 3;
-    const int cg = threadIdx.x % cgs;
+    const int cg_shift = 31 - __clz(cgs);  // C/8 is a power of two (4..64)
+    const int cg = threadIdx.x & (cgs - 1);
+    const int ch = cg * 8;
     const int HW = p.H * p.W;
-    const long long items = (long long)p.N * HW * cgs;
+    const int items = p.N * HW * cgs;
+    const int n_same = p.num_cons - (HAS_POOL ? 1 : 0) - (HAS_UP ? 1 : 0);
     float sc[8], sh[8], mu[8], rs[8], acc1[8], acc2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        sc[i] = p.scale[cg * 8 + i];
-        sh[i] = p.shift[cg * 8 + i];
-        mu[i] = p.mean[cg * 8 + i];
-        rs[i] = p.invstd[cg * 8 + i];
+        sc[i] = p.scale[ch + i];
+        sh[i] = p.shift[ch + i];
+        mu[i] = p.mean[ch + i];
+        rs[i] = p.invstd[ch + i];
         acc1[i] = 0.f;
         acc2[i] = 0.f;
     }
-    for (long long it = blockIdx.x * 256LL + threadIdx.x; it < items; it += (long long)gridDim.x * 256) {
-        const int pix = (int)(it / cgs);
-        const int n = pix / HW, rem = pix - n * HW;
-        const int yy = rem / p.W, xx = rem - yy * p.W;
-        const int ch = cg * 8;
-        float yv[8];
-        unpack8f(__ldg(reinterpret_cast<const uint4*>(p.y + (size_t)pix * p.C + ch)), yv);
-        float g[8];
+    constexpr int U = 2;
+    const int stride = gridDim.x * 256;
+    for (int it0 = blockIdx.x * 256 + threadIdx.x; it0 < items; it0 += stride * U) {
+        uint4 ry[U], rd[U][4];
+        int pix[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = 0.f;
-        for (int ci = 0; ci < p.num_cons; ++ci) {
-            const GradCons& c = p.cons[ci];
-            if (c.kind == NUNET_SRC_SAME) {
-                add8(g, __ldg(reinterpret_cast<const uint4*>(c.dx + (size_t)pix * c.pitch + c.coff + ch)), 1.f);
-            } else if (c.kind == NUNET_SRC_POOL) {
-                // consumer at (H/2, W/2): route to the first maximum of the 2x2 window of a = relu(scale*y+shift)
-                const int y0 = yy & ~1, x0 = xx & ~1;
-                const int me = ((yy & 1) << 1) | (xx & 1);
-                const size_t wbase = ((size_t)n * HW + (size_t)y0 * p.W + x0);
-                float av[4][8];
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * stride;
+            pix[u] = (it < items) ? (it >> cg_shift) : -1;
+            if (pix[u] >= 0) {
+                ry[u] = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)pix[u] * p.C + ch));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float t[8];
-                    if (k == me) {
+                for (int ci = 0; ci < 4; ++ci)
+                    if (ci < n_same)
+                        rd[u][ci] = __ldg(reinterpret_cast<const uint4*>(p.cons[ci].dx + (size_t)pix[u] * p.cons[ci].pitch + p.cons[ci].coff + ch));
+            }
+        }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) t[i] = yv[i];
-                    } else {
-                        unpack8f(__ldg(reinterpret_cast<const uint4*>(p.y + (wbase + (size_t)(k >> 1) * p.W + (k & 1)) * p.C + ch)), t);
-                    }
+        for (int u = 0; u < U; ++u) {
+            if (pix[u] < 0) continue;
+            float yv[8], g[8];
+            unpack8f(ry[u], yv);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) av[k][i] = fmaxf(fmaf(t[i], sc[i], sh[i]), 0.f);
-                }
-                const size_t cpix = ((size_t)n * (p.H >> 1) + (yy >> 1)) * (p.W >> 1) + (xx >> 1);
-                float d[8];
-                unpack8f(__ldg(reinterpret_cast<const uint4*>(c.dx + cpix * c.pitch + c.coff + ch)), d);
+            for (int i = 0; i < 8; ++i) g[i] = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    bool win = true;
+            for (int ci = 0; ci < 4; ++ci)
+                if (ci < n_same) add8(g, rd[u][ci], 1.f);
+            if constexpr (HAS_POOL || HAS_UP || HAS_HEAD) {
+                const int n = pix[u] / HW, rem = pix[u] - n * HW;
+                const int yy = rem / p.W, xx = rem - yy * p.W;
+                if constexpr (HAS_POOL) {
+                    // consumer at (H/2, W/2): route to the first maximum of the 2x2 window of a = relu(scale*y+shift)
+                    const GradCons& c = p.cons[n_same];
+                    const int y0 = yy & ~1, x0 = xx & ~1;
+                    const int me = ((yy & 1) << 1) | (xx & 1);
+                    const size_t wbase = (size_t)n * HW + (size_t)y0 * p.W + x0;
+                    float am[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) am[i] = fmaxf(fmaf(yv[i], sc[i], sh[i]), 0.f);
+                    bool win[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) win[i] = true;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (k < me) win = win && (av[me][i] > av[k][i]);
-                        if (k > me) win = win && (av[me][i] >= av[k][i]);
+                        if (k == me) continue;
+                        float t[8];
+                        unpack8f(__ldg(reinterpret_cast<const uint4*>(p.y + (wbase + (size_t)(k >> 1) * p.W + (k & 1)) * p.C + ch)), t);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float ak = fmaxf(fmaf(t[i], sc[i], sh[i]), 0.f);
+                            win[i] = win[i] && ((k < me) ? (am[i] > ak) : (am[i] >= ak));
+                        }
                     }
-                    if (win) g[i] += d[i];
+                    const size_t cpix = ((size_t)n * (p.H >> 1) + (yy >> 1)) * (p.W >> 1) + (xx >> 1);
+                    float d[8];
+                    unpack8f(__ldg(reinterpret_cast<const uint4*>(c.dx + cpix * c.pitch + c.coff + ch)), d);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (win[i]) g[i] += d[i];
                 }
-            } else {  // NUNET_SRC_UP: consumer at (2H, 2W)
-                const int H2 = 2 * p.H, W2 = 2 * p.W;
-                const float ry = (float)(p.H - 1) / (float)(H2 - 1), rx = (float)(p.W - 1) / (float)(W2 - 1);
-                float wy[8], wx[8];
+                if constexpr (HAS_UP) {  // consumer at (2H, 2W): transposed align_corners bilinear
+                    const GradCons& c = p.cons[n_same + (HAS_POOL ? 1 : 0)];
+                    const int H2 = 2 * p.H, W2 = 2 * p.W;
+                    const float ry_ = (float)(p.H - 1) / (float)(H2 - 1), rx_ = (float)(p.W - 1) / (float)(W2 - 1);
+                    // contributing outputs D of source index s satisfy |r*D - s| < 1  =>  D in (  (s-1)/r , (s+1)/r  ) ~ [2s-2, 2s+3]
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int Y = 2 * yy - 3 + k, X = 2 * xx - 3 + k;
-                    wy[k] = (Y >= 0 && Y < H2) ? up_weight(Y, yy, p.H, ry) : 0.f;
-                    wx[k] = (X >= 0 && X < W2) ? up_weight(X, xx, p.W, rx) : 0.f;
+                    for (int ky = 0; ky < 6; ++ky) {
+                        const int Y = 2 * yy - 2 + ky;
+                        const float wy = (Y >= 0 && Y < H2) ? up_weight(Y, yy, p.H, ry_) : 0.f;
+                        if (wy == 0.f) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 6; ++kx) {
+                            const int X = 2 * xx - 2 + kx;
+                            const float wx = (X >= 0 && X < W2) ? up_weight(X, xx, p.W, rx_) : 0.f;
+                            if (wx == 0.f) continue;
+                            const size_t cpix = ((size_t)n * H2 + Y) * W2 + X;
+                            add8(g, __ldg(reinterpret_cast<const uint4*>(c.dx + cpix * c.pitch + c.coff + ch)), wy * wx);
+                        }
+                    }
                 }
+                if constexpr (HAS_HEAD) {
+                    for (int k = 0; k < p.K; ++k) {
+                        const float dl = __ldg(p.dlogits + ((size_t)n * p.K + k) * HW + rem);
 #pragma unroll
-                for (int ky = 0; ky < 8; ++ky) {
-                    if (wy[ky] == 0.f) continue;
-                    const int Y = 2 * yy - 3 + ky;
-#pragma unroll
-                    for (int kx = 0; kx < 8; ++kx) {
-                        if (wx[kx] == 0.f) continue;
-                        const int X = 2 * xx - 3 + kx;
-                        const size_t cpix = ((size_t)n * H2 + Y) * W2 + X;
-                        add8(g, __ldg(reinterpret_cast<const uint4*>(c.dx + cpix * c.pitch + c.coff + ch)), wy[ky] * wx[kx]);
+                        for (int i = 0; i < 8; ++i) g[i] = fmaf(dl, __ldg(p.wh + k * p.C + ch + i), g[i]);
                     }
                 }
             }
-        }
-        if (p.dlogits != nullptr) {
-            for (int k = 0; k < p.K; ++k) {
-                const float dl = __ldg(p.dlogits + ((size_t)n * p.K + k) * HW + rem);
+            uint32_t o[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = fmaf(dl, __ldg(p.wh + k * p.C + ch + i), g[i]);
+            for (int i = 0; i < 8; ++i) {
+                const float z = fmaf(yv[i], sc[i], sh[i]);
+                const float gz = (z > 0.f) ? g[i] : 0.f;
+                g[i] = gz;
+                acc1[i] += gz;
+                acc2[i] = fmaf(gz, (yv[i] - mu[i]) * rs[i], acc2[i]);
             }
-        }
-        uint32_t o[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float z = fmaf(yv[i], sc[i], sh[i]);
-            const float gz = (z > 0.f) ? g[i] : 0.f;
-            g[i] = gz;
-            acc1[i] += gz;
-            acc2[i] = fmaf(gz, (yv[i] - mu[i]) * rs[i], acc2[i]);
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+                o[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(p.gz + (size_t)pix[u] * p.C + ch) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
-            o[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(p.gz + (size_t)pix * p.C + ch) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     // block reduction: threads with equal cg (tid % cgs) hold the same 8 channels
     __shared__ float red[256][9];
@@ -189,7 +207,7 @@ using namespace nunet;
 extern "C" int nunet_grad_router_rows(int32_t N, int32_t H, int32_t W, int32_t C) {
     long long items = (long long)N * H * W * (C / 8);
     long long b = (items + 255) / 256;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > 148 * 4) b = 148 * 4;
     return (int)(b < 1 ? 1 : b);
 }
 
@@ -202,17 +220,37 @@ extern "C" int nunet_grad_router(const nunet_router_desc_t* d, void* stream) {
     p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C;
     p.y = (const __nv_bfloat16*)d->y; p.scale = d->scale; p.shift = d->shift; p.mean = d->mean; p.invstd = d->invstd;
     p.num_cons = d->num_cons;
-    for (int i = 0; i < d->num_cons; ++i) {
-        const nunet_grad_cons_t& c = d->cons[i];
-        if (!c.dx || c.pitch % 8 != 0 || c.coff % 8 != 0) return NUNET_E_BADARG;
-        if (c.kind != NUNET_SRC_SAME && c.kind != NUNET_SRC_POOL && c.kind != NUNET_SRC_UP) return NUNET_E_BADARG;
-        if (c.kind == NUNET_SRC_POOL && ((d->H | d->W) & 1)) return NUNET_E_UNSUPPORTED;
-        p.cons[i].dx = (const __nv_bfloat16*)c.dx; p.cons[i].pitch = c.pitch; p.cons[i].coff = c.coff; p.cons[i].kind = c.kind;
+    int n_same = 0, n_pool = 0, n_up = 0;
+    for (int pass = 0; pass < 3; ++pass) {  // stable reorder: SAME..., POOL, UP
+        const int want = pass == 0 ? NUNET_SRC_SAME : (pass == 1 ? NUNET_SRC_POOL : NUNET_SRC_UP);
+        for (int i = 0; i < d->num_cons; ++i) {
+            const nunet_grad_cons_t& c = d->cons[i];
+            if (!c.dx || c.pitch % 8 != 0 || c.coff % 8 != 0) return NUNET_E_BADARG;
+            if (c.kind != NUNET_SRC_SAME && c.kind != NUNET_SRC_POOL && c.kind != NUNET_SRC_UP) return NUNET_E_BADARG;
+            if (c.kind != want) continue;
+            if (c.kind == NUNET_SRC_POOL && ((d->H | d->W) & 1)) return NUNET_E_UNSUPPORTED;
+            const int j = n_same + n_pool + n_up;
+            p.cons[j].dx = (const __nv_bfloat16*)c.dx; p.cons[j].pitch = c.pitch; p.cons[j].coff = c.coff; p.cons[j].kind = c.kind;
+            if (pass == 0) ++n_same; else if (pass == 1) ++n_pool; else ++n_up;
+        }
     }
+    if (n_same > 4 || n_pool > 1 || n_up > 1) return NUNET_E_UNSUPPORTED;
+    if ((long long)d->N * d->H * d->W * (d->C / 8) >= (1LL << 31) - (1LL << 22)) return NUNET_E_UNSUPPORTED;
     p.dlogits = d->dlogits; p.wh = d->wh; p.K = d->K;
     p.gz = (__nv_bfloat16*)d->gz; p.part = d->part;
     const int rows = nunet_grad_router_rows(d->N, d->H, d->W, d->C);
-    grad_router_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(p);
+    const bool hp = n_pool > 0, hu = n_up > 0, hh = d->dlogits != nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+#define NUNET_ROUTER_CASE(P_, U_, H_) if (hp == P_ && hu == U_ && hh == H_) grad_router_kernel<P_, U_, H_><<<rows, 256, 0, st>>>(p)
+    NUNET_ROUTER_CASE(false, false, false);
+    NUNET_ROUTER_CASE(false, false, true);
+    NUNET_ROUTER_CASE(false, true, false);
+    NUNET_ROUTER_CASE(false, true, true);
+    NUNET_ROUTER_CASE(true, false, false);
+    NUNET_ROUTER_CASE(true, false, true);
+    NUNET_ROUTER_CASE(true, true, false);
+    NUNET_ROUTER_CASE(true, true, true);
+#undef NUNET_ROUTER_CASE
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
 }
