@@ -147,7 +147,7 @@ int nunet_bn_backward_reduce(const float* part, int32_t rows, int32_t C, double 
                              float* k2, float* k3, double* scratch, uint32_t* counters, double* sums_out, void* stream);
 int nunet_bn_backward_from_sums(const double* sums, int32_t C, double count, const float* gamma, const float* save_mean,
                                 const float* save_invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
-                                void* stream);
+                                float grad_scale, void* stream);
 
 /* ---- weight gradient (autograd of nn.Conv2d, finished/archs1.py:18,20) --------------------------------------------------
  * dw[co][ci][3][3] (fp32 OIHW, overwritten) = sum over pixels of g_y (x) X, with X read through the same fused loaders

@@ -164,8 +164,9 @@ def unet_forward(sd, x, train=True, stats_out=None):
 def bce_dice_loss(logits, target):
     """BCEDiceLoss.forward (losses.py:107-117)."""
     x, t = logits, target
-    # F.binary_cross_entropy_with_logits, mean reduction: max(x,0) - x*t + log1p(exp(-|x|))
-    bce = (torch.clamp(x, min=0) - x * t + torch.log1p(torch.exp(-x.abs()))).mean()
+    # F.binary_cross_entropy_with_logits, mean reduction: (1-t)*x + softplus(-x)  [= max(x,0) - x*t + log1p(exp(-|x|)),
+    # written in the smooth form so that autograd gives sigmoid(x)-t also at x == 0]
+    bce = ((1 - t) * x + F.softplus(-x)).mean()
     smooth = 1e-5
     p = torch.sigmoid(x)
     num = t.size(0)

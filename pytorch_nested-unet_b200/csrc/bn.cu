@@ -27,14 +27,15 @@ struct BnFinalizeArgs {
     float* k1;
     float* k2;
     float* k3;
+    float grad_scale;  // mode 1: multiplies dgamma / dbeta (1/world_size under SyncBN, see dist.py)
 };
 
 // BatchNorm backward (nn.BatchNorm2d, train): dbeta = S1, dgamma = S2,
 //   g_y = gamma*r*(g_z - S1/M - yhat*S2/M),  yhat = (y-mean)*r   =>   g_y = k1*g_z + k2*y + k3.
 __device__ __forceinline__ void bn_backward_channel(const BnFinalizeArgs& a, int c, double S1, double S2) {
     const double g = a.gamma[c], r = a.save_invstd[c], mu = a.save_mean[c], M = a.count;
-    a.dbeta[c] = (float)S1;
-    a.dgamma[c] = (float)S2;
+    a.dbeta[c] = (float)(S1 * a.grad_scale);
+    a.dgamma[c] = (float)(S2 * a.grad_scale);
     a.k1[c] = (float)(g * r);
     a.k2[c] = (float)(-g * r * r * S2 / M);
     a.k3[c] = (float)(-g * r * S1 / M + g * r * r * mu * S2 / M);
@@ -168,17 +169,19 @@ extern "C" int nunet_bn_backward_reduce(const float* part, int32_t rows, int32_t
     BnFinalizeArgs f{};
     f.mode = 1; f.count = count; f.gamma = gamma; f.save_mean = const_cast<float*>(save_mean);
     f.save_invstd = const_cast<float*>(save_invstd); f.dgamma = dgamma; f.dbeta = dbeta; f.k1 = k1; f.k2 = k2; f.k3 = k3;
+    f.grad_scale = 1.f;
     bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(part, rows, C, scratch, counters, sums_out, f);
     return cuda_rc();
 }
 
 extern "C" int nunet_bn_backward_from_sums(const double* sums, int32_t C, double count, const float* gamma, const float* save_mean,
                                            const float* save_invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
-                                           void* stream) {
+                                           float grad_scale, void* stream) {
     if (!sums || C <= 0 || !gamma || !save_mean || !save_invstd || !dgamma || !dbeta || !k1 || !k2 || !k3 || count <= 0) return NUNET_E_BADARG;
     BnFinalizeArgs f{};
     f.mode = 1; f.count = count; f.gamma = gamma; f.save_mean = const_cast<float*>(save_mean);
     f.save_invstd = const_cast<float*>(save_invstd); f.dgamma = dgamma; f.dbeta = dbeta; f.k1 = k1; f.k2 = k2; f.k3 = k3;
+    f.grad_scale = grad_scale;
     bn_finalize_from_sums_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, f);
     return cuda_rc();
 }

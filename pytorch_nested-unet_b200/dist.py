@@ -1,0 +1,136 @@
+"""Data-parallel training of the fused engine: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch).
+
+The reference is single-GPU; this is the north_star's addition.  Exchange steps:
+  1. gradient all-reduce (AVG) — the engine writes every parameter gradient straight into one flat fp32 buffer laid out
+     in the order backward produces them; buckets of that buffer are all-reduced asynchronously as soon as their last
+     gradient has been written, so the transfers overlap the remaining backward kernels (no copy-in / copy-out);
+  2. SyncBN — per BatchNorm layer the fp64 [sum, sum of squares] (forward) and [sum g_z, sum g_z*yhat] (backward) are
+     all-reduced and finalised with the GLOBAL count, which reproduces nn.BatchNorm2d on the global batch
+     (= torch.nn.SyncBatchNorm semantics: var+eps, unbiased running_var over the global count);
+  3. IoU — the integer intersection / union counts are all-reduced (not per-rank ratios), metrics.py:15-18 on the global
+     batch; the scalar loss is averaged for logging.
+With equal per-rank batches the mean of the local losses is the global-batch loss for both BCE (mean) and Dice
+(per-sample mean), so averaging the local-loss gradients is exact."""
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class GradBuckets(object):
+    """Flat gradient buffer with bucketed asynchronous all-reduce (device-agnostic: tested with gloo on CPU)."""
+
+    def __init__(self, params_in_backward_order, bucket_bytes=8 << 20, group=None):
+        self.group = group
+        self.params = list(params_in_backward_order)
+        self.offsets, self.bucket_of, self.bucket_ranges = {}, {}, []
+        off = start = 0
+        for p in self.params:
+            n = (p.numel() + 31) // 32 * 32          # keep every gradient 128-byte aligned
+            self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
+            self.bucket_of[id(p)] = len(self.bucket_ranges)
+            off += n
+            if (off - start) * 4 >= bucket_bytes:
+                self.bucket_ranges.append((start, off))
+                start = off
+        if off > start:
+            self.bucket_ranges.append((start, off))
+        self.total = off
+        self.flat = None
+        self.pending = None
+        self.works = []
+
+    def begin(self, device):
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.pending = [0] * len(self.bucket_ranges)
+        for p in self.params:
+            self.pending[self.bucket_of[id(p)]] += 1
+        self.works = []
+
+    def view(self, p):
+        off, n, shape = self.offsets[id(p)]
+        return self.flat[off:off + n].view(shape)
+
+    def ready(self, p):
+        """Marks p's gradient as written; launches the bucket's all-reduce when it is complete."""
+        b = self.bucket_of[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            s, e = self.bucket_ranges[b]
+            op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
+            w = dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True)
+            self.works.append((w, s, e, op))
+
+    def finish(self):
+        """Flushes buckets whose parameters produced no gradient (kept zero) and waits (stream-level) for all transfers."""
+        for b, left in enumerate(self.pending):
+            if left > 0:
+                self.pending[b] = 0
+                s, e = self.bucket_ranges[b]
+                op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
+                self.works.append((dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True), s, e, op))
+        ws = dist.get_world_size(self.group)
+        for w, s, e, op in self.works:
+            w.wait()
+            if op == dist.ReduceOp.SUM:
+                self.flat[s:e].div_(ws)
+        self.works = []
+
+
+class DataParallel(nn.Module):
+    """Wraps archs.UNet / archs.NestedUNet for one-process-per-GPU data parallelism.
+
+    state_dict()/load_state_dict() keep the reference's key layout (no 'module.' prefix) so checkpoints interchange."""
+
+    def __init__(self, module, sync_bn=True, bucket_bytes=8 << 20, process_group=None):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (backend nccl) before wrapping the model")
+        self.module = module
+        self.sync_bn = bool(sync_bn)
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=0, group=process_group)
+        import engine
+        order = []
+        for s in reversed(engine._state(module).specs):
+            if s.head is not None:
+                order += [s.head.weight, s.head.bias]
+            order += [s.bn.weight, s.bn.bias, s.conv.weight] + ([s.conv.bias] if s.conv.bias is not None else [])
+        self.buckets = GradBuckets(order, bucket_bytes, process_group)
+        module.__dict__["_nunet_dp"] = self
+
+    # ---- engine hooks
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    # ---- nn.Module surface
+    def forward(self, x):
+        return self.module(x)
+
+    def state_dict(self, *a, **kw):
+        return self.module.state_dict(*a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        return self.module.load_state_dict(*a, **kw)
+
+
+def global_iou_score(output, target, group=None):
+    """metrics.iou_score over the GLOBAL batch: integer counts are all-reduced, then the float64 ratio is formed."""
+    import metrics
+    i, u = metrics.iou_counts(output, target)
+    dev = output.device if torch.is_tensor(output) else "cpu"
+    c = torch.tensor([i, u], dtype=torch.int64, device=dev)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    i, u = c.tolist()
+    return (i + 1e-5) / (u + 1e-5)
+
+
+def global_mean(value, device, group=None):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t /= dist.get_world_size(group)
+    return float(t)

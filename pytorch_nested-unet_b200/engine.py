@@ -216,6 +216,18 @@ def _backward(model, x, recs, grad_logits):
     ws = st.workspace(dev)
     dp = _world(model)
     grads, dxs = {}, {}
+    buckets = dp.buckets if dp is not None else None
+    if buckets is not None:
+        buckets.begin(dev)
+
+    def galloc(p):
+        return buckets.view(p) if buckets is not None else torch.empty(p.shape, dtype=torch.float32, device=dev)
+
+    def gdone(p, g):
+        grads[id(p)] = g
+        if buckets is not None:
+            buckets.ready(p)
+
     for s in reversed(specs):
         r = recs[s.idx]
         h, w = r.h, r.w
@@ -226,15 +238,15 @@ def _backward(model, x, recs, grad_logits):
             if dl is not None:
                 K = s.head.out_channels
                 wh = s.head.weight.detach().view(K, -1)
-                dwh, dbh = ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K)
-                grads[id(s.head.weight)] = dwh.view_as(s.head.weight)
-                grads[id(s.head.bias)] = dbh
+                dwh, dbh = galloc(s.head.weight), galloc(s.head.bias)
+                ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
+                gdone(s.head.weight, dwh)
+                gdone(s.head.bias, dbh)
         if not cons and dl is None:
             dl = torch.zeros((N, 1, h, w), dtype=torch.float32, device=dev)
             wh = torch.zeros((1, s.cout), dtype=torch.float32, device=dev)
         gz, rpart = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh)
-        dgamma = torch.empty(s.cout, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        dgamma, dbeta = galloc(s.bn.weight), galloc(s.bn.bias)
         k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
         count = float(N * h * w)
         if dp is None or not dp.sync_bn:
@@ -243,11 +255,12 @@ def _backward(model, x, recs, grad_logits):
             sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
             ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, ws, dgamma, dbeta, k1, k2, k3, sums_out=sums, finalize=False)
             dp.all_reduce_sum(sums)
-            ops.bn_backward_from_sums(sums, count * dp.world_size, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3)
-            # dgamma / dbeta now hold GLOBAL sums; the gradient all-reduce averages, so pre-divide to keep them global
-            dp.mark_global(dgamma, dbeta)
-        grads[id(s.bn.weight)] = dgamma
-        grads[id(s.bn.bias)] = dbeta
+            # local gradients are those of the LOCAL mean loss (= world_size x the global-loss gradient); the all-reduced sums
+            # therefore give world_size x dgamma/dbeta on every rank: scale by 1/world so the later AVG keeps the true value
+            ops.bn_backward_from_sums(sums, count * dp.world_size, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3,
+                                      grad_scale=1.0 / dp.world_size)
+        gdone(s.bn.weight, dgamma)
+        gdone(s.bn.bias, dbeta)
         srcs = []
         for pi, kind, c in s.sources:
             if pi < 0:
@@ -255,12 +268,12 @@ def _backward(model, x, recs, grad_logits):
             else:
                 pr = recs[pi]
                 srcs.append(ops.Source(kind, pr.y, c, pr.scale, pr.shift))
-        dw = torch.empty_like(s.conv.weight, dtype=torch.float32)
+        dw = galloc(s.conv.weight)
         ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gz, r.y, k1, k2, k3, dw)
-        grads[id(s.conv.weight)] = dw
+        gdone(s.conv.weight, dw)
         if s.conv.bias is not None:
             # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
-            grads[id(s.conv.bias)] = torch.zeros_like(s.conv.bias)
+            gdone(s.conv.bias, galloc(s.conv.bias) if buckets is not None else torch.zeros_like(s.conv.bias))
         if s.sources[0][0] >= 0:
             plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
             wpd = st.pack(s, plan, L.PACK_DGRAD)
@@ -269,6 +282,8 @@ def _backward(model, x, recs, grad_logits):
         for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
             if specs[m].sources[0][0] == s.idx:
                 dxs.pop(m, None)
+    if buckets is not None:
+        buckets.finish()
     return grads
 
 

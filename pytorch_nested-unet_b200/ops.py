@@ -196,12 +196,14 @@ def loss_bwd(logits, target, sums, gscale, gmul=1.0, dlogits=None):
     return dlogits
 
 
-def head_bwd_params(y, scale, shift, dlogits, N, H, W, K):
+def head_bwd_params(y, scale, shift, dlogits, N, H, W, K, dwh=None, dbh=None):
     dev = y.device
     rows = L.lib().nunet_head_bwd_params_rows()
     part = torch.empty((rows, K, 33), dtype=torch.float32, device=dev)
-    dwh = torch.empty((K, 32), dtype=torch.float32, device=dev)
-    dbh = torch.empty((K,), dtype=torch.float32, device=dev)
+    if dwh is None:
+        dwh = torch.empty((K, 32), dtype=torch.float32, device=dev)
+    if dbh is None:
+        dbh = torch.empty((K,), dtype=torch.float32, device=dev)
     _call("head_bwd", 2, None, "nunet_head_bwd_params", L.lib().nunet_head_bwd_params, _ptr(y), _ptr(scale), _ptr(shift), _ptr(dlogits), N, H, W, K, _ptr(part), _ptr(dwh), _ptr(dbh), 0,
                                           _stream())
     return dwh, dbh
@@ -242,9 +244,9 @@ def bn_backward_reduce(part, count, gamma, mean, invstd, ws, dgamma, dbeta, k1, 
                                              _ptr(sums_out), _stream())
 
 
-def bn_backward_from_sums(sums, count, gamma, mean, invstd, dgamma, dbeta, k1, k2, k3):
+def bn_backward_from_sums(sums, count, gamma, mean, invstd, dgamma, dbeta, k1, k2, k3, grad_scale=1.0):
     _call("bn_bwd", 1, None, "nunet_bn_backward_from_sums", L.lib().nunet_bn_backward_from_sums, _ptr(sums), gamma.numel(), float(count), _ptr(gamma), _ptr(mean), _ptr(invstd), _ptr(dgamma),
-                                                _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), _stream())
+                                                _ptr(dbeta), _ptr(k1), _ptr(k2), _ptr(k3), float(grad_scale), _stream())
 
 
 @functools.lru_cache(maxsize=None)

@@ -1,0 +1,130 @@
+"""Host-side logic that needs no GPU: engine graph bookkeeping, drop-in module surface, no-CPU-fallback behaviour,
+gradient bucketing and the SyncBN statistics exchange over gloo with world_size 2."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_engine_specs_match_reference_graph():
+    import archs
+    import engine
+    import _lib as L
+    m = archs.NestedUNet(2, 3, True)
+    specs = engine._state(m).specs
+    assert len(specs) == 30
+    by = {(s.node, s.which): s for s in specs}
+    s = by[("0_4", 1)]
+    assert s.cin_pad == 192 and s.cout == 32 and [k for _, k, _ in s.sources] == [L.SRC_SAME] * 4 + [L.SRC_UP]
+    assert [c for _, _, c in s.sources] == [32, 32, 32, 32, 64]
+    assert by[("0_0", 1)].cin_pad == 16 and by[("0_0", 1)].sources[0][1] == L.SRC_INPUT
+    assert by[("3_0", 1)].sources == [(by[("2_0", 2)].idx, L.SRC_POOL, 128)]
+    # x0_0 is consumed by conv1_0 (pool) and conv0_1..conv0_4 (same, channel offset 0)
+    cons = by[("0_0", 2)].consumers
+    assert sorted(k for _, _, k in cons) == sorted([L.SRC_POOL] + [L.SRC_SAME] * 4) and all(off == 0 for _, off, _ in cons)
+    # x1_2 enters conv0_3.conv1 upsampled at channel offset 3*32
+    c13 = [(m_, off, k) for (m_, off, k) in by[("1_2", 2)].consumers if specs[m_].node == "0_3"]
+    assert c13 == [(by[("0_3", 1)].idx, 96, L.SRC_UP)]
+    assert [s.node for s in specs if s.head is not None] == ["0_1", "0_2", "0_3", "0_4"]
+    u = archs.UNet(1, 3)
+    assert len(engine._state(u).specs) == 18 and [s.node for s in engine._state(u).specs if s.head is not None] == ["0_4"]
+
+
+def test_state_dict_layout_and_param_counts():
+    import archs
+    m = archs.NestedUNet(1, 3, True)
+    keys = list(m.state_dict().keys())
+    assert len(keys) == 218 and keys[0] == "conv0_0.conv1.weight"
+    assert m.state_dict()["conv0_4.conv1.weight"].shape == (32, 192, 3, 3)
+    assert sum(p.numel() for p in m.parameters()) == 9163428
+    assert sum(p.numel() for p in archs.NestedUNet(1, 3, False).parameters()) == 9163329
+    assert sum(p.numel() for p in archs.UNet(1, 3).parameters()) == 7852545
+    assert archs.__all__ == ['UNet', 'NestedUNet']
+
+
+def test_no_cpu_fallback():
+    import archs
+    import losses
+    import _lib as L
+    m = archs.UNet(1, 3)
+    with pytest.raises(L.NunetError):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(L.NunetError):
+        losses.BCEDiceLoss()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(ValueError):
+        if torch.cuda.is_available():
+            m.cuda()(torch.zeros(1, 3, 40, 40, device="cuda"))
+        else:
+            raise ValueError("no gpu: shape check covered on the GPU box")
+
+
+def test_utils_and_cli_defaults_match_reference():
+    import train
+    import utils
+    a = utils.AverageMeter()
+    a.update(2.0, 3)
+    a.update(4.0, 1)
+    assert a.avg == 2.5 and a.count == 4 and a.val == 4.0
+    assert utils.str2bool("True") is True and utils.str2bool("false") is False
+    cfg = vars(train.parse_args([]))
+    ref = dict(epochs=100, batch_size=16, arch="NestedUNet", deep_supervision=False, input_channels=3, num_classes=1, input_w=96,
+               input_h=96, loss="BCEDiceLoss", dataset="dsb2018_96", optimizer="SGD", lr=1e-3, momentum=0.9, weight_decay=1e-4,
+               nesterov=False, scheduler="CosineAnnealingLR", min_lr=1e-5, factor=0.1, patience=2, milestones="1,2",
+               early_stopping=-1, num_workers=4)
+    for k, v in ref.items():
+        assert cfg[k] == v, k
+
+
+# ------------------------------------------------------------------------------------------------ gloo, world_size 2
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "pytorch_nested-unet_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from dist import GradBuckets
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((7, 5), (33,), (64, 3, 3, 3), (5,), (1000,))]
+    gb = GradBuckets(params, bucket_bytes=4096)
+    gb.begin("cpu")
+    for i, p in enumerate(params):
+        gb.view(p).copy_(torch.full(p.shape, float((rank + 1) * (i + 1))))
+        if i != 3:                       # parameter 3 never reports: finish() must flush its bucket
+            gb.ready(p)
+    gb.finish()
+    ok = all(torch.allclose(gb.view(p), torch.full(p.shape, 1.5 * (i + 1))) for i, p in enumerate(params))
+    # SyncBN exchange: all-reduced [sum, sumsq] + global count == statistics of the concatenated batch
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(8, 16, 6, 6, generator=g, dtype=torch.float64)
+    mine = full[rank * 4:(rank + 1) * 4]
+    sums = torch.stack([mine.sum((0, 2, 3)), (mine * mine).sum((0, 2, 3))])
+    dist.all_reduce(sums)
+    cnt = full.numel() / 16
+    mean = sums[0] / cnt
+    var = sums[1] / cnt - mean * mean
+    ok = ok and torch.allclose(mean, full.mean((0, 2, 3))) and torch.allclose(var, full.var((0, 2, 3), unbiased=False))
+    # IoU: counts are all-reduced, not ratios
+    c = torch.tensor([10 * (rank + 1), 40], dtype=torch.int64)
+    dist.all_reduce(c)
+    ok = ok and c.tolist() == [30, 80]
+    q.put((rank, bool(ok), len(gb.bucket_ranges)))
+    dist.destroy_process_group()
+
+
+def test_grad_buckets_and_syncbn_exchange_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] >= 2  # more than one bucket was exercised
