@@ -259,12 +259,14 @@ def run_native(args):
     raw = model.module if hasattr(model, "module") else model
     roof = None
     layer_rows = []
+    # every rank runs the extra (untimed) profiling step: under DP it contains collectives
+    ops.enable_kernel_timing(rank == 0)
+    step(x_dev, t_dev)
+    torch.cuda.synchronize()
+    timing = ops.collect_kernel_timing() if rank == 0 else None
+    ops.enable_kernel_timing(False)
+    barrier()
     if rank == 0:
-        ops.enable_kernel_timing(True)
-        step(x_dev, t_dev)
-        torch.cuda.synchronize()
-        timing = ops.collect_kernel_timing()
-        ops.enable_kernel_timing(False)
         conv_ms = sum(v for k, v in timing["by_class"].items() if k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
         total_ms = sum(timing["by_class"].values())
         _, train_fl = conv_flops_per_image(args.arch, S)

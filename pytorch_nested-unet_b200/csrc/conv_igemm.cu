@@ -29,6 +29,18 @@ constexpr int kMmaWarp = 12;                      // warp 12   : tcgen05.mma iss
 constexpr int kFetchWarp = 13;                    // warp 13   : weight fetcher (cp.async.bulk, one lane)
 constexpr int kThreads = 14 * 32;
 
+// Optional wait/work cycle accounting per warp role (build with -DNUNET_PROFILE_WAITS; tools/prof_waits.py reads it).
+#ifdef NUNET_PROFILE_WAITS
+__device__ unsigned long long g_wait_prof[16];
+#define PROF_DECL long long prof_t = clock64(); long long prof_acc[4] = {0, 0, 0, 0};
+#define PROF_MARK(slot) { long long now_ = clock64(); prof_acc[slot] += now_ - prof_t; prof_t = now_; }
+#define PROF_FLUSH(base) { for (int i_ = 0; i_ < 4; ++i_) atomicAdd(&g_wait_prof[(base) + i_], (unsigned long long)prof_acc[i_]); }
+#else
+#define PROF_DECL
+#define PROF_MARK(slot) {}
+#define PROF_FLUSH(base) {}
+#endif
+
 // Persistent: CTA (x, n_tile) processes tile groups x, x+gridDim.x, ... of 128*T positions each.  Accumulators and the
 // position table are double-buffered so the producers / tensor core work on group i+1 while the epilogue drains group i.
 template <int MODE>
@@ -111,15 +123,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
         const int blk_stride = (cgs == 4) ? kProducerWarps : 2 * kProducerWarps;
         int cc = 0;  // running chunk counter across tile groups
         int it = 0;
+        PROF_DECL
         for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
             const int b = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
             PixInfo* tab = pixtab + (size_t)b * p.P;
             const int qbase = tg * group_positions - p.Wp - 1;
             mbar_wait(&acc_empty[b], (k & 1) ^ 1);  // the epilogue of group it-2 no longer reads table b
+            PROF_MARK(0)
             for (int i = threadIdx.x; i < p.P; i += kProducerWarps * 32) tab[i] = decode_position(qbase + i, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (lane == 0) mbar_arrive(&tab_full[b]);
+            PROF_MARK(1)
             int si = 0, src_c0 = 0;  // current source and its first concatenated channel
             for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                 const int s = cc % p.S;
@@ -133,14 +148,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                 }
                 const int ch = cglob - src_c0 + cg * 8;  // channel inside the source
                 mbar_wait(&empty[s], ph ^ 1);
+                PROF_MARK(2)
                 uint8_t* dstA = sA + (size_t)s * a_bytes + (size_t)cg * p.P * 16;
                 stage_blocks_mode<MODE>(p.src[si], p.H, p.W, tab, 0, p.P, first_blk, nblk, blk_stride, pl, ch, s_scale + cglob + cg * 8,
                                       s_shift + cglob + cg * 8, s_k2 + cglob + cg * 8, dstA);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
+                PROF_MARK(3)
             }
         }
+        if (threadIdx.x == 0) PROF_FLUSH(0)
     } else if (warp < kMmaWarp) {
         // =============================== epilogue (4 warps, one TMEM lane quadrant each)
         const int lq = warp & 3;
@@ -149,12 +167,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
         const bool want_stats = p.stat_part != nullptr;
         float* my_stat = s_stat + (size_t)lq * 2 * p.NT;
         int it = 0;
+        PROF_DECL
         for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
             const int b = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
             const PixInfo* tab = pixtab + (size_t)b * p.P;
             mbar_wait(&tab_full[b], k & 1);
             mbar_wait(&acc_full[b], k & 1);
+            PROF_MARK(0)
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);
             for (int cs = 0; cs < nslab; ++cs) {
@@ -216,7 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[b]);
+            PROF_MARK(1)
         }
+        if (warp == kEpilogueWarp0 && lane == 0) PROF_FLUSH(4)
         if (want_stats) {
             asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps only
             float* dst = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n_tile * p.NT;
@@ -243,16 +265,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3));
             int cc = 0, it = 0;
+            PROF_DECL
             for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
                 const int b = it & 1;
                 const uint32_t k = (uint32_t)(it >> 1);
                 mbar_wait(&acc_empty[b], (k & 1) ^ 1);
+                PROF_MARK(0)
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(b * p.T * p.NT);
                 for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                     const int s = cc % p.S;
                     const uint32_t ph = (uint32_t)(cc / p.S) & 1;
                     mbar_wait(&full[s], ph);
+                    PROF_MARK(1)
                     tc_fence_after();
                     const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA + (size_t)s * a_bytes), a_lbo);
                     const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB + (size_t)s * b_bytes), b_lbo);
@@ -277,9 +302,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                         }
                     }
                     umma_commit(&empty[s]);
+                    PROF_MARK(2)
                 }
                 umma_commit(&acc_full[b]);
             }
+            PROF_FLUSH(8)
         }
         __syncwarp();
     } else {
@@ -287,15 +314,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)n_tile * p.nchunks * b_bytes;
             int cc = 0;
+            PROF_DECL
             for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x) {
                 for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                     const int s = cc % p.S;
                     const uint32_t ph = (uint32_t)(cc / p.S) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
+                    PROF_MARK(0)
                     mbar_arrive_expect_tx(&full[s], b_bytes);
                     bulk_g2s(sB + (size_t)s * b_bytes, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
+                    PROF_MARK(1)
                 }
             }
+            PROF_FLUSH(12)
         }
         __syncwarp();
     }
@@ -461,6 +492,18 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     }
     return NUNET_E_UNSUPPORTED;  // source-kind combination outside {input | same* | pool | same*+up | grad}
 }
+
+#ifdef NUNET_PROFILE_WAITS
+extern "C" int nunet_debug_read_wait_prof(unsigned long long* out16, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_wait_prof, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_wait_prof, z, sizeof(z));
+    }
+    return e == cudaSuccess ? 0 : NUNET_E_CUDA + (int)e;
+}
+#endif
 
 extern "C" int nunet_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t mode, const nunet_conv_plan_t* pl,
                                   void* wpack, void* stream) {

@@ -1,0 +1,95 @@
+"""Data-parallel parity on 2 GPUs: 2 ranks x batch 2 with SyncBN + bucketed gradient all-reduce must reproduce the
+single-process step on the concatenated batch of 4 (same loss, logits, gradients, running statistics)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _setup_paths():
+    for p in (ROOT, os.path.join(ROOT, "pytorch_nested-unet_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def _batch():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 3, 64, 64, generator=g)
+    t = (torch.rand(4, 1, 64, 64, generator=g) > 0.5).float()
+    return x, t
+
+
+def _step(model, x, t):
+    import losses
+    import metrics
+    crit = losses.BCEDiceLoss()
+    out = model(x)
+    loss = sum(crit(o, t) for o in out) / len(out)
+    counts = metrics.iou_counts(out[-1], t)
+    loss.backward()
+    return out, loss, counts
+
+
+def _worker(rank, world, port, q):
+    _setup_paths()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import archs
+    import dist as nd
+    torch.manual_seed(0)
+    model = nd.DataParallel(archs.NestedUNet(1, 3, True).cuda(), sync_bn=True, bucket_bytes=1 << 20)
+    x, t = _batch()
+    xs, ts = x[rank * 2:(rank + 1) * 2].cuda(), t[rank * 2:(rank + 1) * 2].cuda()
+    out, loss, counts = _step(model, xs, ts)
+    gl = nd.global_mean(float(loss.detach()), xs.device)
+    giou = nd.global_iou_score(out[-1], ts)
+    torch.cuda.synchronize()
+    res = {"rank": rank, "loss": gl, "iou": giou, "logits": out[-1].detach().cpu(),
+           "grads": {k: p.grad.detach().cpu() for k, p in model.module.named_parameters()},
+           "rm": model.module.conv2_0.bn1.running_mean.cpu(), "rv": model.module.conv0_4.bn2.running_var.cpu()}
+    q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_dp2_syncbn_equals_single_process_global_batch():
+    _setup_paths()
+    import archs
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r["rank"])
+    for p in procs:
+        p.join(timeout=120)
+    # single-process reference on the global batch (same engine, one GPU)
+    torch.manual_seed(0)
+    model = archs.NestedUNet(1, 3, True).cuda()
+    x, t = _batch()
+    out, loss, counts = _step(model, x.cuda(), t.cuda())
+    torch.cuda.synchronize()
+    assert abs(res[0]["loss"] - float(loss.detach())) < 2e-5 and abs(res[1]["loss"] - res[0]["loss"]) < 1e-9
+    I, U = counts
+    assert res[0]["iou"] == res[1]["iou"]
+    # the statistics are summed in a different order across ranks: a handful of |logit| ~ 1e-6 pixels may flip
+    assert abs(res[0]["iou"] - (I + 1e-5) / (U + 1e-5)) < 2e-3
+    both = torch.cat([res[0]["logits"], res[1]["logits"]])
+    assert float((both - out[-1].detach().cpu()).abs().max()) <= 2e-3 * float(out[-1].abs().max())
+    named = dict(model.named_parameters())
+    for k, g0 in res[0]["grads"].items():
+        assert torch.equal(g0, res[1]["grads"][k]), k                      # all ranks hold the same averaged gradient
+        r = named[k].grad.cpu()
+        rel = float((g0 - r).norm() / (r.norm() + 1e-12))
+        assert rel <= 3e-2 or float(r.norm()) < 1e-9, (k, rel)
+    assert torch.allclose(res[0]["rm"], model.conv2_0.bn1.running_mean.cpu(), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(res[0]["rv"], model.conv0_4.bn2.running_var.cpu(), rtol=1e-4, atol=1e-6)

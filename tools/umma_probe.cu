@@ -14,6 +14,8 @@
 
 using namespace nunet;
 
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
+
 struct ProbeArgs {
     const uint8_t* a_img; uint32_t a_bytes;
     const uint8_t* b_img; uint32_t b_bytes;
@@ -70,10 +72,71 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
     if (threadIdx.x < 32) tmem_dealloc<512>(tb);
 }
 
+__global__ void __launch_bounds__(128, 1) rate_kernel(ProbeArgs p, int reps, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    // operands: whatever bytes are in smem (zero-filled); only timing matters
+    for (uint32_t i = threadIdx.x * 16; i < p.a_bytes + p.b_bytes + 2048; i += blockDim.x * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tb = tmem_base;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + ((p.a_bytes + 1023u) & ~1023u);
+    if (threadIdx.x == 0) {
+        const uint32_t a_lo0 = p.mode == 0 ? umma_desc_lo(smem_u32(sa), p.a_lbo) : (uint32_t)(umma_desc_sw128(smem_u32(sa), p.a_sbo) & 0xffffffffu);
+        const uint32_t b_lo0 = p.mode == 0 ? umma_desc_lo(smem_u32(sb), p.b_lbo) : (uint32_t)(umma_desc_sw128(smem_u32(sb), p.b_sbo) & 0xffffffffu);
+        const uint32_t a_hi = p.mode == 0 ? umma_desc_hi(p.a_sbo) : (uint32_t)(umma_desc_sw128(smem_u32(sa), p.a_sbo) >> 32);
+        const uint32_t b_hi = p.mode == 0 ? umma_desc_hi(p.b_sbo) : (uint32_t)(umma_desc_sw128(smem_u32(sb), p.b_sbo) >> 32);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k)
+                umma_bf16_lohi(tb + (k & 1) * p.ncols, a_lo0 + (k & 3) * (p.a_kstep >> 4), a_hi, b_lo0 + (k & 3) * (p.b_kstep >> 4), b_hi, p.idesc, 1u);
+        }
+        umma_commit(&bar);
+        while (!mbar_try_wait(&bar, 0)) {}
+        long long t1 = clock64();
+        cycles[0] = t1 - t0;
+    }
+    __syncthreads();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tb);
+}
+
+int run_rate_test(const char* name, int M, int N, int amaj, int bmaj) {
+    // layouts as in run_gemm_test with nk = 4 K-steps available to cycle through
+    ProbeArgs p{};
+    const int K = 64;
+    if (amaj == 0) { p.a_lbo = M * 16; p.a_sbo = 128; p.a_kstep = 2 * p.a_lbo; p.a_bytes = M * K * 2; }
+    else if (amaj == 1) { p.a_lbo = 128; p.a_sbo = K * 16; p.a_kstep = 256; p.a_bytes = M * K * 2; }
+    else { p.a_lbo = 16; p.a_sbo = 1024; p.a_kstep = 32; p.a_bytes = M * 128; }
+    if (bmaj == 0) { p.b_lbo = N * 16; p.b_sbo = 128; p.b_kstep = 2 * p.b_lbo; p.b_bytes = N * K * 2; }
+    else if (bmaj == 1) { p.b_lbo = 128; p.b_sbo = K * 16; p.b_kstep = 256; p.b_bytes = N * K * 2; }
+    else { p.b_lbo = 16; p.b_sbo = 1024; p.b_kstep = 32; p.b_bytes = N * 128; }
+    p.mode = (amaj == 2) ? 1 : 0;
+    p.idesc = umma_idesc_bf16(M, N, amaj == 1 ? kMajorMN : kMajorK, bmaj == 1 ? kMajorMN : kMajorK);
+    p.ncols = N;
+    long long* dc; CK(cudaMalloc(&dc, 8));
+    uint32_t smem_bytes = ((p.a_bytes + 1023u) & ~1023u) + p.b_bytes + 4096;
+    CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int reps = 2000;
+    for (int it = 0; it < 2; ++it) { rate_kernel<<<1, 128, smem_bytes>>>(p, reps, dc); CK(cudaDeviceSynchronize()); }
+    long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+    double per = (double)c / (reps * 8.0);
+    printf("[rate %s] M=%d N=%d: %.1f cycles per MMA (K=16)  -> %.0f MAC/cycle/SM (peak 4096)\n", name, M, N, per, (double)M * N * 16 / per);
+    cudaFree(dc);
+    return 0;
+}
+
 static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }  // exact for small ints
 static float rnd_small(uint32_t& s) { s = s * 1664525u + 1013904223u; return (float)((int)((s >> 24) % 5) - 2); }
 
-#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
 
 struct Layout {  // byte offset of element (row, k) inside an operand image
     int major;    // 0 K-major nosw, 1 MN-major nosw, 2 sw128 K-major
@@ -183,6 +246,13 @@ int main(int argc, char** argv) {
         case 11: return run_gemm_test("nosw A=K B=MN", 128, 64, 4, 0, 1, 7, 3, 2, 6, 0);
         case 12: return run_gemm_test("nosw MNMN M=64", 64, 64, 2, 1, 1, 5, 5, 4, 4, 0);
         case 13: return run_gemm_test("nosw KK N=48", 128, 48, 2, 0, 0, 2, 0, 7, 0, 0);
+        case 100: run_rate_test("nosw KK", 128, 32, 0, 0); run_rate_test("nosw KK", 128, 64, 0, 0); run_rate_test("nosw KK", 128, 128, 0, 0);
+                  return run_rate_test("nosw KK", 128, 256, 0, 0);
+        case 101: run_rate_test("sw128 KK", 128, 32, 2, 2); run_rate_test("sw128 KK", 128, 64, 2, 2); run_rate_test("sw128 KK", 128, 128, 2, 2);
+                  return run_rate_test("sw128 KK", 128, 256, 2, 2);
+        case 102: run_rate_test("nosw MNMN", 128, 32, 1, 1); run_rate_test("nosw MNMN", 128, 64, 1, 1); run_rate_test("nosw MNMN", 128, 128, 1, 1);
+                  return run_rate_test("nosw MNMN", 128, 256, 1, 1);
+        case 103: run_rate_test("nosw A=K B=MN", 128, 32, 0, 1); return run_rate_test("nosw A=MN B=K", 128, 32, 1, 0);
     }
     return 0;
 }
