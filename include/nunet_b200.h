@@ -27,7 +27,13 @@ enum {
     NUNET_SRC_SAME = 1,  /* relu(scale*y+shift) of a raw conv output y at the same resolution (bf16 NHWC)       */
     NUNET_SRC_POOL = 2,  /* 2x2 max-pool of relu(scale*y+shift), y at (2H,2W)   — finished/archs1.py:82        */
     NUNET_SRC_UP = 3,    /* bilinear 2x (align_corners=True) of relu(scale*y+shift), y at (H/2,W/2) — :83       */
-    NUNET_SRC_GRAD = 4   /* backward operand: scale*gz + k2*y + shift (BatchNorm backward folded into loader)   */
+    NUNET_SRC_GRAD = 4,  /* backward operand: scale*gz + k2*y + shift (BatchNorm backward folded into loader)   */
+    /* The same three skip-pathway kinds reading an ALREADY ACTIVATED bf16 NHWC tensor a = relu(scale*y+shift)
+     * (written once per node output by nunet_bn_apply because up to ten loaders re-read it): no BN math in the loader,
+     * and the same-resolution kind is staged with cp.async (global -> shared, zero-filled padding) without registers. */
+    NUNET_SRC_ACT = 5,
+    NUNET_SRC_POOL_ACT = 6,
+    NUNET_SRC_UP_ACT = 7
 };
 
 typedef struct {
@@ -92,6 +98,9 @@ int nunet_bn_finalize_from_sums(const double* sums, int32_t C, double count, con
                                 const float* conv_bias, float* running_mean, float* running_var, float momentum,
                                 float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                                 void* stream);
+/* a = relu(scale*y + shift), bf16 NHWC -> bf16 NHWC (nn.BatchNorm2d apply + ReLU of a node output that several later
+ * convolutions consume, finished/archs1.py:29-30). npix = N*H*W, C % 8 == 0. */
+int nunet_bn_apply(const void* y, const float* scale, const float* shift, long long npix, int32_t C, void* a, void* stream);
 /* Eval mode: scale = gamma*rsqrt(running_var+eps), shift = beta + (conv_bias - running_mean)*scale. */
 int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
                        const float* running_mean, const float* running_var, float eps, float* scale, float* shift,

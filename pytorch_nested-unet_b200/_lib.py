@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnunet_b200.so")
 
 MAX_SRC = 5
-SRC_INPUT, SRC_SAME, SRC_POOL, SRC_UP, SRC_GRAD = 0, 1, 2, 3, 4
+SRC_INPUT, SRC_SAME, SRC_POOL, SRC_UP, SRC_GRAD, SRC_ACT, SRC_POOL_ACT, SRC_UP_ACT = 0, 1, 2, 3, 4, 5, 6, 7
+ACT_KIND = {SRC_SAME: SRC_ACT, SRC_POOL: SRC_POOL_ACT, SRC_UP: SRC_UP_ACT}
 PACK_FWD, PACK_DGRAD = 0, 1
 
 
@@ -79,6 +80,7 @@ _SIGS = {
     "nunet_bn_backward_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 8 + [C.c_float, C.c_void_p], C.c_int),
     "nunet_conv3x3_wgrad_plan": ([C.c_int32] * 5 + [C.POINTER(WgradPlan)], C.c_int),
     "nunet_conv3x3_wgrad": ([C.POINTER(WgradDesc), C.c_void_p], C.c_int),
+    "nunet_bn_apply": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
 }
 

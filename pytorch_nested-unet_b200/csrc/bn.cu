@@ -119,6 +119,39 @@ __global__ void bn_fold_eval_kernel(int C, const float* gamma, const float* beta
     shift[c] = beta[c] + ((bias ? bias[c] : 0.f) - rm[c]) * sc;
 }
 
+// a = relu(scale*y+shift): one 16-byte group (8 channels) per thread-iteration, fully coalesced, HBM-bound.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, long long ngroups, int cgs, uint4* __restrict__ a) {
+    extern __shared__ float s_coef[];  // [2][C]
+    const int C = cgs * 8;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_coef[i] = scale[i]; s_coef[C + i] = shift[i]; }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups; g += 4 * stride) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (g + u * stride < ngroups) r[u] = __ldg(y + g + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long gi = g + u * stride;
+            if (gi >= ngroups) continue;
+            const int c0 = (int)(gi % cgs) * 8;
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r[u]);
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                const float v0 = fmaxf(fmaf(t.x, s_coef[c0 + 2 * i], s_coef[C + c0 + 2 * i]), 0.f);
+                const float v1 = fmaxf(fmaf(t.y, s_coef[c0 + 2 * i + 1], s_coef[C + c0 + 2 * i + 1]), 0.f);
+                __nv_bfloat162 q = __floats2bfloat162_rn(v0, v1);
+                o[i] = *reinterpret_cast<uint32_t*>(&q);
+            }
+            a[gi] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -183,5 +216,14 @@ extern "C" int nunet_bn_backward_from_sums(const double* sums, int32_t C, double
     f.save_invstd = const_cast<float*>(save_invstd); f.dgamma = dgamma; f.dbeta = dbeta; f.k1 = k1; f.k2 = k2; f.k3 = k3;
     f.grad_scale = grad_scale;
     bn_finalize_from_sums_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, f);
+    return cuda_rc();
+}
+
+extern "C" int nunet_bn_apply(const void* y, const float* scale, const float* shift, long long npix, int32_t C, void* a, void* stream) {
+    if (!y || !scale || !shift || !a || npix <= 0 || C <= 0 || C % 8 != 0 || C > 4096) return NUNET_E_BADARG;
+    const long long ngroups = npix * (C / 8);
+    long long blocks = (ngroups + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bn_apply_kernel<<<(int)blocks, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)y, scale, shift, ngroups, C / 8, (uint4*)a);
     return cuda_rc();
 }

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             const ConvSrc& s = p.src[si];
             const int cpad = (s.kind == NUNET_SRC_INPUT) ? 16 : s.C;
             for (int c = threadIdx.x; c < cpad; c += kThreads) {
-                const bool has = (s.kind != NUNET_SRC_INPUT);
+                const bool has = (s.kind != NUNET_SRC_INPUT) && s.scale != nullptr;
                 s_scale[cbase + c] = has ? s.scale[c] : 1.f;
                 s_shift[cbase + c] = has ? s.shift[c] : 0.f;
                 s_k2[cbase + c] = (s.kind == NUNET_SRC_GRAD) ? s.k2[c] : 0.f;
@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                 uint8_t* dstA = sA + (size_t)s * a_bytes + (size_t)cg * p.P * 16;
                 stage_blocks_mode<MODE>(p.src[si], p.H, p.W, tab, 0, p.P, first_blk, nblk, blk_stride, pl, ch, s_scale + cglob + cg * 8,
                                       s_shift + cglob + cg * 8, s_k2 + cglob + cg * 8, dstA);
+                if constexpr (MODE == MODE_ACT || MODE == MODE_ACT_UP) {
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
@@ -460,9 +464,10 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
             if (s.C < 1 || s.C > 16 || d->num_src != 1) return NUNET_E_UNSUPPORTED;
             cin += 16;
         } else {
-            if (s.C % 32 != 0 || !s.scale || !s.shift) return NUNET_E_BADARG;
+            const bool act = (s.kind == NUNET_SRC_ACT || s.kind == NUNET_SRC_POOL_ACT || s.kind == NUNET_SRC_UP_ACT);
+            if (s.C % 32 != 0 || (!act && (!s.scale || !s.shift))) return NUNET_E_BADARG;
             if (s.kind == NUNET_SRC_GRAD && (!s.data2 || !s.k2)) return NUNET_E_BADARG;
-            if ((s.kind == NUNET_SRC_UP) && ((d->H | d->W) & 1)) return NUNET_E_UNSUPPORTED;
+            if ((s.kind == NUNET_SRC_UP || s.kind == NUNET_SRC_UP_ACT) && ((d->H | d->W) & 1)) return NUNET_E_UNSUPPORTED;
             cin += s.C;
         }
     }
@@ -489,6 +494,9 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
         case MODE_POOL: return launch_conv<MODE_POOL>(p, pl, (cudaStream_t)stream);
         case MODE_SAME_UP: return launch_conv<MODE_SAME_UP>(p, pl, (cudaStream_t)stream);
         case MODE_GRAD: return launch_conv<MODE_GRAD>(p, pl, (cudaStream_t)stream);
+        case MODE_ACT: return launch_conv<MODE_ACT>(p, pl, (cudaStream_t)stream);
+        case MODE_POOL_ACT: return launch_conv<MODE_POOL_ACT>(p, pl, (cudaStream_t)stream);
+        case MODE_ACT_UP: return launch_conv<MODE_ACT_UP>(p, pl, (cudaStream_t)stream);
     }
     return NUNET_E_UNSUPPORTED;  // source-kind combination outside {input | same* | pool | same*+up | grad}
 }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             const ConvSrc& s = p.src[si];
             const int cpad = (s.kind == NUNET_SRC_INPUT) ? 16 : s.C;
             for (int c = threadIdx.x; c < cpad; c += kWThreads) {
-                const bool has = (s.kind != NUNET_SRC_INPUT);
+                const bool has = (s.kind != NUNET_SRC_INPUT) && s.scale != nullptr;
                 s_scale[cbase + c] = has ? s.scale[c] : 1.f;
                 s_shift[cbase + c] = has ? s.shift[c] : 0.f;
             }
@@ -97,12 +97,6 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             mbar_wait(&empty[s], ph ^ 1);
             for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position((int)k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, (int)p.Q);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // ---- gy with halo: 4 channel groups x Pg positions (lane group r = channel group)
-            {
-                uint8_t* dst = sG + (size_t)s * g_bytes + (size_t)r * p.Pg * 16;
-                stage_blocks<NUNET_SRC_GRAD, 4>(p.gsrc, p.H, p.W, tab, 0, p.Pg, warp, (p.Pg + 7) >> 3, kWProducerWarps, pl, n_tile * 32 + r * 8,
-                                                s_g + r * 8, s_g + 64 + r * 8, s_g + 32 + r * 8, dst);
-            }
             // ---- X: mcg channel groups x KP positions (positions [Wp+1, Wp+1+KP) of the table), one quad of channel
             //      groups (= 32 channels, never straddling a source) per pass
             {
@@ -122,6 +116,16 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
                     stage_blocks_mode<MODE>(p.src[si], p.H, p.W, tab, p.Wp + 1, p.KP, warp, p.KP >> 3, kWProducerWarps, pl, cglob - c0, s_scale + cglob,
                                           s_shift + cglob, s_scale + cglob, dst);
                 }
+            }
+            // ---- gy with halo: 4 channel groups x Pg positions (lane group r = channel group)
+            {
+                uint8_t* dst = sG + (size_t)s * g_bytes + (size_t)r * p.Pg * 16;
+                stage_blocks<NUNET_SRC_GRAD, 4>(p.gsrc, p.H, p.W, tab, 0, p.Pg, warp, (p.Pg + 7) >> 3, kWProducerWarps, pl, n_tile * 32 + r * 8,
+                                                s_g + r * 8, s_g + 64 + r * 8, s_g + 32 + r * 8, dst);
+            }
+            if constexpr (MODE == MODE_ACT || MODE == MODE_ACT_UP) {
+                cp_async_commit();
+                cp_async_wait<0>();
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -257,7 +261,8 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
             if (s.C < 1 || s.C > 16 || d->num_src != 1) return NUNET_E_UNSUPPORTED;
             cin += 16; cin_real += s.C;
         } else {
-            if (s.kind == NUNET_SRC_GRAD || s.C % 32 != 0 || !s.scale || !s.shift) return NUNET_E_BADARG;
+            const bool act = (s.kind == NUNET_SRC_ACT || s.kind == NUNET_SRC_POOL_ACT || s.kind == NUNET_SRC_UP_ACT);
+            if (s.kind == NUNET_SRC_GRAD || s.C % 32 != 0 || (!act && (!s.scale || !s.shift))) return NUNET_E_BADARG;
             cin += s.C; cin_real += s.C;
         }
     }
@@ -284,6 +289,9 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
         case MODE_SAME: lrc = launch_wgrad<MODE_SAME>(p, pl, (cudaStream_t)stream); break;
         case MODE_POOL: lrc = launch_wgrad<MODE_POOL>(p, pl, (cudaStream_t)stream); break;
         case MODE_SAME_UP: lrc = launch_wgrad<MODE_SAME_UP>(p, pl, (cudaStream_t)stream); break;
+        case MODE_ACT: lrc = launch_wgrad<MODE_ACT>(p, pl, (cudaStream_t)stream); break;
+        case MODE_POOL_ACT: lrc = launch_wgrad<MODE_POOL_ACT>(p, pl, (cudaStream_t)stream); break;
+        case MODE_ACT_UP: lrc = launch_wgrad<MODE_ACT_UP>(p, pl, (cudaStream_t)stream); break;
         default: return NUNET_E_UNSUPPORTED;
     }
     if (lrc) return lrc;

@@ -47,7 +47,7 @@ __device__ __forceinline__ void bn_relu8(const uint4& raw, const float (&sc)[8],
 // Number of 16-byte global loads one item of this kind needs.
 template <int KIND>
 struct LoadsOf {
-    static constexpr int n = (KIND == NUNET_SRC_SAME) ? 1 : (KIND == NUNET_SRC_GRAD || KIND == NUNET_SRC_INPUT) ? 2 : 4;
+    static constexpr int n = (KIND == NUNET_SRC_SAME || KIND == NUNET_SRC_ACT) ? 1 : (KIND == NUNET_SRC_GRAD || KIND == NUNET_SRC_INPUT) ? 2 : 4;
 };
 
 struct UpTaps {  // bilinear taps of one output pixel (ATen area_pixel_compute_scale, align_corners=True)
@@ -79,9 +79,9 @@ __device__ __forceinline__ UpTaps up_taps(int H, int W, PixInfo pi) {
 template <int KIND>
 __device__ __forceinline__ void issue_loads(const ConvSrc& s, int H, int W, PixInfo pi, int ch, uint4 (&r)[LoadsOf<KIND>::n]) {
     const int C = s.C;
-    if constexpr (KIND == NUNET_SRC_SAME) {
+    if constexpr (KIND == NUNET_SRC_SAME || KIND == NUNET_SRC_ACT) {
         r[0] = ldg16(reinterpret_cast<const __nv_bfloat16*>(s.data) + (size_t)pi.pix * C + ch);
-    } else if constexpr (KIND == NUNET_SRC_POOL) {
+    } else if constexpr (KIND == NUNET_SRC_POOL || KIND == NUNET_SRC_POOL_ACT) {
         const int x = pi.yx & 0xffff;
         const size_t base = (size_t)4 * pi.pix - 2 * x;  // (n*2H + 2y)*2W + 2x
         const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(s.data) + base * C + ch;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void issue_loads(const ConvSrc& s, int H, int W, PixI
         r[1] = ldg16(p + C);
         r[2] = ldg16(p + (size_t)2 * W * C);
         r[3] = ldg16(p + (size_t)(2 * W + 1) * C);
-    } else if constexpr (KIND == NUNET_SRC_UP) {
+    } else if constexpr (KIND == NUNET_SRC_UP || KIND == NUNET_SRC_UP_ACT) {
         const UpTaps t = up_taps(H, W, pi);
         const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(s.data) + ch;
         r[0] = ldg16(p + (size_t)t.o00 * C);
@@ -137,6 +137,30 @@ __device__ __forceinline__ uint4 finish_item(int H, int W, PixInfo pi, const uin
         bn_relu8(r[3], sc, sh, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = t.ly0 * (t.lx0 * a[i] + t.lx1 * b[i]) + t.ly1 * (t.lx0 * c[i] + t.lx1 * d[i]);
+    } else if constexpr (KIND == NUNET_SRC_ACT) {
+        return r[0];
+    } else if constexpr (KIND == NUNET_SRC_POOL_ACT) {
+        // max of four already-activated bf16 values: exact in bf16x2 arithmetic
+        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r[0]);
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 m = h0[i];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) m = __hmax2(m, reinterpret_cast<const __nv_bfloat162*>(&r[k])[i]);
+            ow[i] = *reinterpret_cast<uint32_t*>(&m);
+        }
+        return o;
+    } else if constexpr (KIND == NUNET_SRC_UP_ACT) {
+        const UpTaps t = up_taps(H, W, pi);
+        float b[8], c[8], d[8];
+        unpack8(r[0], a);
+        unpack8(r[1], b);
+        unpack8(r[2], c);
+        unpack8(r[3], d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = t.ly0 * (t.lx0 * a[i] + t.lx1 * b[i]) + t.ly1 * (t.lx0 * c[i] + t.lx1 * d[i]);
     } else if constexpr (KIND == NUNET_SRC_GRAD) {
         float g[8], y[8];
         unpack8(r[0], g);
@@ -158,11 +182,12 @@ __device__ __forceinline__ void stage_blocks(const ConvSrc& s, int H, int W, con
                                              int first_blk, int nblk, int blk_stride, int pl, int ch, const float* __restrict__ psc,
                                              const float* __restrict__ psh, const float* __restrict__ pk2, uint8_t* dst) {
     constexpr int NL = LoadsOf<KIND>::n;
+    constexpr bool kCoef = (KIND == NUNET_SRC_SAME || KIND == NUNET_SRC_POOL || KIND == NUNET_SRC_UP || KIND == NUNET_SRC_GRAD);
     float sc[8], sh[8], k2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        sc[i] = (KIND != NUNET_SRC_INPUT) ? psc[i] : 1.f;
-        sh[i] = (KIND != NUNET_SRC_INPUT) ? psh[i] : 0.f;
+        sc[i] = kCoef ? psc[i] : 1.f;
+        sh[i] = kCoef ? psh[i] : 0.f;
         k2[i] = (KIND == NUNET_SRC_GRAD) ? pk2[i] : 0.f;
     }
     for (int b0 = first_blk; b0 < nblk; b0 += blk_stride * U) {
@@ -188,9 +213,25 @@ __device__ __forceinline__ void stage_blocks(const ConvSrc& s, int H, int W, con
     }
 }
 
+// Same-resolution pre-activated source: pure copy, issued as cp.async (no registers, many copies in flight per thread;
+// padding positions are zero-filled by a zero-byte source).  The caller commits / waits the cp.async group.
+__device__ __forceinline__ void stage_blocks_cpasync(const ConvSrc& s, const PixInfo* __restrict__ tab, int tab_off, int plimit,
+                                                     int first_blk, int nblk, int blk_stride, int pl, int ch, uint8_t* dst) {
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(s.data) + ch;
+    const int C = s.C;
+    for (int b = first_blk; b < nblk; b += blk_stride) {
+        const int pp = b * 8 + pl;
+        if (pp < plimit) {
+            const int pix = tab[pp + tab_off].pix;
+            const bool ok = pix >= 0;
+            cp_async16(dst + (size_t)pp * 16, base + (size_t)(ok ? pix : 0) * C, ok ? 16u : 0u);
+        }
+    }
+}
+
 // Source-kind combinations that occur in the network; the conv kernels are specialised on them so that only the loader
 // variants a launch can need are compiled into it (keeps the producer loop in registers).
-enum { MODE_INPUT = 0, MODE_SAME = 1, MODE_POOL = 2, MODE_SAME_UP = 3, MODE_GRAD = 4 };
+enum { MODE_INPUT = 0, MODE_SAME = 1, MODE_POOL = 2, MODE_SAME_UP = 3, MODE_GRAD = 4, MODE_ACT = 5, MODE_POOL_ACT = 6, MODE_ACT_UP = 7 };
 
 template <int MODE>
 __device__ __forceinline__ void stage_blocks_mode(const ConvSrc& s, int H, int W, const PixInfo* __restrict__ tab, int tab_off, int plimit,
@@ -204,6 +245,15 @@ __device__ __forceinline__ void stage_blocks_mode(const ConvSrc& s, int H, int W
         stage_blocks<NUNET_SRC_POOL, 2>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
     } else if constexpr (MODE == MODE_GRAD) {
         stage_blocks<NUNET_SRC_GRAD, 4>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
+    } else if constexpr (MODE == MODE_ACT) {
+        stage_blocks_cpasync(s, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, dst);
+    } else if constexpr (MODE == MODE_POOL_ACT) {
+        stage_blocks<NUNET_SRC_POOL_ACT, 2>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
+    } else if constexpr (MODE == MODE_ACT_UP) {
+        if (s.kind == NUNET_SRC_UP_ACT)
+            stage_blocks<NUNET_SRC_UP_ACT, 2>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
+        else
+            stage_blocks_cpasync(s, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, dst);
     } else {
         if (s.kind == NUNET_SRC_UP)
             stage_blocks<NUNET_SRC_UP, 2>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
@@ -221,8 +271,19 @@ static inline int sources_mode(const int* kinds, int n) {
             case NUNET_SRC_POOL: return MODE_POOL;
             case NUNET_SRC_GRAD: return MODE_GRAD;
             case NUNET_SRC_UP: return MODE_SAME_UP;
+            case NUNET_SRC_ACT: return MODE_ACT;
+            case NUNET_SRC_POOL_ACT: return MODE_POOL_ACT;
+            case NUNET_SRC_UP_ACT: return MODE_ACT_UP;
         }
         return -1;
+    }
+    if (kinds[0] == NUNET_SRC_ACT || kinds[0] == NUNET_SRC_UP_ACT) {
+        for (int i = 0; i < n; ++i) {
+            if (kinds[i] == NUNET_SRC_ACT) continue;
+            if (kinds[i] == NUNET_SRC_UP_ACT && i == n - 1) continue;
+            return -1;
+        }
+        return (kinds[n - 1] == NUNET_SRC_UP_ACT) ? MODE_ACT_UP : MODE_ACT;
     }
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);

@@ -14,6 +14,9 @@ import _lib as L
 import ops
 
 NB_FILTER = (32, 64, 128, 256, 512)
+# Node outputs (up to 5 forward + 5 wgrad loaders re-read each) are activated once into a bf16 tensor; False = every
+# loader applies BatchNorm+ReLU itself from the raw conv output.
+MATERIALIZE_NODE_OUTPUTS = True
 
 
 # --------------------------------------------------------------------------------------------- graphs
@@ -135,7 +138,23 @@ def _world(model):
 
 
 class _Record(object):
-    __slots__ = ("y", "scale", "shift", "mean", "invstd", "h", "w")
+    __slots__ = ("y", "a", "scale", "shift", "mean", "invstd", "h", "w")
+
+
+def _sources(spec, recs, x):
+    """Loader descriptors of a conv: node outputs are read from their materialised activation (copy / pool / upsample
+    loaders without BN math), a block's first conv output through the fused BN+ReLU loader."""
+    srcs = []
+    for pi, kind, c in spec.sources:
+        if pi < 0:
+            srcs.append(ops.Source(kind, x, c))
+        else:
+            r = recs[pi]
+            if r.a is not None:
+                srcs.append(ops.Source(L.ACT_KIND[kind], r.a, c))
+            else:
+                srcs.append(ops.Source(kind, r.y, c, r.scale, r.shift))
+    return srcs
 
 
 def _forward(model, x, train):
@@ -157,18 +176,12 @@ def _forward(model, x, train):
     recs = []
     for s in specs:
         h, w = H >> s.level, W >> s.level
-        srcs = []
-        for pi, kind, c in s.sources:
-            if pi < 0:
-                srcs.append(ops.Source(kind, x, c))
-            else:
-                r = recs[pi]
-                srcs.append(ops.Source(kind, r.y, c, r.scale, r.shift))
+        srcs = _sources(s, recs, x)
         plan = ops.conv_plan(N, h, w, s.cin_pad, s.cout)
         wp = st.pack(s, plan, L.PACK_FWD)
         y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
         r = _Record()
-        r.y, r.h, r.w = y, h, w
+        r.y, r.h, r.w, r.a = y, h, w, None
         r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
         r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
         bn = s.bn
@@ -193,6 +206,8 @@ def _forward(model, x, train):
         else:
             r.mean = r.invstd = None
             ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
+        if s.which == 2 and MATERIALIZE_NODE_OUTPUTS and s.consumers:
+            r.a = ops.bn_apply(y, r.scale, r.shift)
         recs.append(r)
     if train:
         nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]
@@ -261,13 +276,7 @@ def _backward(model, x, recs, grad_logits):
                                       grad_scale=1.0 / dp.world_size)
         gdone(s.bn.weight, dgamma)
         gdone(s.bn.bias, dbeta)
-        srcs = []
-        for pi, kind, c in s.sources:
-            if pi < 0:
-                srcs.append(ops.Source(kind, x, c))
-            else:
-                pr = recs[pi]
-                srcs.append(ops.Source(kind, pr.y, c, pr.scale, pr.shift))
+        srcs = _sources(s, recs, x)
         dw = galloc(s.conv.weight)
         ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gz, r.y, k1, k2, k3, dw)
         gdone(s.conv.weight, dw)

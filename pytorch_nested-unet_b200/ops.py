@@ -151,6 +151,15 @@ def bn_finalize_from_sums(sums, count, gamma, beta, conv_bias, running_mean, run
         _stream())
 
 
+def bn_apply(y, scale, shift, out=None):
+    """a = relu(scale*y+shift), bf16 NHWC -> bf16 NHWC (materialised once for node outputs that many loaders re-read)."""
+    if out is None:
+        out = torch.empty_like(y)
+    Cc = y.shape[-1]
+    _call("bn_apply", 1, None, "nunet_bn_apply", L.lib().nunet_bn_apply, _ptr(y), _ptr(scale), _ptr(shift), y.numel() // Cc, Cc, _ptr(out), _stream())
+    return out
+
+
 def bn_fold_eval(gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift):
     _call("bn_fold", 1, None, "nunet_bn_fold_eval", L.lib().nunet_bn_fold_eval, gamma.numel(), _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
                                        _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), _stream())

@@ -130,6 +130,10 @@ WG_CASES = [
     (2, 6, 6, [("same", 512)], 512),
     (3, 12, 20, [("same", 32), ("same", 32), ("same", 32), ("same", 32), ("up", 64)], 32),
     (8, 96, 96, [("same", 32), ("up", 64)], 32),
+    (2, 32, 32, [("same_act", 32), ("same_act", 32), ("up_act", 64)], 32),
+    (2, 8, 8, [("pool_act", 64)], 128),
+    (8, 96, 96, [("same_act", 32), ("up_act", 64)], 32),
+    (2, 6, 6, [("same_act", 256), ("up_act", 512)], 256),
 ]
 
 

@@ -9,10 +9,19 @@ def _mk_src(kind, N, H, W, C, gen, dev):
     """Random raw producer output at the resolution the kind implies + random BN coefficients (both signs)."""
     import _lib as L
     import ops
-    hs, ws = {"same": (H, W), "pool": (2 * H, 2 * W), "up": (H // 2, W // 2)}[kind]
+    base = kind.replace("_act", "")
+    hs, ws = {"same": (H, W), "pool": (2 * H, 2 * W), "up": (H // 2, W // 2)}[base]
     y = (torch.randn(N, hs, ws, C, generator=gen, device=dev) * 1.5).to(torch.bfloat16)
     scale = torch.randn(C, generator=gen, device=dev)
     shift = torch.randn(C, generator=gen, device=dev) * 0.5
+    if kind.endswith("_act"):
+        # pre-activated source: the loader reads a = relu(scale*y+shift) materialised by nunet_bn_apply
+        a = ops.bn_apply(y, scale, shift)
+        ref_a = torch.relu(y.float() * scale + shift)
+        assert bool(((a.float() - ref_a).abs() <= 0.008 * ref_a.abs() + 1e-6).all())   # fma vs mul+add: at most one bf16 ulp
+        k = {"same": L.SRC_ACT, "pool": L.SRC_POOL_ACT, "up": L.SRC_UP_ACT}[base]
+        one, zero = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        return ops.Source(k, a, C), (base, a, one, zero)
     k = {"same": L.SRC_SAME, "pool": L.SRC_POOL, "up": L.SRC_UP}[kind]
     return ops.Source(k, y, C, scale, shift), (kind, y, scale, shift)
 
@@ -33,6 +42,12 @@ CASES = [
     (3, 48, 80, [("same", 32), ("up", 64)], 32),
     (16, 96, 96, [("same", 32)], 32),
     (16, 48, 48, [("same", 64), ("up", 128)], 64),
+    (2, 32, 32, [("same_act", 32)], 32),
+    (2, 16, 16, [("pool_act", 32)], 64),
+    (2, 32, 32, [("same_act", 32), ("same_act", 32), ("same_act", 32), ("same_act", 32), ("up_act", 64)], 32),
+    (3, 12, 20, [("same_act", 256), ("up_act", 512)], 256),
+    (16, 96, 96, [("same_act", 32), ("up_act", 64)], 32),
+    (2, 6, 6, [("up_act", 512)], 256),
 ]
 
 

@@ -113,7 +113,7 @@ def test_train_step_and_eval_against_reference_golden(name):
     opt.step()
     for k, n_ref in g["param_after_norms"].items():
         if sd[k].is_floating_point() and "running" not in k:
-            assert abs(float(model.state_dict()[k].float().norm()) - n_ref) <= 1e-3 * max(n_ref, 1e-6) + 1e-6, k
+            assert abs(float(model.state_dict()[k].float().norm()) - n_ref) <= 1e-3 * max(n_ref, 1e-6) + 1e-5, k  # zero-initialised BN biases: after one step their norm is lr*|grad|
     # val.py-style eval forward with the post-step weights and running statistics
     model.eval()
     with torch.no_grad():
