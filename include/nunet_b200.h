@@ -158,11 +158,16 @@ int nunet_bn_backward_from_sums(const double* sums, int32_t C, double count, con
                                 const float* save_invstd, float* dgamma, float* dbeta, float* k1, float* k2, float* k3,
                                 float grad_scale, void* stream);
 
+/* g_y = k1*g_z + k2*y + k3 (bf16 NHWC, may alias gz): the affine rest of BatchNorm backward, materialised once because
+ * both dgrad (as a pre-activated NUNET_SRC_ACT source) and every wgrad CTA re-read it. */
+int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1, const float* k2, const float* k3, long long npix,
+                       int32_t C, void* gy, void* stream);
+
 /* ---- weight gradient (autograd of nn.Conv2d, finished/archs1.py:18,20) --------------------------------------------------
  * dw[co][ci][3][3] (fp32 OIHW, overwritten) = sum over pixels of g_y (x) X, with X read through the same fused loaders
- * as the forward conv (src[]) and g_y = k1*gz + k2*y + k3.  part: plan.part_elems fp32 of scratch. */
+ * as the forward conv (src[]).  part: plan.part_elems fp32 of scratch. */
 typedef struct {
-    int32_t KP, S, Pg, cpc, nchunks_total, splits, m_tiles, n_tiles, cin_pad, smem_bytes;
+    int32_t KP, S, Pg, cpc, nchunks_total, splits, m_tiles, n_tiles, cin_pad, smem_bytes, triple;
     int64_t part_elems;
 } nunet_wgrad_plan_t;
 typedef struct {
@@ -170,9 +175,7 @@ typedef struct {
     int32_t num_src;
     nunet_src_t src[NUNET_MAX_SRC];
     int32_t Cout;
-    const void* gz; /* bf16 NHWC [N,H,W,Cout] */
-    const void* y;  /* raw conv output, bf16 NHWC */
-    const float *k1, *k2, *k3;
+    const void* gy; /* bf16 NHWC [N,H,W,Cout]: g_y = k1*g_z + k2*y + k3 from nunet_bn_bwd_apply */
     float* part;
     float* dw;
 } nunet_wgrad_desc_t;

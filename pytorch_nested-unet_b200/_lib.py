@@ -42,13 +42,12 @@ class RouterDesc(C.Structure):
 
 class WgradPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("KP", "S", "Pg", "cpc", "nchunks_total", "splits", "m_tiles", "n_tiles", "cin_pad",
-                                         "smem_bytes")] + [("part_elems", C.c_int64)]
+                                         "smem_bytes", "triple")] + [("part_elems", C.c_int64)]
 
 
 class WgradDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_src", C.c_int32), ("src", Src * MAX_SRC),
-                ("Cout", C.c_int32), ("gz", C.c_void_p), ("y", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p),
-                ("k3", C.c_void_p), ("part", C.c_void_p), ("dw", C.c_void_p)]
+                ("Cout", C.c_int32), ("gy", C.c_void_p), ("part", C.c_void_p), ("dw", C.c_void_p)]
 
 
 class NunetError(RuntimeError):
@@ -81,6 +80,7 @@ _SIGS = {
     "nunet_conv3x3_wgrad_plan": ([C.c_int32] * 5 + [C.POINTER(WgradPlan)], C.c_int),
     "nunet_conv3x3_wgrad": ([C.POINTER(WgradDesc), C.c_void_p], C.c_int),
     "nunet_bn_apply": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_bn_bwd_apply": ([C.c_void_p] * 5 + [C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
 }
 

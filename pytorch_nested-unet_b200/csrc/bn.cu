@@ -152,6 +152,42 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
     }
 }
 
+// g_y = k1*g_z + k2*y + k3 per channel; 16-byte groups, coalesced; gy may alias gz.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* gz, const uint4* __restrict__ y, const float* __restrict__ k1,
+                                                           const float* __restrict__ k2, const float* __restrict__ k3, long long ngroups,
+                                                           int cgs, uint4* gy) {
+    extern __shared__ float s_coef[];  // [3][C]
+    const int C = cgs * 8;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_coef[i] = k1[i]; s_coef[C + i] = k2[i]; s_coef[2 * C + i] = k3[i]; }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups; g += 2 * stride) {
+        uint4 rg[2], ry[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (g + u * stride < ngroups) { rg[u] = gz[g + u * stride]; ry[u] = __ldg(y + g + u * stride); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long gi = g + u * stride;
+            if (gi >= ngroups) continue;
+            const int c0 = (int)(gi % cgs) * 8;
+            const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&rg[u]);
+            const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&ry[u]);
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 a = __bfloat1622float2(hg[i]), b = __bfloat1622float2(hy[i]);
+                const int c = c0 + 2 * i;
+                const float v0 = fmaf(a.x, s_coef[c], fmaf(b.x, s_coef[C + c], s_coef[2 * C + c]));
+                const float v1 = fmaf(a.y, s_coef[c + 1], fmaf(b.y, s_coef[C + c + 1], s_coef[2 * C + c + 1]));
+                __nv_bfloat162 q = __floats2bfloat162_rn(v0, v1);
+                o[i] = *reinterpret_cast<uint32_t*>(&q);
+            }
+            gy[gi] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -225,5 +261,16 @@ extern "C" int nunet_bn_apply(const void* y, const float* scale, const float* sh
     long long blocks = (ngroups + 1023) / 1024;
     if (blocks > 148 * 8) blocks = 148 * 8;
     bn_apply_kernel<<<(int)blocks, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)y, scale, shift, ngroups, C / 8, (uint4*)a);
+    return cuda_rc();
+}
+
+extern "C" int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1, const float* k2, const float* k3, long long npix,
+                                  int32_t C, void* gy, void* stream) {
+    if (!gz || !y || !k1 || !k2 || !k3 || !gy || npix <= 0 || C <= 0 || C % 8 != 0 || C > 2048) return NUNET_E_BADARG;
+    const long long ngroups = npix * (C / 8);
+    long long blocks = (ngroups + 511) / 512;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bn_bwd_apply_kernel<<<(int)blocks, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)gz, (const uint4*)y, k1, k2, k3, ngroups,
+                                                                                          C / 8, (uint4*)gy);
     return cuda_rc();
 }

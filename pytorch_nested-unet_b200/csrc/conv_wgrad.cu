@@ -2,44 +2,59 @@
 //
 //   dW[co][ci][tap] = sum_q gy[q][co] * X[q + off(tap)][ci] = sum_q' X[q'][ci] * gy[q' - off(tap)][co]
 // over the flattened padded positions of conv_igemm.cu.  The reduction index (GEMM K) is the POSITION, so both
-// operands are MN-major for the tensor core; the producers stage, per chunk of KP positions,
-//   X  [cgroup(16)][KP][8 ci]        — the conv's virtual input through the FORWARD loaders (BN+ReLU, pool, upsample,
-//                                      concat), unshifted
-//   gy [cgroup(4)][KP + 2Wp + 2][8 co] — k1*g_z + k2*y + k3 (BatchNorm backward folded in), with the halo, so that the
-//                                      nine taps are nine start-address shifts of the SMALL operand.
-// A CTA owns a (128 ci) x (32 co) x (9 taps) accumulator block = 288 TMEM columns and a contiguous range of chunks;
-// partial blocks are written as fp32 and summed in a fixed order by wgrad_reduce_kernel (deterministic).
+// operands are MN-major for the tensor core.  Per chunk of KP positions the producers stage
+//   X   [cgroup(16)][KP][8 ci]            — the conv's virtual input through the FORWARD loaders, unshifted
+//   gy  [dc(3)][cgroup(4)][KP + 2Wp][8 co] — the materialised BatchNorm-backward gradient (nunet_bn_bwd_apply), copied
+//        three times with a one-position stagger, so that for a kernel row dr the twelve (dc, cgroup) planes form ONE
+//        MN-major operand of N = 96 whose start address encodes the row shift (2-dr)*Wp.
+// Each K step (16 positions) therefore issues 3 MMAs of 128x96x16 (~50 cycles each) instead of 9 of 128x32x16
+// (~45 cycles each: the tensor pipe is operand-fetch bound at N=32, tools/umma_probe.cu test 100).
+// A CTA owns a (128 ci) x (32 co) x (9 taps) accumulator block = 288 TMEM columns (column = tap*32 + co) and a
+// contiguous range of chunks; partial blocks are written as fp32 and summed in a fixed order (deterministic).
 #include "conv_common.cuh"
 #include "loaders.cuh"
+#include <cstdlib>
 
 namespace nunet {
 
 struct WgradParams {
     int N, H, W, Wp, Hp1;
     long long Q;
-    int KP, S, Pg, cpc, nchunks_total;
+    int KP, S, Pg, Pg2, cpc, nchunks_total;  // Pg2: positions per gy plane (TRIPLE: KP + 2Wp, else Pg = KP + 2Wp + 2)
     int cin_pad, Cout, num_src;
     ConvSrc src[NUNET_MAX_SRC];
-    ConvSrc gsrc;  // GRAD: data = g_z, data2 = y, scale = k1, k2, shift = k3 ; C = Cout
-    float* part;   // [splits][Cout/32][9][cin_pad][32]
+    const __nv_bfloat16* gy;  // bf16 NHWC [N,H,W,Cout]
+    float* part;              // [splits][Cout/32][9][cin_pad][32]
 };
+
+#ifdef NUNET_PROFILE_WAITS
+__device__ unsigned long long g_wgrad_prof[16];
+#define WPROF_DECL long long prof_t = clock64(); long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+#define WPROF_MARK(slot) { long long now_ = clock64(); prof_acc[slot] += now_ - prof_t; prof_t = now_; }
+#define WPROF_FLUSH(base, n) { for (int i_ = 0; i_ < n; ++i_) atomicAdd(&g_wgrad_prof[(base) + i_], (unsigned long long)prof_acc[i_]); }
+#else
+#define WPROF_DECL
+#define WPROF_MARK(slot) {}
+#define WPROF_FLUSH(base, n) {}
+#endif
 
 constexpr int kWThreads = 320;
 constexpr int kWProducerWarps = 8;
 
-template <int MODE>
+// TRIPLE: three staggered gy copies, 3 MMAs of N=96 per K step; else one gy copy with the full halo and 9 MMAs of N=32
+// per K step (needs a third of the shared memory for gy: wide images).
+template <int MODE, bool TRIPLE>
 __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const WgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t x_bytes = 16u * p.KP * 16u;
-    const uint32_t g_bytes = 4u * p.Pg * 16u;
+    const uint32_t g_bytes = (TRIPLE ? 12u : 4u) * p.Pg2 * 16u;
     uint8_t* sX = smem;
     uint8_t* sG = sX + (size_t)p.S * x_bytes;
     PixInfo* tabs = reinterpret_cast<PixInfo*>(sG + (size_t)p.S * g_bytes);  // [S][Pg]
     float* s_scale = reinterpret_cast<float*>(tabs + (size_t)p.S * p.Pg);    // [cin_pad]
     float* s_shift = s_scale + p.cin_pad;
-    float* s_g = s_shift + p.cin_pad;  // [3][32]: k1, k2, k3 of this CTA's 32 output channels
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_g + 96);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + p.cin_pad);
     uint64_t* full = bars;
     uint64_t* empty = bars + p.S;
     uint64_t* accum = bars + 2 * p.S;
@@ -75,11 +90,6 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             }
             cbase += cpad;
         }
-        if (threadIdx.x < 32) {
-            s_g[threadIdx.x] = p.gsrc.scale[n_tile * 32 + threadIdx.x];
-            s_g[32 + threadIdx.x] = p.gsrc.k2[n_tile * 32 + threadIdx.x];
-            s_g[64 + threadIdx.x] = p.gsrc.shift[n_tile * 32 + threadIdx.x];
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -89,14 +99,43 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
     if (warp < kWProducerWarps) {
         const int pl = lane & 7, r = lane >> 3;
         const int tid = threadIdx.x;  // 0..255
+        WPROF_DECL
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int s = chunk % p.S;
             const uint32_t ph = (chunk / p.S) & 1;
-            const long long k0 = (long long)(chunk0 + chunk) * p.KP;  // first position of the chunk
+            const int k0 = (chunk0 + chunk) * p.KP;  // first position of the chunk
             PixInfo* tab = tabs + (size_t)s * p.Pg;
             mbar_wait(&empty[s], ph ^ 1);
-            for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position((int)k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, (int)p.Q);
+            WPROF_MARK(0)
+            for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position(k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, (int)p.Q);
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            WPROF_MARK(1)
+            // ---- gy, all cp.async.  TRIPLE: three staggered copies (dc = 0,1,2) of 4 channel groups x Pg2 positions:
+            //      plane (dc, cg) entry i holds position k0 - Wp - 1 + i + (2 - dc)  (= table index i + 2 - dc).
+            //      else: one copy, entry i = table index i.
+            {
+                const __nv_bfloat16* gbase = p.gy + n_tile * 32 + r * 8;
+                const int nblk = (p.Pg2 + 7) >> 3;
+#pragma unroll
+                for (int dc = 0; dc < (TRIPLE ? 3 : 1); ++dc) {
+                    uint8_t* dst = sG + (size_t)s * g_bytes + (size_t)(dc * 4 + r) * p.Pg2 * 16;
+                    const int toff = TRIPLE ? (2 - dc) : 0;
+                    for (int blk = warp; blk < nblk; blk += kWProducerWarps * 4) {
+                        int pix[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int pp = (blk + u * kWProducerWarps) * 8 + pl;
+                            pix[u] = (pp < p.Pg2) ? tab[pp + toff].pix : -2;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int pp = (blk + u * kWProducerWarps) * 8 + pl;
+                            if (pix[u] != -2) cp_async16(dst + (size_t)pp * 16, gbase + (size_t)(pix[u] >= 0 ? pix[u] : 0) * p.Cout, pix[u] >= 0 ? 16u : 0u);
+                        }
+                    }
+                }
+            }
+            WPROF_MARK(2)
             // ---- X: mcg channel groups x KP positions (positions [Wp+1, Wp+1+KP) of the table), one quad of channel
             //      groups (= 32 channels, never straddling a source) per pass
             {
@@ -114,23 +153,18 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
                     }
                     uint8_t* dst = sX + (size_t)s * x_bytes + (size_t)cg * p.KP * 16;
                     stage_blocks_mode<MODE>(p.src[si], p.H, p.W, tab, p.Wp + 1, p.KP, warp, p.KP >> 3, kWProducerWarps, pl, cglob - c0, s_scale + cglob,
-                                          s_shift + cglob, s_scale + cglob, dst);
+                                            s_shift + cglob, s_scale + cglob, dst);
                 }
             }
-            // ---- gy with halo: 4 channel groups x Pg positions (lane group r = channel group)
-            {
-                uint8_t* dst = sG + (size_t)s * g_bytes + (size_t)r * p.Pg * 16;
-                stage_blocks<NUNET_SRC_GRAD, 4>(p.gsrc, p.H, p.W, tab, 0, p.Pg, warp, (p.Pg + 7) >> 3, kWProducerWarps, pl, n_tile * 32 + r * 8,
-                                                s_g + r * 8, s_g + 64 + r * 8, s_g + 32 + r * 8, dst);
-            }
-            if constexpr (MODE == MODE_ACT || MODE == MODE_ACT_UP) {
-                cp_async_commit();
-                cp_async_wait<0>();
-            }
+            cp_async_commit();
+            WPROF_MARK(3)
+            cp_async_wait<0>();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+            WPROF_MARK(4)
         }
+        if (tid == 0) WPROF_FLUSH(0, 5)
         // ---- epilogue: TMEM -> fp32 partial block
         mbar_wait(accum, 0);
         tc_fence_after();
@@ -149,31 +183,41 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
         }
     } else if (warp == 8) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, 32, kMajorMN, kMajorMN);
-            const uint32_t a_hi = umma_desc_hi((uint32_t)p.KP * 16u), b_hi = umma_desc_hi((uint32_t)p.Pg * 16u);
+            const uint32_t idesc = umma_idesc_bf16(128, TRIPLE ? 96 : 32, kMajorMN, kMajorMN);
+            const uint32_t a_hi = umma_desc_hi((uint32_t)p.KP * 16u), b_hi = umma_desc_hi((uint32_t)p.Pg2 * 16u);
             const int ksteps = p.KP >> 4;
             uint32_t tapoff[9];
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((2 - tap / 3) * p.Wp + (2 - tap % 3));
+            WPROF_DECL
             for (int chunk = 0; chunk < nchunks; ++chunk) {
                 const int s = chunk % p.S;
                 const uint32_t ph = (chunk / p.S) & 1;
                 mbar_wait(&full[s], ph);
+                WPROF_MARK(0)
                 tc_fence_after();
                 uint32_t a_lo = umma_desc_lo(smem_u32(sX + (size_t)s * x_bytes), 128u);
                 uint32_t b_lo = umma_desc_lo(smem_u32(sG + (size_t)s * g_bytes), 128u);
-                // K-step outer, taps inner: each K step (16 positions = 16 address units) feeds nine accumulators
+                // one K step = 16 positions = 16 address units
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const uint32_t accf = (uint32_t)((chunk | ks) != 0);
+                    if constexpr (TRIPLE) {  // kernel row dr reads the planes shifted by (2-dr)*Wp positions
+                        umma_bf16_lohi(tmem_base + 0u, a_lo, a_hi, b_lo + 2u * (uint32_t)p.Wp, b_hi, idesc, accf);
+                        umma_bf16_lohi(tmem_base + 96u, a_lo, a_hi, b_lo + (uint32_t)p.Wp, b_hi, idesc, accf);
+                        umma_bf16_lohi(tmem_base + 192u, a_lo, a_hi, b_lo, b_hi, idesc, accf);
+                    } else {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap)
-                        umma_bf16_lohi(tmem_base + (uint32_t)(tap * 32), a_lo, a_hi, b_lo + tapoff[tap], b_hi, idesc, accf);
+                        for (int tap = 0; tap < 9; ++tap)
+                            umma_bf16_lohi(tmem_base + (uint32_t)(tap * 32), a_lo, a_hi, b_lo + tapoff[tap], b_hi, idesc, accf);
+                    }
                     a_lo += 16u;
                     b_lo += 16u;
                 }
                 umma_commit(&empty[s]);
+                WPROF_MARK(1)
             }
             umma_commit(accum);
+            WPROF_FLUSH(8, 2)
         }
         __syncwarp();
     }
@@ -203,9 +247,21 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
 
 using namespace nunet;
 
-static size_t wgrad_smem_bytes(int KP, int S, int Pg, int cin_pad) {
-    return (size_t)S * (256ull * KP + 64ull * Pg + 8ull * Pg) + (size_t)cin_pad * 8 + 96 * 4 + (2 * S + 1) * 8 + 16 + 128;
+static size_t wgrad_smem_bytes(int KP, int S, int Pg, int planes, int Pg2, int cin_pad) {
+    return (size_t)S * (256ull * KP + 64ull * planes * Pg2 + 8ull * Pg) + (size_t)cin_pad * 8 + (2 * S + 1) * 8 + 16 + 128;
 }
+
+#ifdef NUNET_PROFILE_WAITS
+extern "C" int nunet_debug_read_wgrad_prof(unsigned long long* out16, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_wgrad_prof, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_wgrad_prof, z, sizeof(z));
+    }
+    return e == cudaSuccess ? 0 : NUNET_E_CUDA + (int)e;
+}
+#endif
 
 extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* pl) {
     if (!pl || N <= 0 || H <= 0 || W <= 0 || cin_total <= 0 || Cout <= 0 || Cout % 32 != 0) return NUNET_E_BADARG;
@@ -215,12 +271,19 @@ extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t
     const long long Q = ((long long)N * (H + 1) + 1) * (W + 2);
     if (Q >= (1LL << 31) - 4096) return NUNET_E_UNSUPPORTED;
     const size_t budget = 220 * 1024;
-    int KP = 0, S = 0;
-    for (int kp = 256; kp >= 64 && !KP; kp >>= 1) {
-        const int Pg = kp + 2 * (W + 2) + 2;
-        if ((size_t)Pg * 16 >= (1u << 18)) continue;
-        for (int s = 3; s >= 2; --s)
-            if (wgrad_smem_bytes(kp, s, Pg, cin_pad) <= budget) { KP = kp; S = s; break; }
+    int KP = 0, S = 0, triple = 0;
+    const char* env_tr = getenv("NUNET_WGRAD_TRIPLE");
+    const int tr_max = env_tr ? atoi(env_tr) : 0;  // default: single gy plane (the producers, not the tensor pipe, bound wgrad)
+    // prefer the three-plane layout (3 MMAs of N=96 per K step) with >= 2 stages; fall back to one plane (9 MMAs of N=32)
+    for (int tr = tr_max; tr >= 0 && !KP; --tr) {
+        static const int kps[] = {256, 192, 128, 96, 64};
+        for (int ki = 0; ki < (tr ? 3 : 5) && !KP; ++ki) {
+            const int kp = kps[ki];
+            const int Pg = kp + 2 * (W + 2) + 2, Pg2 = tr ? kp + 2 * (W + 2) : Pg;
+            if ((size_t)Pg * 16 >= (1u << 18)) continue;
+            for (int s = 3; s >= 2; --s)
+                if (wgrad_smem_bytes(kp, s, Pg, tr ? 3 : 1, Pg2, cin_pad) <= budget) { KP = kp; S = s; triple = tr; break; }
+        }
     }
     if (!KP) return NUNET_E_SMEM;
     const int nchunks_total = (int)((Q + KP - 1) / KP);
@@ -236,23 +299,28 @@ extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t
     if (S > cpc) S = cpc < 1 ? 1 : cpc;
     pl->KP = KP; pl->S = S; pl->Pg = KP + 2 * (W + 2) + 2; pl->cpc = cpc; pl->nchunks_total = nchunks_total;
     pl->splits = splits; pl->m_tiles = m_tiles; pl->n_tiles = n_tiles; pl->cin_pad = cin_pad;
-    pl->smem_bytes = (int)wgrad_smem_bytes(KP, S, pl->Pg, cin_pad);
+    pl->triple = triple;
+    pl->smem_bytes = (int)wgrad_smem_bytes(KP, S, pl->Pg, triple ? 3 : 1, triple ? KP + 2 * (W + 2) : pl->Pg, cin_pad);
     pl->part_elems = (int64_t)splits * n_tiles * 9 * cin_pad * 32;
     return NUNET_OK;
 }
 
-template <int MODE>
-static int launch_wgrad(const WgradParams& p, const nunet_wgrad_plan_t& pl, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+template <int MODE, bool TRIPLE>
+static int launch_wgrad2(const WgradParams& p, const nunet_wgrad_plan_t& pl, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<MODE, TRIPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
-    conv3x3_wgrad_kernel<MODE><<<dim3(pl.splits, pl.m_tiles, pl.n_tiles), kWThreads, pl.smem_bytes, stream>>>(p);
+    conv3x3_wgrad_kernel<MODE, TRIPLE><<<dim3(pl.splits, pl.m_tiles, pl.n_tiles), kWThreads, pl.smem_bytes, stream>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+}
+template <int MODE>
+static int launch_wgrad(const WgradParams& p, const nunet_wgrad_plan_t& pl, cudaStream_t stream) {
+    return pl.triple ? launch_wgrad2<MODE, true>(p, pl, stream) : launch_wgrad2<MODE, false>(p, pl, stream);
 }
 
 extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
     if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->part || !d->dw) return NUNET_E_BADARG;
-    if (!d->gz || !d->y || !d->k1 || !d->k2 || !d->k3) return NUNET_E_BADARG;
+    if (!d->gy) return NUNET_E_BADARG;
     int cin = 0, cin_real = 0;
     for (int i = 0; i < d->num_src; ++i) {
         const nunet_src_t& s = d->src[i];
@@ -272,14 +340,13 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
     WgradParams p{};
     p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
     p.Q = ((long long)d->N * (d->H + 1) + 1) * (d->W + 2);
-    p.KP = pl.KP; p.S = pl.S; p.Pg = pl.Pg; p.cpc = pl.cpc; p.nchunks_total = pl.nchunks_total;
+    p.KP = pl.KP; p.S = pl.S; p.Pg = pl.Pg; p.Pg2 = pl.triple ? pl.KP + 2 * (d->W + 2) : pl.Pg; p.cpc = pl.cpc; p.nchunks_total = pl.nchunks_total;
     p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src;
     for (int i = 0; i < d->num_src; ++i) {
         p.src[i].data = d->src[i].data; p.src[i].data2 = nullptr; p.src[i].scale = d->src[i].scale;
         p.src[i].shift = d->src[i].shift; p.src[i].k2 = nullptr; p.src[i].C = d->src[i].C; p.src[i].kind = d->src[i].kind;
     }
-    p.gsrc.data = d->gz; p.gsrc.data2 = d->y; p.gsrc.scale = d->k1; p.gsrc.k2 = d->k2; p.gsrc.shift = d->k3;
-    p.gsrc.C = d->Cout; p.gsrc.kind = NUNET_SRC_GRAD;
+    p.gy = (const __nv_bfloat16*)d->gy;
     p.part = d->part;
     int kinds[NUNET_MAX_SRC];
     for (int i = 0; i < d->num_src; ++i) kinds[i] = d->src[i].kind;

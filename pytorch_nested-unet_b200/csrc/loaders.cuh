@@ -219,12 +219,17 @@ __device__ __forceinline__ void stage_blocks_cpasync(const ConvSrc& s, const Pix
                                                      int first_blk, int nblk, int blk_stride, int pl, int ch, uint8_t* dst) {
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(s.data) + ch;
     const int C = s.C;
-    for (int b = first_blk; b < nblk; b += blk_stride) {
-        const int pp = b * 8 + pl;
-        if (pp < plimit) {
-            const int pix = tab[pp + tab_off].pix;
-            const bool ok = pix >= 0;
-            cp_async16(dst + (size_t)pp * 16, base + (size_t)(ok ? pix : 0) * C, ok ? 16u : 0u);
+    for (int b = first_blk; b < nblk; b += blk_stride * 4) {
+        int pix[4];  // -2: nothing to stage, -1: padding (zero fill)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int bb = b + u * blk_stride, pp = bb * 8 + pl;
+            pix[u] = (bb < nblk && pp < plimit) ? tab[pp + tab_off].pix : -2;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pp = (b + u * blk_stride) * 8 + pl;
+            if (pix[u] != -2) cp_async16(dst + (size_t)pp * 16, base + (size_t)(pix[u] >= 0 ? pix[u] : 0) * C, pix[u] >= 0 ? 16u : 0u);
         }
     }
 }

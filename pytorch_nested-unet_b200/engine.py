@@ -276,9 +276,10 @@ def _backward(model, x, recs, grad_logits):
                                       grad_scale=1.0 / dp.world_size)
         gdone(s.bn.weight, dgamma)
         gdone(s.bn.bias, dbeta)
+        gy = ops.bn_bwd_apply(gz, r.y, k1, k2, k3, out=gz)  # in place: g_z is dead once the BN sums are reduced
         srcs = _sources(s, recs, x)
         dw = galloc(s.conv.weight)
-        ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gz, r.y, k1, k2, k3, dw)
+        ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw)
         gdone(s.conv.weight, dw)
         if s.conv.bias is not None:
             # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
@@ -286,8 +287,7 @@ def _backward(model, x, recs, grad_logits):
         if s.sources[0][0] >= 0:
             plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
             wpd = st.pack(s, plan, L.PACK_DGRAD)
-            gsrc = ops.Source(L.SRC_GRAD, gz, s.cout, k1, k3, data2=r.y, k2=k2)
-            dxs[s.idx], _ = ops.conv3x3(N, h, w, [gsrc], s.cin_pad, wpd)
+            dxs[s.idx], _ = ops.conv3x3(N, h, w, [ops.Source(L.SRC_ACT, gy, s.cout)], s.cin_pad, wpd, cls="conv_dgrad")
         for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
             if specs[m].sources[0][0] == s.idx:
                 dxs.pop(m, None)

@@ -99,7 +99,7 @@ def pack_weights(w_oihw, mode, plan, out=None):
     return out
 
 
-def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False):
+def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False, cls=None):
     """Launches the fused implicit-GEMM conv. Returns (out bf16 [N,H,W,Cout], stat_part [grid_m,2,Cout] or None)."""
     cin = sum(s.cpad for s in sources)
     plan = conv_plan(N, H, W, cin, Cout)
@@ -121,7 +121,8 @@ def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=
     d.wpack = wpack.data_ptr()
     d.out = out.data_ptr()
     d.stat_part = stat_part.data_ptr() if stat_part is not None else None
-    cls = "conv_dgrad" if sources[0].kind == L.SRC_GRAD else "conv_fwd"
+    if cls is None:
+        cls = "conv_dgrad" if sources[0].kind == L.SRC_GRAD else "conv_fwd"
     _call(cls, 1, (N, H, W, cin, Cout), "nunet_conv3x3_fwd", L.lib().nunet_conv3x3_fwd, C.byref(d), _stream())
     return out, stat_part
 
@@ -265,12 +266,22 @@ def wgrad_plan(N, H, W, cin_total, Cout):
     return pl
 
 
-def conv3x3_wgrad(N, H, W, sources, Cout, gz, y, k1, k2, k3, dw, part=None):
-    """dw: fp32 [Cout, Cin_real, 3, 3] (overwritten)."""
+def bn_bwd_apply(gz, y, k1, k2, k3, out=None):
+    """g_y = k1*g_z + k2*y + k3 (bf16 NHWC); out may be gz itself (in place)."""
+    if out is None:
+        out = torch.empty_like(gz)
+    Cc = gz.shape[-1]
+    _call("bn_bwd_apply", 1, None, "nunet_bn_bwd_apply", L.lib().nunet_bn_bwd_apply, _ptr(gz), _ptr(y), _ptr(k1), _ptr(k2), _ptr(k3),
+          gz.numel() // Cc, Cc, _ptr(out), _stream())
+    return out
+
+
+def conv3x3_wgrad(N, H, W, sources, Cout, gy, dw, part=None):
+    """dw: fp32 [Cout, Cin_real, 3, 3] (overwritten); gy from bn_bwd_apply."""
     cin = sum(s.cpad for s in sources)
     plan = wgrad_plan(N, H, W, cin, Cout)
     if part is None:
-        part = torch.empty(plan.part_elems, dtype=torch.float32, device=gz.device)
+        part = torch.empty(plan.part_elems, dtype=torch.float32, device=gy.device)
     d = L.WgradDesc()
     d.N, d.H, d.W, d.num_src, d.Cout = N, H, W, len(sources), Cout
     for i, s in enumerate(sources):
@@ -279,7 +290,7 @@ def conv3x3_wgrad(N, H, W, sources, Cout, gz, y, k1, k2, k3, dw, part=None):
         d.src[i].shift = s.shift.data_ptr() if s.shift is not None else None
         d.src[i].C = s.C
         d.src[i].kind = s.kind
-    d.gz, d.y, d.k1, d.k2, d.k3 = gz.data_ptr(), y.data_ptr(), k1.data_ptr(), k2.data_ptr(), k3.data_ptr()
+    d.gy = gy.data_ptr()
     d.part, d.dw = part.data_ptr(), dw.data_ptr()
     _call("conv_wgrad", 2, (N, H, W, cin, Cout), "nunet_conv3x3_wgrad", L.lib().nunet_conv3x3_wgrad, C.byref(d), _stream())
     return dw

@@ -119,6 +119,13 @@ def test_dgrad(N, H, W, Cin, Cout):
     got = dx.float().permute(0, 3, 1, 2)
     err = (got - ref).abs()
     assert bool((err <= 0.008 * ref.abs() + 2e-3 * ref.abs().max()).all()), err.max()
+    # the engine's path: g_y materialised once (in place), dgrad reads it as a pre-activated source through cp.async
+    gyb = ops.bn_bwd_apply(gz, y, k1, k2, k3, out=gz)
+    dx2, _ = ops.conv3x3(N, H, W, [ops.Source(L.SRC_ACT, gyb, Cout)], Cin, wp)
+    torch.cuda.synchronize()
+    ref2 = F.conv_transpose2d(gyb.float().permute(0, 3, 1, 2), _bf(w), padding=1)
+    err2 = (dx2.float().permute(0, 3, 1, 2) - ref2).abs()
+    assert bool((err2 <= 0.008 * ref2.abs() + 2e-3 * ref2.abs().max()).all()), err2.max()
 
 
 WG_CASES = [
@@ -153,10 +160,12 @@ def test_wgrad(case):
     cin = sum(c for _, c in srcs)
     gz, y, k1, k2, k3, gy = _grad_operands(N, H, W, Cout, gen)
     dw = torch.full((Cout, cin, 3, 3), float("nan"), device=DEV)
-    ops.conv3x3_wgrad(N, H, W, sources, Cout, gz, y, k1, k2, k3, dw)
+    gyb = ops.bn_bwd_apply(gz, y, k1, k2, k3)
+    assert bool(((gyb.float().permute(0, 3, 1, 2) - gy).abs() <= 0.008 * gy.abs() + 1e-6).all())
+    ops.conv3x3_wgrad(N, H, W, sources, Cout, gyb, dw)
     torch.cuda.synchronize()
     x = _bf(torch.cat([source_tensor(*r) for r in refs], 1))
-    ref = torch.nn.grad.conv2d_weight(x, (Cout, cin, 3, 3), _bf(gy), padding=1)
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, cin, 3, 3), gyb.float().permute(0, 3, 1, 2), padding=1)
     err = (dw - ref).abs()
     assert bool(torch.isfinite(dw).all())
     assert bool((err <= 2e-3 * ref.abs() + 2e-3 * ref.abs().max()).all()), (err.max(), ref.abs().max())
@@ -170,8 +179,9 @@ def test_wgrad_stem():
     x = torch.randn(N, Cin, H, W, generator=gen, device=DEV)
     gz, y, k1, k2, k3, gy = _grad_operands(N, H, W, Cout, gen)
     dw = torch.full((Cout, Cin, 3, 3), float("nan"), device=DEV)
-    ops.conv3x3_wgrad(N, H, W, [ops.Source(L.SRC_INPUT, x, Cin)], Cout, gz, y, k1, k2, k3, dw)
+    gyb = ops.bn_bwd_apply(gz, y, k1, k2, k3)
+    ops.conv3x3_wgrad(N, H, W, [ops.Source(L.SRC_INPUT, x, Cin)], Cout, gyb, dw)
     torch.cuda.synchronize()
-    ref = torch.nn.grad.conv2d_weight(_bf(x), (Cout, Cin, 3, 3), _bf(gy), padding=1)
+    ref = torch.nn.grad.conv2d_weight(_bf(x), (Cout, Cin, 3, 3), gyb.float().permute(0, 3, 1, 2), padding=1)
     err = (dw - ref).abs()
     assert bool((err <= 2e-3 * ref.abs() + 2e-3 * ref.abs().max()).all()), (err.max(), ref.abs().max())

@@ -23,7 +23,7 @@ for it in range(3):
         ops.conv3x3(N, H, W, [src], Cout, wp, want_stats=True)
     elif which == "wgrad":
         dw = torch.empty(Cout, Cin, 3, 3, device=dev)
-        ops.conv3x3_wgrad(N, H, W, [src], Cout, gz, yo, k1, k2, k3, dw)
+        ops.conv3x3_wgrad(N, H, W, [src], Cout, ops.bn_bwd_apply(gz, yo, k1, k2, k3), dw)
     elif which == "router":
         dx = torch.randn(N, H, W, Cout, generator=g, device=dev).to(torch.bfloat16)
         ops.grad_router(N, H, W, Cout, yo, k1, k2, mean, inv, [ops.Consumer(dx, Cout, 0, L.SRC_SAME)])
