@@ -149,6 +149,11 @@ typedef struct {
 } nunet_router_desc_t;
 int nunet_grad_router_rows(int32_t N, int32_t H, int32_t W, int32_t C);
 int nunet_grad_router(const nunet_router_desc_t* d, void* stream);
+/* Transposed align_corners bilinear 2x upsample: out[N,h,w,C] (bf16 NHWC, dense) = backward of the UP loader applied to
+ * the channel slice [coff, coff+C) of a consumer's dgrad buffer dx[N,2h,2w,pitch]; the router then reads `out` as a
+ * NUNET_SRC_SAME consumer (pitch C, offset 0). */
+int nunet_up_transpose(const void* dx, int32_t pitch, int32_t coff, int32_t N, int32_t h, int32_t w, int32_t C, void* out,
+                       void* stream);
 /* Finishes BatchNorm backward: dbeta = S1, dgamma = S2 and the loader coefficients of g_y = k1*g_z + k2*y + k3.
  * gamma == NULL: only sums_out ([2][C] fp64) is produced (SyncBN: all-reduce, then nunet_bn_backward_from_sums). */
 int nunet_bn_backward_reduce(const float* part, int32_t rows, int32_t C, double count, const float* gamma,

@@ -75,6 +75,7 @@ _SIGS = {
     "nunet_head_bwd_params": ([C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p], C.c_int),
     "nunet_grad_router_rows": ([C.c_int32] * 4, C.c_int),
     "nunet_grad_router": ([C.POINTER(RouterDesc), C.c_void_p], C.c_int),
+    "nunet_up_transpose": ([C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_backward_reduce": ([C.c_void_p, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 12, C.c_int),
     "nunet_bn_backward_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 8 + [C.c_float, C.c_void_p], C.c_int),
     "nunet_conv3x3_wgrad_plan": ([C.c_int32] * 5 + [C.POINTER(WgradPlan)], C.c_int),

@@ -246,7 +246,12 @@ def _backward(model, x, recs, grad_logits):
     for s in reversed(specs):
         r = recs[s.idx]
         h, w = r.h, r.w
-        cons = [ops.Consumer(dxs[m], specs[m].cin_pad, off, kind) for (m, off, kind) in s.consumers]
+        cons = []
+        for (m, off, kind) in s.consumers:
+            if kind == L.SRC_UP:   # transposed bilinear gather in its own tiled kernel; the router then sees a dense SAME slice
+                cons.append(ops.Consumer(ops.up_transpose(dxs[m], specs[m].cin_pad, off, N, h, w, s.cout), s.cout, 0, L.SRC_SAME))
+            else:
+                cons.append(ops.Consumer(dxs[m], specs[m].cin_pad, off, kind))
         dl = wh = None
         if s.head is not None:
             dl = grad_logits.get(s.idx)

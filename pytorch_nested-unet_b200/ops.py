@@ -247,6 +247,14 @@ def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, 
     return gz, part
 
 
+def up_transpose(dx, pitch, coff, N, h, w, Cc, out=None):
+    """Backward of the bilinear-2x loader: dx [N,2h,2w,pitch] slice -> dense bf16 [N,h,w,Cc]."""
+    if out is None:
+        out = torch.empty((N, h, w, Cc), dtype=torch.bfloat16, device=dx.device)
+    _call("up_transpose", 1, (N, h, w, Cc), "nunet_up_transpose", L.lib().nunet_up_transpose, _ptr(dx), pitch, coff, N, h, w, Cc, _ptr(out), _stream())
+    return out
+
+
 def bn_backward_reduce(part, count, gamma, mean, invstd, ws, dgamma, dbeta, k1, k2, k3, sums_out=None, finalize=True):
     rows, _, Cc = part.shape
     _call("bn_bwd", 1, None, "nunet_bn_backward_reduce", L.lib().nunet_bn_backward_reduce, _ptr(part), rows, Cc, float(count), _ptr(gamma if finalize else None), _ptr(mean), _ptr(invstd),

@@ -65,6 +65,21 @@ def test_grad_router(N, H, W, Cc, kinds):
     assert torch.allclose(g2, s2, rtol=1e-3, atol=tol * 3), (g2 - s2).abs().max()
 
 
+@pytest.mark.parametrize("N,h,w,Cc,pitch,coff", [(2, 8, 8, 64, 64, 0), (3, 6, 10, 128, 192, 64), (2, 3, 5, 512, 768, 256), (4, 24, 24, 32, 96, 32),
+                                                    (2, 48, 48, 64, 192, 128)])
+def test_up_transpose(N, h, w, Cc, pitch, coff):
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(17 + h)
+    dx = torch.randn(N, 2 * h, 2 * w, pitch, generator=gen, device=DEV).to(torch.bfloat16)
+    out = ops.up_transpose(dx, pitch, coff, N, h, w, Cc)
+    a = torch.zeros(N, Cc, h, w, device=DEV, requires_grad=True)
+    up = F.interpolate(a, scale_factor=2, mode="bilinear", align_corners=True)
+    (up * dx[..., coff:coff + Cc].float().permute(0, 3, 1, 2)).sum().backward()
+    torch.cuda.synchronize()
+    err = (out.float().permute(0, 3, 1, 2) - a.grad).abs()
+    assert bool((err <= 0.008 * a.grad.abs() + 1e-3 * a.grad.abs().max()).all()), err.max()
+
+
 def test_bn_backward_reduce():
     import ops
     gen = torch.Generator(device=DEV).manual_seed(9)
