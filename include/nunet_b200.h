@@ -101,6 +101,9 @@ int nunet_bn_finalize_from_sums(const double* sums, int32_t C, double count, con
 /* a = relu(scale*y + shift), bf16 NHWC -> bf16 NHWC (nn.BatchNorm2d apply + ReLU of a node output that several later
  * convolutions consume, finished/archs1.py:29-30). npix = N*H*W, C % 8 == 0. */
 int nunet_bn_apply(const void* y, const float* scale, const float* shift, long long npix, int32_t C, void* a, void* stream);
+/* out[N,2h,2w,C] = bilinear 2x (align_corners=True) of an activated bf16 NHWC tensor (nn.Upsample, finished/archs1.py:83),
+ * for callers that prefer one materialised operand over the NUNET_SRC_UP* loaders. */
+int nunet_upsample2x(const void* in, int32_t N, int32_t h, int32_t w, int32_t C, void* out, void* stream);
 /* Eval mode: scale = gamma*rsqrt(running_var+eps), shift = beta + (conv_bias - running_mean)*scale. */
 int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
                        const float* running_mean, const float* running_var, float eps, float* scale, float* shift,

@@ -82,6 +82,7 @@ _SIGS = {
     "nunet_conv3x3_wgrad": ([C.POINTER(WgradDesc), C.c_void_p], C.c_int),
     "nunet_bn_apply": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_bwd_apply": ([C.c_void_p] * 5 + [C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_upsample2x": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
 }
 

@@ -188,6 +188,45 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* gz, cons
     }
 }
 
+// Bilinear 2x upsample (align_corners=True, ATen area_pixel_compute_scale) of an activated bf16 NHWC tensor:
+// out[N,2h,2w,C].  One 16-byte group per thread-iteration, fp32 blend, one rounding.  Used when the engine materialises
+// the upsampled skip operand once instead of re-blending it in every loader that reads it (forward + Cout/32 wgrad CTAs).
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int N, int h, int w, int cgs,
+                                                         __nv_bfloat16* __restrict__ out) {
+    const int H = 2 * h, W = 2 * w, C = cgs * 8;
+    const long long items = (long long)N * H * W * cgs;
+    const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    const float rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(it % cgs);
+        long long pix = it / cgs;
+        const int X = (int)(pix % W); pix /= W;
+        const int Y = (int)(pix % H);
+        const int n = (int)(pix / H);
+        const float sy = ry * (float)Y, sx = rx * (float)X;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+        const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        const __nv_bfloat16* base = in + (size_t)n * h * w * C + cg * 8;
+        const uint4 r00 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * C));
+        const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * C));
+        const uint4 r10 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * C));
+        const uint4 r11 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * C));
+        const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&r00), *b = reinterpret_cast<const __nv_bfloat162*>(&r01),
+                             *c = reinterpret_cast<const __nv_bfloat162*>(&r10), *d = reinterpret_cast<const __nv_bfloat162*>(&r11);
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = __bfloat1622float2(a[i]), fb = __bfloat1622float2(b[i]), fc = __bfloat1622float2(c[i]), fd = __bfloat1622float2(d[i]);
+            const float v0 = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
+            const float v1 = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
+            __nv_bfloat162 q = __floats2bfloat162_rn(v0, v1);
+            o[i] = *reinterpret_cast<uint32_t*>(&q);
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)it * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -272,5 +311,14 @@ extern "C" int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1
     if (blocks > 148 * 8) blocks = 148 * 8;
     bn_bwd_apply_kernel<<<(int)blocks, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)gz, (const uint4*)y, k1, k2, k3, ngroups,
                                                                                           C / 8, (uint4*)gy);
+    return cuda_rc();
+}
+
+extern "C" int nunet_upsample2x(const void* in, int32_t N, int32_t h, int32_t w, int32_t C, void* out, void* stream) {
+    if (!in || !out || N < 1 || h < 1 || w < 1 || C < 8 || C % 8 != 0) return NUNET_E_BADARG;
+    const long long items = (long long)N * 4 * h * w * (C / 8);
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    upsample2x_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, h, w, C / 8, (__nv_bfloat16*)out);
     return cuda_rc();
 }

@@ -17,6 +17,9 @@ NB_FILTER = (32, 64, 128, 256, 512)
 # Node outputs (up to 5 forward + 5 wgrad loaders re-read each) are activated once into a bf16 tensor; False = every
 # loader applies BatchNorm+ReLU itself from the raw conv output.
 MATERIALIZE_NODE_OUTPUTS = True
+# The upsampled skip operand is re-read by the forward conv and by Cout/32 wgrad CTAs per position; blending it in every
+# loader costs 4-8x the arithmetic of writing it once (measured: tools/prof_wgrad.py). False = fused NUNET_SRC_UP* loaders.
+MATERIALIZE_UPSAMPLED = True
 
 
 # --------------------------------------------------------------------------------------------- graphs
@@ -138,7 +141,7 @@ def _world(model):
 
 
 class _Record(object):
-    __slots__ = ("y", "a", "scale", "shift", "mean", "invstd", "h", "w")
+    __slots__ = ("y", "a", "a_up", "scale", "shift", "mean", "invstd", "h", "w")
 
 
 def _sources(spec, recs, x):
@@ -150,7 +153,9 @@ def _sources(spec, recs, x):
             srcs.append(ops.Source(kind, x, c))
         else:
             r = recs[pi]
-            if r.a is not None:
+            if kind == L.SRC_UP and r.a_up is not None:
+                srcs.append(ops.Source(L.SRC_ACT, r.a_up, c))
+            elif r.a is not None:
                 srcs.append(ops.Source(L.ACT_KIND[kind], r.a, c))
             else:
                 srcs.append(ops.Source(kind, r.y, c, r.scale, r.shift))
@@ -181,7 +186,7 @@ def _forward(model, x, train):
         wp = st.pack(s, plan, L.PACK_FWD)
         y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
         r = _Record()
-        r.y, r.h, r.w, r.a = y, h, w, None
+        r.y, r.h, r.w, r.a, r.a_up = y, h, w, None, None
         r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
         r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
         bn = s.bn
@@ -208,6 +213,8 @@ def _forward(model, x, train):
             ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
         if s.which == 2 and MATERIALIZE_NODE_OUTPUTS and s.consumers:
             r.a = ops.bn_apply(y, r.scale, r.shift)
+            if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
+                r.a_up = ops.upsample2x(r.a)
         recs.append(r)
     if train:
         nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]

@@ -15,7 +15,7 @@ def _ptr(t):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 # ---------------------------------------------------------------------------------------------- launch accounting
@@ -158,6 +158,15 @@ def bn_apply(y, scale, shift, out=None):
         out = torch.empty_like(y)
     Cc = y.shape[-1]
     _call("bn_apply", 1, None, "nunet_bn_apply", L.lib().nunet_bn_apply, _ptr(y), _ptr(scale), _ptr(shift), y.numel() // Cc, Cc, _ptr(out), _stream())
+    return out
+
+
+def upsample2x(a, out=None):
+    """bf16 NHWC [N,h,w,C] -> [N,2h,2w,C], bilinear align_corners=True."""
+    N, h, w, Cc = a.shape
+    if out is None:
+        out = torch.empty((N, 2 * h, 2 * w, Cc), dtype=torch.bfloat16, device=a.device)
+    _call("upsample2x", 1, None, "nunet_upsample2x", L.lib().nunet_upsample2x, _ptr(a), N, h, w, Cc, _ptr(out), _stream())
     return out
 
 

@@ -144,3 +144,16 @@ def test_bn_finalize_matches_batchnorm():
     ops.bn_finalize_from_sums(sums, count, gamma, beta, None, None, None, 0.1, 1e-5, scale2, shift2, None, None)
     torch.cuda.synchronize()
     assert torch.allclose(scale2, scale) and torch.allclose(shift2, shift)
+
+
+def test_upsample2x_matches_torch():
+    import ops
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(5)
+    for (N, h, w, Cc) in [(2, 6, 6, 512), (3, 12, 20, 64), (2, 48, 48, 64), (1, 3, 5, 128)]:
+        a = torch.rand(N, h, w, Cc, generator=gen, device=dev).to(torch.bfloat16)
+        up = ops.upsample2x(a)
+        ref = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        torch.cuda.synchronize()
+        assert bool(((up.float() - ref).abs() <= 0.008 * ref.abs() + 1e-6).all())
