@@ -24,10 +24,11 @@ namespace nunet {
 
 // ------------------------------------------------------------------------------------------------ kernel
 constexpr int kProducerWarps = 8;                 // warps 0-7 : stage the transformed input halo
-constexpr int kEpilogueWarp0 = 8;                 // warps 8-11: TMEM -> bf16 NHWC + BN statistics (warp % 4 = TMEM lane quadrant)
-constexpr int kMmaWarp = 12;                      // warp 12   : tcgen05.mma issuer (one lane) + TMEM owner
-constexpr int kFetchWarp = 13;                    // warp 13   : weight fetcher (cp.async.bulk, one lane)
-constexpr int kThreads = 14 * 32;
+constexpr int kEpilogueWarp0 = 8;                 // warps 8-15: TMEM -> bf16 NHWC + BN statistics (warp % 4 = TMEM lane quadrant,
+constexpr int kEpilogueWarps = 8;                 //             two warps per quadrant split the column slabs)
+constexpr int kMmaWarp = 16;                      // warp 16   : tcgen05.mma issuer (one lane) + TMEM owner
+constexpr int kFetchWarp = 17;                    // warp 17   : weight fetcher (cp.async.bulk, one lane)
+constexpr int kThreads = 18 * 32;
 
 // Optional wait/work cycle accounting per warp role (build with -DNUNET_PROFILE_WAITS; tools/prof_waits.py reads it).
 #ifdef NUNET_PROFILE_WAITS
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
     float* s_scale = reinterpret_cast<float*>(pixtab + 2 * p.P);
     float* s_shift = s_scale + p.cin_pad;
     float* s_k2 = s_shift + p.cin_pad;
-    float* s_stat = s_k2 + p.cin_pad;  // [4 quadrant warps][2][NT], each slot owned by one thread (deterministic)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 8 * p.NT);
+    float* s_stat = s_k2 + p.cin_pad;  // [8 epilogue warps][2][NT], each slot owned by one thread (deterministic)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 16 * p.NT);
     uint64_t* full = bars;                 // [S]  producers + fetcher -> MMA
     uint64_t* empty = bars + p.S;          // [S]  MMA -> producers + fetcher
     uint64_t* acc_full = bars + 2 * p.S;   // [2]  MMA -> epilogue
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&acc_full[b], 1);
-                mbar_init(&acc_empty[b], 4);
+                mbar_init(&acc_empty[b], kEpilogueWarps);
                 mbar_init(&tab_full[b], kProducerWarps);
             }
             mbar_init_fence();
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             }
             cbase += cpad;
         }
-        for (int i = threadIdx.x; i < 8 * p.NT; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < 16 * p.NT; i += kThreads) s_stat[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -165,11 +166,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
         if (threadIdx.x == 0) PROF_FLUSH(0)
     } else if (warp < kMmaWarp) {
         // =============================== epilogue (4 warps, one TMEM lane quadrant each)
-        const int lq = warp & 3;
+        const int lq = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
         const int nslab = p.NT >> 4;  // 16-channel slabs
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
         const bool want_stats = p.stat_part != nullptr;
-        float* my_stat = s_stat + (size_t)lq * 2 * p.NT;
+        float* my_stat = s_stat + (size_t)(warp - kEpilogueWarp0) * 2 * p.NT;
         int it = 0;
         PROF_DECL
         for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
@@ -181,7 +182,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             PROF_MARK(0)
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);
-            for (int cs = 0; cs < nslab; ++cs) {
+            if (!want_stats) {
+                // plain store path (dgrad, eval): 32 columns per TMEM load -> 64 contiguous bytes per pixel and lane
+                const int nslab32 = p.NT >> 5;
+                for (int t = 0; t < p.T; ++t) {
+                    const PixInfo pi = tab[t * 128 + lq * 32 + lane + p.Wp + 1];
+                    for (int cs = half; cs < nslab32; cs += 2) {
+                        uint32_t v[32];
+                        tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
+                        tmem_ld_wait();
+                        if (pi.pix >= 0) {
+                            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pi.pix * p.Cout + n_tile * p.NT + cs * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                                o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                                o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                                o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                                dst[j] = o;
+                            }
+                        }
+                    }
+                }
+            } else {
+            for (int cs = half; cs < nslab; cs += 2) {
                 float ssum[16], ssq[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
@@ -201,41 +226,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                             o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
                             dst[j] = o;
                         }
-                        if (want_stats) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float f = __uint_as_float(v[i]);
-                                ssum[i] += f;
-                                ssq[i] = fmaf(f, f, ssq[i]);
-                            }
+                        for (int i = 0; i < 16; ++i) {
+                            const float f = __uint_as_float(v[i]);
+                            ssum[i] += f;
+                            ssq[i] = fmaf(f, f, ssq[i]);
                         }
                     }
                 }
-                if (want_stats) {
-                    // fold the two half-warps, then a transposing butterfly: lane L ends with the total of channel L & 15
+                // fold the two half-warps, then a transposing butterfly: lane L ends with the total of channel L & 15
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
-                        ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
+                    ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
+                }
 #pragma unroll
-                    for (int off = 8; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
+                for (int off = 8; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
 #pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float sa = up ? ssum[i] : ssum[i + off];
-                            const float ka = up ? ssum[i + off] : ssum[i];
-                            ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-                            const float sb = up ? ssq[i] : ssq[i + off];
-                            const float kb = up ? ssq[i + off] : ssq[i];
-                            ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
-                        }
-                    }
-                    if (lane < 16) {  // this thread is the only writer of these two slots, groups are visited in a fixed order
-                        my_stat[cs * 16 + lane] += ssum[0];
-                        my_stat[p.NT + cs * 16 + lane] += ssq[0];
+                    for (int i = 0; i < off; ++i) {
+                        const float sa = up ? ssum[i] : ssum[i + off];
+                        const float ka = up ? ssum[i + off] : ssum[i];
+                        ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+                        const float sb = up ? ssq[i] : ssq[i + off];
+                        const float kb = up ? ssq[i + off] : ssq[i];
+                        ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
                     }
                 }
+                if (lane < 16) {  // this thread is the only writer of these two slots, groups are visited in a fixed order
+                    my_stat[cs * 16 + lane] += ssum[0];
+                    my_stat[p.NT + cs * 16 + lane] += ssq[0];
+                }
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -244,12 +266,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
         }
         if (warp == kEpilogueWarp0 && lane == 0) PROF_FLUSH(4)
         if (want_stats) {
-            asm volatile("bar.sync 2, 128;" ::: "memory");  // the 4 epilogue warps only
+            asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps only
             float* dst = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n_tile * p.NT;
-            for (int c = threadIdx.x - kEpilogueWarp0 * 32; c < p.NT; c += 128) {
+            for (int c = threadIdx.x - kEpilogueWarp0 * 32; c < p.NT; c += 256) {
                 float a = 0.f, bb = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     a += s_stat[(q * 2 + 0) * p.NT + c];
                     bb += s_stat[(q * 2 + 1) * p.NT + c];
                 }
@@ -393,7 +415,7 @@ static int pick_nt(int C) {
 
 static size_t conv_smem_bytes(int T, int NT, int CK, int S, int P, int cin_pad) {
     size_t a = (size_t)(CK / 8) * P * 16, b = (size_t)9 * CK * NT * 2;
-    return S * (a + b) + (size_t)2 * P * 8 + (size_t)cin_pad * 12 + (size_t)8 * NT * 4 + (2 * S + 6) * 8 + 16 + 128;
+    return S * (a + b) + (size_t)2 * P * 8 + (size_t)cin_pad * 12 + (size_t)16 * NT * 4 + (2 * S + 6) * 8 + 16 + 128;
 }
 
 extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* pl) {
@@ -411,6 +433,7 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     const size_t budget = 220 * 1024;
     int bestT = 0, bestCK = 0, bestS = 0;
     // prefer: large T (halo amortisation) while keeping >= 2 waves of CTAs, CK=32, 2 stages
+    for (int minS = 2; minS >= 1 && !bestT; --minS)
     for (int T = (256 / NT < 4 ? 256 / NT : 4); T >= 1 && !bestT; --T) {
         if (T == 3) continue;
         const long long groups = ((Q + 128LL * T - 1) / (128LL * T)) * n_tiles;
@@ -419,7 +442,7 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
             if (cin_pad % CK != 0) continue;
             const int nch = cin_pad / CK;
             const int P = 128 * T + 2 * (W + 2) + 2;
-            for (int S = (nch >= 3 ? 3 : nch); S >= (nch >= 2 ? 2 : 1); --S) {
+            for (int S = 3; S >= minS; --S) {  // the stage ring runs across tile groups, so S may exceed the chunks per group
                 if ((size_t)P * 16 >= (1u << 18)) continue;
                 if (conv_smem_bytes(T, NT, CK, S, P, cin_pad) <= budget) { bestT = T; bestCK = CK; bestS = S; break; }
             }

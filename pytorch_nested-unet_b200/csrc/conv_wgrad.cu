@@ -38,8 +38,11 @@ __device__ unsigned long long g_wgrad_prof[16];
 #define WPROF_FLUSH(base, n) {}
 #endif
 
-constexpr int kWThreads = 320;
-constexpr int kWProducerWarps = 8;
+#ifndef NUNET_WGRAD_PRODUCER_WARPS
+#define NUNET_WGRAD_PRODUCER_WARPS 8
+#endif
+constexpr int kWProducerWarps = NUNET_WGRAD_PRODUCER_WARPS;   // warps 0..P-1 producers (then epilogue: first 8), warp P: MMA issuer
+constexpr int kWThreads = (kWProducerWarps + 2) * 32;
 
 // TRIPLE: three staggered gy copies, 3 MMAs of N=96 per K step; else one gy copy with the full halo and 9 MMAs of N=32
 // per K step (needs a third of the shared memory for gy: wide images).
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
     const int ci0 = m_tile * 128;
     const int mcg = min(16, (p.cin_pad - ci0) >> 3);  // staged channel groups of this M tile
 
-    if (warp == 8) {
+    if (warp == kWProducerWarps) {
         if (lane == 0) {
             for (int s = 0; s < p.S; ++s) {
                 mbar_init(&full[s], kWProducerWarps);
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
 
     if (warp < kWProducerWarps) {
         const int pl = lane & 7, r = lane >> 3;
-        const int tid = threadIdx.x;  // 0..255
+        const int tid = threadIdx.x;  // producer thread index
         WPROF_DECL
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int s = chunk % p.S;
@@ -107,8 +110,8 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             PixInfo* tab = tabs + (size_t)s * p.Pg;
             mbar_wait(&empty[s], ph ^ 1);
             WPROF_MARK(0)
-            for (int i = tid; i < p.Pg; i += 256) tab[i] = decode_position(k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, (int)p.Q);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = tid; i < p.Pg; i += kWProducerWarps * 32) tab[i] = decode_position(k0 - p.Wp - 1 + i, p.N, p.H, p.W, p.Wp, p.Hp1, (int)p.Q);
+            asm volatile("bar.sync 1, %0;" ::"n"(kWProducerWarps * 32) : "memory");
             WPROF_MARK(1)
             // ---- gy, all cp.async.  TRIPLE: three staggered copies (dc = 0,1,2) of 4 channel groups x Pg2 positions:
             //      plane (dc, cg) entry i holds position k0 - Wp - 1 + i + (2 - dc)  (= table index i + 2 - dc).
@@ -165,7 +168,8 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             WPROF_MARK(4)
         }
         if (tid == 0) WPROF_FLUSH(0, 5)
-        // ---- epilogue: TMEM -> fp32 partial block
+        // ---- epilogue: TMEM -> fp32 partial block (first 8 producer warps)
+        if (warp >= 8) goto done;
         mbar_wait(accum, 0);
         tc_fence_after();
         const int lq = warp & 3, half = warp >> 2;
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
                 for (int j = 0; j < 8; ++j) d[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kWProducerWarps) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, TRIPLE ? 96 : 32, kMajorMN, kMajorMN);
             const uint32_t a_hi = umma_desc_hi((uint32_t)p.KP * 16u), b_hi = umma_desc_hi((uint32_t)p.Pg2 * 16u);
@@ -222,9 +226,10 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
         __syncwarp();
     }
 
+done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem_base);
+    if (warp == kWProducerWarps) tmem_dealloc<512>(tmem_base);
 }
 
 // dW[co][ci][tap] (fp32 OIHW, ci < Cin real) = sum over splits, fixed order.

@@ -11,7 +11,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 y = torch.randn(N, H, W, Cin, generator=g, device=dev).to(torch.bfloat16)
 sc = torch.randn(Cin, generator=g, device=dev); sh = torch.randn(Cin, generator=g, device=dev)
 w = torch.randn(Cout, Cin, 3, 3, generator=g, device=dev) * 0.05
-src = ops.Source(L.SRC_SAME, y, Cin, sc, sh)
+src = ops.Source(L.SRC_ACT if os.environ.get('ACT') else L.SRC_SAME, y, Cin, sc, sh)
 gz = torch.randn(N, H, W, Cout, generator=g, device=dev).to(torch.bfloat16)
 yo = torch.randn(N, H, W, Cout, generator=g, device=dev).to(torch.bfloat16)
 k1, k2, k3 = (torch.randn(Cout, generator=g, device=dev) for _ in range(3))

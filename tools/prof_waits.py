@@ -10,20 +10,21 @@ rd.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_ulonglong * 16)()
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
-CASES = [("fwd", 256, 96, 96, [("same", 32)], 32), ("fwd", 256, 96, 96, [("same", 32)] * 4 + [("up", 64)], 32),
-         ("fwd", 256, 48, 48, [("same", 64)] * 3 + [("up", 128)], 64), ("fwd", 256, 24, 24, [("same", 128)] * 2 + [("up", 256)], 128),
-         ("fwd", 256, 12, 12, [("same", 256), ("up", 512)], 256), ("fwd", 256, 6, 6, [("same", 512)], 512),
-         ("dgrad", 256, 96, 96, [("grad", 32)], 192), ("dgrad", 256, 24, 24, [("grad", 128)], 512)]
+CASES = [("fwd", 256, 96, 96, [("same", 32)], 32), ("fwd", 256, 96, 96, [("act", 32)] * 4 + [("act", 64)], 32),
+         ("fwd", 256, 48, 48, [("act", 64)] * 3 + [("act", 128)], 64), ("fwd", 256, 24, 24, [("act", 128)] * 2 + [("act", 256)], 128),
+         ("fwd", 256, 12, 12, [("act", 256), ("act", 512)], 256), ("fwd", 256, 6, 6, [("same", 512)], 512),
+         ("dgrad", 256, 96, 96, [("act", 32)], 192), ("dgrad", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 48, 48, [("act", 64)], 320),
+         ("dgrad", 256, 24, 24, [("act", 128)], 512)]
 for kind, N, H, W, srcs, Cout in CASES:
     sources = []
     for k, Cc in srcs:
-        hs, ws = {"same": (H, W), "grad": (H, W), "up": (H // 2, W // 2)}[k]
+        hs, ws = {"same": (H, W), "grad": (H, W), "act": (H, W), "up": (H // 2, W // 2)}[k]
         y = torch.randn(N, hs, ws, Cc, generator=g, device=dev).to(torch.bfloat16)
         sc = torch.randn(Cc, generator=g, device=dev); sh = torch.randn(Cc, generator=g, device=dev)
         if k == "grad":
             sources.append(ops.Source(L.SRC_GRAD, y, Cc, sc, sh, data2=y, k2=sc))
         else:
-            sources.append(ops.Source({"same": L.SRC_SAME, "up": L.SRC_UP}[k], y, Cc, sc, sh))
+            sources.append(ops.Source({"same": L.SRC_SAME, "up": L.SRC_UP, "act": L.SRC_ACT}[k], y, Cc, sc, sh))
     cin = sum(c for _, c in srcs)
     plan = ops.conv_plan(N, H, W, cin, Cout)
     w = torch.randn(Cout, cin, 3, 3, generator=g, device=dev) * 0.05 if kind == "fwd" else torch.randn(cin, Cout, 3, 3, generator=g, device=dev) * 0.05
