@@ -17,6 +17,8 @@ NB_FILTER = (32, 64, 128, 256, 512)
 # Node outputs (up to 5 forward + 5 wgrad loaders re-read each) are activated once into a bf16 tensor; False = every
 # loader applies BatchNorm+ReLU itself from the raw conv output.
 MATERIALIZE_NODE_OUTPUTS = True
+import os as _os
+MATERIALIZE_ALL = _os.environ.get("NUNET_MATERIALIZE_ALL", "0") == "1"   # also a block's first conv output (one forward + one wgrad reader)
 # The upsampled skip operand is re-read by the forward conv and by Cout/32 wgrad CTAs per position; blending it in every
 # loader costs 4-8x the arithmetic of writing it once (measured: tools/prof_wgrad.py). False = fused NUNET_SRC_UP* loaders.
 MATERIALIZE_UPSAMPLED = True
@@ -211,7 +213,7 @@ def _forward(model, x, train):
         else:
             r.mean = r.invstd = None
             ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
-        if s.which == 2 and MATERIALIZE_NODE_OUTPUTS and s.consumers:
+        if (s.which == 2 or MATERIALIZE_ALL) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
             r.a = ops.bn_apply(y, r.scale, r.shift)
             if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
                 r.a_up = ops.upsample2x(r.a)
@@ -332,6 +334,42 @@ class _NetFunction(torch.autograd.Function):
         return (None, None) + tuple(out)
 
 
+# Eval-mode forwards (val.py:87-98) are ~65 short launches; at small batch the step is launch-bound, so the whole forward is
+# captured once per input shape into a CUDA graph and replayed (re-captured when any parameter changes).
+GRAPH_EVAL = _os.environ.get("NUNET_GRAPH_EVAL", "1") == "1"
+
+
+class _EvalGraph(object):
+    __slots__ = ("tag", "graph", "x", "outs")
+
+
+def _weights_tag(params):
+    return (params[0].data_ptr(), sum(p._version for p in params))
+
+
+def _graphed_eval(model, x, params):
+    st = _state(model)
+    graphs = st.__dict__.setdefault("graphs", {})
+    key = (tuple(x.shape), x.device.index)
+    tag = _weights_tag(params)
+    g = graphs.get(key)
+    if g is None or g.tag != tag:
+        with torch.no_grad():
+            _forward(model, x, False)                      # eager warm-up: fills the packed-weight cache, loads kernels
+        torch.cuda.current_stream().synchronize()
+        g = _EvalGraph()
+        g.tag = tag
+        g.x = x.clone()
+        g.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g.graph):
+            _, _, logits = _forward(model, g.x, False)
+        g.outs = tuple(t for _, t in logits)
+        graphs[key] = g
+    g.x.copy_(x)
+    g.graph.replay()
+    return tuple(t.clone() for t in g.outs)
+
+
 def run_model(model, x):
     """model(input) of the reference (trains.py:117-125, val.py:92-95)."""
     L.lib()  # fail loudly if the CUDA library is missing
@@ -339,6 +377,9 @@ def run_model(model, x):
     need_grad = model.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
     if need_grad:
         outs = _NetFunction.apply(model, x, *params)
+    elif (GRAPH_EVAL and not model.training and torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32
+          and x.is_contiguous() and not torch.cuda.is_current_stream_capturing() and _world(model) is None):
+        outs = _graphed_eval(model, x, params)
     else:
         with torch.no_grad():
             _, _, logits = _forward(model, x, model.training)
