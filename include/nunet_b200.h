@@ -67,6 +67,7 @@ typedef struct {
     int32_t T, NT, CK, S, P; /* M-tiles per CTA, N tile, channels per K chunk, pipeline stages, staged positions */
     int32_t nchunks, n_tiles, grid_m, cin_pad; /* grid_m = CTAs along x = rows of stat_part (persistent kernel) */
     int32_t smem_bytes, tmem_cols, ntg;       /* ntg = tile groups of 128*T positions */
+    int32_t tma_a_stage_bytes, tma_smem_bytes; /* > 0: the TMA tensor-load variant of this tiling fits (copy-mode sources) */
     int64_t wpack_elems; /* bf16 elements the packed weights occupy */
 } nunet_conv_plan_t;
 

@@ -19,6 +19,8 @@
 // train-mode BatchNorm, reduced by a transposing warp butterfly, one partial row per CTA).
 #include "conv_common.cuh"
 #include "loaders.cuh"
+#include "tma.cuh"
+#include <cstdlib>
 
 namespace nunet {
 
@@ -45,11 +47,14 @@ __device__ unsigned long long g_wait_prof[16];
 // Persistent: CTA (x, n_tile) processes tile groups x, x+gridDim.x, ... of 128*T positions each.  Accumulators and the
 // position table are double-buffered so the producers / tensor core work on group i+1 while the epilogue drains group i.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cgs = p.CK >> 3;
-    const uint32_t a_bytes = (uint32_t)cgs * p.P * 16u;
+    constexpr bool kTma = (MODE == MODE_ACT_TMA);
+    // TMA mode: an A stage is (P + Wp) whole padded rows of 32 channels (64-byte rows, 64B hardware swizzle) written by
+    // tensor loads; otherwise the no-swizzle [channel group][position][8] layout written by the producer warps.
+    const uint32_t a_bytes = kTma ? (uint32_t)p.a_stage_bytes : (uint32_t)cgs * p.P * 16u;
     const uint32_t b_bytes = 9u * p.CK * p.NT * 2u;
 
     uint8_t* sA = smem;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
     if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int s = 0; s < p.S; ++s) {
-                mbar_init(&full[s], kProducerWarps + 1);
+                mbar_init(&full[s], kTma ? 1 : kProducerWarps + 1);
                 mbar_init(&empty[s], 1);
             }
             for (int b = 0; b < 2; ++b) {
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (lane == 0) mbar_arrive(&tab_full[b]);
             PROF_MARK(1)
+            if constexpr (kTma) continue;  // operands are staged by the fetch warp's tensor loads
             int si = 0, src_c0 = 0;  // current source and its first concatenated channel
             for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                 const int s = cc % p.S;
@@ -305,8 +311,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                     mbar_wait(&full[s], ph);
                     PROF_MARK(1)
                     tc_fence_after();
-                    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA + (size_t)s * a_bytes), a_lbo);
                     const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB + (size_t)s * b_bytes), b_lbo);
+                    if constexpr (kTma) {
+                        // A rows are positions (64 B each, 64B swizzle, 8-row atoms of 512 B); the stage holds whole padded rows
+                        // starting at row R_lo, so position (q0 - Wp - 1) sits `woff` rows into it.  Address-field units are 16 B.
+                        const int qb = tg * group_positions - p.Wp - 1;
+                        const int R_lo = (qb >= 0) ? qb / p.Wp : -((-qb + p.Wp - 1) / p.Wp);
+                        const uint32_t woff = (uint32_t)(qb - R_lo * p.Wp);
+                        const uint32_t a_hi_sw = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B, version 1, SWIZZLE_64B
+                        const uint32_t a_base = ((smem_u32(sA + (size_t)s * a_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                        for (int t = 0; t < p.T; ++t) {
+                            const uint32_t d_addr = acc + (uint32_t)(t * p.NT);
+                            uint32_t b_lo = b_lo0;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint32_t a_lo = a_base + (woff + (uint32_t)(t * 128) + tapoff[tap]) * 4u;   // 64 B per position
+                                umma_bf16_lohi(d_addr, a_lo, a_hi_sw, b_lo, hi, idesc, (uint32_t)((chunk | tap) != 0));
+                                umma_bf16_lohi(d_addr, a_lo + 2u, a_hi_sw, b_lo + b_step, hi, idesc, 1u);         // next 16 channels: +32 B
+                                b_lo += 2 * b_step;
+                            }
+                        }
+                    } else {
+                    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA + (size_t)s * a_bytes), a_lbo);
                     for (int t = 0; t < p.T; ++t) {
                         const uint32_t d_addr = acc + (uint32_t)(t * p.NT);
                         const uint32_t a_t = a_lo0 + (uint32_t)(t * 128);
@@ -327,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
                             }
                         }
                     }
+                    }
                     umma_commit(&empty[s]);
                     PROF_MARK(2)
                 }
@@ -341,14 +368,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const ConvPa
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)n_tile * p.nchunks * b_bytes;
             int cc = 0;
             PROF_DECL
+            if constexpr (kTma) {
+                for (int si = 0; si < p.num_src; ++si) tma_prefetch_desc(&p.tmap[si]);
+            }
             for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x) {
+                int si = 0, src_c0 = 0;
+                // TMA mode: the padded rows [R_lo, R_lo + nrows) cover positions [q0 - Wp - 1, q0 + 128T + Wp + 1)
+                const int qb = tg * group_positions - p.Wp - 1;
+                const int R_lo = (qb >= 0) ? qb / p.Wp : -((-qb + p.Wp - 1) / p.Wp);
+                const int nrows = (qb - R_lo * p.Wp + p.P + p.Wp - 1) / p.Wp;
+                const uint32_t row_bytes = (uint32_t)p.Wp * 64u;
                 for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                     const int s = cc % p.S;
                     const uint32_t ph = (uint32_t)(cc / p.S) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     PROF_MARK(0)
-                    mbar_arrive_expect_tx(&full[s], b_bytes);
-                    bulk_g2s(sB + (size_t)s * b_bytes, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
+                    if constexpr (kTma) {
+                        const int cglob = chunk * 32;
+                        while (cglob >= src_c0 + p.src[si].C) { src_c0 += p.src[si].C; ++si; }
+                        mbar_arrive_expect_tx(&full[s], b_bytes + (uint32_t)nrows * row_bytes);
+                        bulk_g2s(sB + (size_t)s * b_bytes, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
+                        uint8_t* dstA = sA + (size_t)s * a_bytes;
+                        for (int r = 0; r < nrows; ++r) {
+                            const int R = R_lo + r;
+                            // padded row R = n*(H+1) + 1 + y ; separator rows (y = -1) and rows outside the batch are out of bounds -> zeros
+                            const int n = (R >= 0) ? R / p.Hp1 : -1;
+                            const int y = (R >= 0) ? R - n * p.Hp1 - 1 : 0;
+                            tma_load_4d(dstA + (size_t)r * row_bytes, &p.tmap[si], cglob - src_c0, -1, y, n, &full[s]);
+                        }
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], b_bytes);
+                        bulk_g2s(sB + (size_t)s * b_bytes, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
+                    }
                     PROF_MARK(1)
                 }
             }
@@ -461,6 +512,15 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     }
     pl->cin_pad = cin_pad;
     pl->smem_bytes = (int)conv_smem_bytes(bestT, NT, bestCK, bestS, pl->P, cin_pad);
+    // TMA variant of the same tiling: A stage = (P + Wp) rows of 64 B rounded to 1 KB (first in shared memory: 1 KB aligned)
+    pl->tma_a_stage_bytes = 0;
+    pl->tma_smem_bytes = 0;
+    if (bestCK == 32) {
+        const size_t a_tma = (((size_t)(pl->P + 2 * (W + 2)) * 64) + 1023) & ~(size_t)1023;  // whole rows: up to 2 Wp - 2 extra positions
+        const size_t a_old = (size_t)4 * pl->P * 16;
+        const size_t total = (size_t)pl->smem_bytes + bestS * (a_tma - a_old) + 1024;
+        if (total <= 227 * 1024) { pl->tma_a_stage_bytes = (int)a_tma; pl->tma_smem_bytes = (int)total; }
+    }
     int cols = 2 * bestT * NT, tc = 32;
     while (tc < cols) tc <<= 1;
     pl->tmem_cols = tc;
@@ -517,7 +577,22 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
         case MODE_POOL: return launch_conv<MODE_POOL>(p, pl, (cudaStream_t)stream);
         case MODE_SAME_UP: return launch_conv<MODE_SAME_UP>(p, pl, (cudaStream_t)stream);
         case MODE_GRAD: return launch_conv<MODE_GRAD>(p, pl, (cudaStream_t)stream);
-        case MODE_ACT: return launch_conv<MODE_ACT>(p, pl, (cudaStream_t)stream);
+        case MODE_ACT: {
+            // tensor-load path: box = (32 ch, W+2 px, 1, 1) per padded row, needs W+2 <= 256 and the CK=32 tiling
+            static const bool no_tma = getenv("NUNET_NO_TMA") != nullptr;
+            if (!no_tma && pl.CK == 32 && d->W + 2 <= 256 && pl.tma_smem_bytes > 0) {
+                bool ok = true;
+                for (int i = 0; i < d->num_src && ok; ++i)
+                    ok = encode_nhwc_map(&p.tmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, d->W + 2, 64) == 0;
+                if (ok) {
+                    nunet_conv_plan_t pt = pl;
+                    pt.smem_bytes = pl.tma_smem_bytes;
+                    p.a_stage_bytes = pl.tma_a_stage_bytes;
+                    return launch_conv<MODE_ACT_TMA>(p, pt, (cudaStream_t)stream);
+                }
+            }
+            return launch_conv<MODE_ACT>(p, pl, (cudaStream_t)stream);
+        }
         case MODE_POOL_ACT: return launch_conv<MODE_POOL_ACT>(p, pl, (cudaStream_t)stream);
         case MODE_ACT_UP: return launch_conv<MODE_ACT_UP>(p, pl, (cudaStream_t)stream);
     }

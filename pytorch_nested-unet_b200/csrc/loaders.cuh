@@ -236,7 +236,8 @@ __device__ __forceinline__ void stage_blocks_cpasync(const ConvSrc& s, const Pix
 
 // Source-kind combinations that occur in the network; the conv kernels are specialised on them so that only the loader
 // variants a launch can need are compiled into it (keeps the producer loop in registers).
-enum { MODE_INPUT = 0, MODE_SAME = 1, MODE_POOL = 2, MODE_SAME_UP = 3, MODE_GRAD = 4, MODE_ACT = 5, MODE_POOL_ACT = 6, MODE_ACT_UP = 7 };
+enum { MODE_INPUT = 0, MODE_SAME = 1, MODE_POOL = 2, MODE_SAME_UP = 3, MODE_GRAD = 4, MODE_ACT = 5, MODE_POOL_ACT = 6, MODE_ACT_UP = 7,
+       MODE_ACT_TMA = 8 /* all sources pre-activated, same resolution, staged by TMA tensor loads (conv_igemm only) */ };
 
 template <int MODE>
 __device__ __forceinline__ void stage_blocks_mode(const ConvSrc& s, int H, int W, const PixInfo* __restrict__ tab, int tab_off, int plimit,
@@ -250,7 +251,7 @@ __device__ __forceinline__ void stage_blocks_mode(const ConvSrc& s, int H, int W
         stage_blocks<NUNET_SRC_POOL, 2>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
     } else if constexpr (MODE == MODE_GRAD) {
         stage_blocks<NUNET_SRC_GRAD, 4>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
-    } else if constexpr (MODE == MODE_ACT) {
+    } else if constexpr (MODE == MODE_ACT || MODE == MODE_ACT_TMA) {
         stage_blocks_cpasync(s, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, dst);
     } else if constexpr (MODE == MODE_POOL_ACT) {
         stage_blocks<NUNET_SRC_POOL_ACT, 2>(s, H, W, tab, tab_off, plimit, first_blk, nblk, blk_stride, pl, ch, sc, sh, k2, dst);
