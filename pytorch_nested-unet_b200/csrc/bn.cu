@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
         for (int u = 0; u < 4; ++u) {
             const long long gi = g + u * stride;
             if (gi >= ngroups) continue;
-            const int c0 = (int)(gi % cgs) * 8;
+            const int c0 = (int)(gi & (long long)(cgs - 1)) * 8;   // C/8 is a power of two (host-checked)
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r[u]);
             uint32_t o[4];
 #pragma unroll
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* gz, cons
         for (int u = 0; u < 2; ++u) {
             const long long gi = g + u * stride;
             if (gi >= ngroups) continue;
-            const int c0 = (int)(gi % cgs) * 8;
+            const int c0 = (int)(gi & (long long)(cgs - 1)) * 8;
             const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&rg[u]);
             const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&ry[u]);
             uint32_t o[4];
@@ -194,36 +194,51 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* gz, cons
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int N, int h, int w, int cgs,
                                                          __nv_bfloat16* __restrict__ out) {
     const int H = 2 * h, W = 2 * w, C = cgs * 8;
-    const long long items = (long long)N * H * W * cgs;
+    const int cg_shift = 31 - __clz(cgs);  // C/8 is a power of two
+    const unsigned items = (unsigned)N * H * W * cgs;   // < 2^31 (checked by the host)
     const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
     const float rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(it % cgs);
-        long long pix = it / cgs;
-        const int X = (int)(pix % W); pix /= W;
-        const int Y = (int)(pix % H);
-        const int n = (int)(pix / H);
-        const float sy = ry * (float)Y, sx = rx * (float)X;
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
-        const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-        const __nv_bfloat16* base = in + (size_t)n * h * w * C + cg * 8;
-        const uint4 r00 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * C));
-        const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * C));
-        const uint4 r10 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * C));
-        const uint4 r11 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * C));
-        const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&r00), *b = reinterpret_cast<const __nv_bfloat162*>(&r01),
-                             *c = reinterpret_cast<const __nv_bfloat162*>(&r10), *d = reinterpret_cast<const __nv_bfloat162*>(&r11);
-        uint32_t o[4];
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 2 * stride) {
+        uint4 r[2][4];
+        float wts[2][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 fa = __bfloat1622float2(a[i]), fb = __bfloat1622float2(b[i]), fc = __bfloat1622float2(c[i]), fd = __bfloat1622float2(d[i]);
-            const float v0 = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
-            const float v1 = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
-            __nv_bfloat162 q = __floats2bfloat162_rn(v0, v1);
-            o[i] = *reinterpret_cast<uint32_t*>(&q);
+        for (int u = 0; u < 2; ++u) {
+            const unsigned it = it0 + u * stride;
+            if (it >= items) continue;
+            const int cg = it & (cgs - 1);
+            unsigned pix = it >> cg_shift;
+            const int X = pix % W; pix /= W;
+            const int Y = pix % H;
+            const int n = pix / H;
+            const float sy = ry * (float)Y, sx = rx * (float)X;
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+            wts[u][1] = sy - (float)y0; wts[u][3] = sx - (float)x0; wts[u][0] = 1.f - wts[u][1]; wts[u][2] = 1.f - wts[u][3];
+            const __nv_bfloat16* base = in + (size_t)n * h * w * C + cg * 8;
+            r[u][0] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * C));
+            r[u][1] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * C));
+            r[u][2] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * C));
+            r[u][3] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * C));
         }
-        *reinterpret_cast<uint4*>(out + (size_t)it * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned it = it0 + u * stride;
+            if (it >= items) continue;
+            const float ly0 = wts[u][0], ly1 = wts[u][1], lx0 = wts[u][2], lx1 = wts[u][3];
+            const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&r[u][0]), *b = reinterpret_cast<const __nv_bfloat162*>(&r[u][1]),
+                                 *c = reinterpret_cast<const __nv_bfloat162*>(&r[u][2]), *d = reinterpret_cast<const __nv_bfloat162*>(&r[u][3]);
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = __bfloat1622float2(a[i]), fb = __bfloat1622float2(b[i]), fc = __bfloat1622float2(c[i]), fd = __bfloat1622float2(d[i]);
+                const float v0 = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
+                const float v1 = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
+                __nv_bfloat162 q = __floats2bfloat162_rn(v0, v1);
+                o[i] = *reinterpret_cast<uint32_t*>(&q);
+            }
+            *reinterpret_cast<uint4*>(out + (size_t)it * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -295,7 +310,7 @@ extern "C" int nunet_bn_backward_from_sums(const double* sums, int32_t C, double
 }
 
 extern "C" int nunet_bn_apply(const void* y, const float* scale, const float* shift, long long npix, int32_t C, void* a, void* stream) {
-    if (!y || !scale || !shift || !a || npix <= 0 || C <= 0 || C % 8 != 0 || C > 4096) return NUNET_E_BADARG;
+    if (!y || !scale || !shift || !a || npix <= 0 || C <= 0 || C % 8 != 0 || C > 4096 || ((C / 8) & (C / 8 - 1)) != 0) return NUNET_E_BADARG;
     const long long ngroups = npix * (C / 8);
     long long blocks = (ngroups + 1023) / 1024;
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -305,7 +320,7 @@ extern "C" int nunet_bn_apply(const void* y, const float* scale, const float* sh
 
 extern "C" int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1, const float* k2, const float* k3, long long npix,
                                   int32_t C, void* gy, void* stream) {
-    if (!gz || !y || !k1 || !k2 || !k3 || !gy || npix <= 0 || C <= 0 || C % 8 != 0 || C > 2048) return NUNET_E_BADARG;
+    if (!gz || !y || !k1 || !k2 || !k3 || !gy || npix <= 0 || C <= 0 || C % 8 != 0 || C > 2048 || ((C / 8) & (C / 8 - 1)) != 0) return NUNET_E_BADARG;
     const long long ngroups = npix * (C / 8);
     long long blocks = (ngroups + 511) / 512;
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -317,7 +332,8 @@ extern "C" int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1
 extern "C" int nunet_upsample2x(const void* in, int32_t N, int32_t h, int32_t w, int32_t C, void* out, void* stream) {
     if (!in || !out || N < 1 || h < 1 || w < 1 || C < 8 || C % 8 != 0) return NUNET_E_BADARG;
     const long long items = (long long)N * 4 * h * w * (C / 8);
-    long long blocks = (items + 255) / 256;
+    if (items >= (1LL << 31) || ((C / 8) & (C / 8 - 1)) != 0) return NUNET_E_UNSUPPORTED;
+    long long blocks = (items + 511) / 512;
     if (blocks > 148 * 16) blocks = 148 * 16;
     upsample2x_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, h, w, C / 8, (__nv_bfloat16*)out);
     return cuda_rc();
