@@ -271,8 +271,18 @@ def run_native(args):
         total_ms = sum(timing["by_class"].values())
         _, train_fl = conv_flops_per_image(args.arch, S)
         tflops = train_fl * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic = None
+        try:  # DRAM bytes of the same kernels, from the committed ncu pass (profiles/r01_traffic.json; batch 256 @96x96 only)
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("batch") == B and tj.get("size") == S and args.arch == "NestedUNet" and ds:
+                traffic = tj["conv_dram_bytes_per_step"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "achieved": tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tflops / pk["tc_sustained"],
-                "traffic": None, "kernel": "conv3x3_igemm_kernel + conv3x3_wgrad_kernel (all 89 conv launches of one step)",
+                "traffic": traffic, "traffic_note": "dram__bytes_read+write summed over the step's conv launches (ncu, profiles/r01_ncu_dram_bytes.csv); "
+                                                    "the unit of `achieved` is likewise one step's conv launches",
+                "algorithmic_flops_per_step": train_fl * B, "kernel": "conv3x3_igemm_kernel + conv3x3_wgrad_kernel (all 89 conv launches of one step)",
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "kernel_ms_per_step": conv_ms, "all_kernels_ms_per_step": total_ms,
                 "class_ms": {k: round(v, 4) for k, v in sorted(timing["by_class"].items())}}
