@@ -8,6 +8,8 @@ raw bf16 NHWC conv outputs.  The backward pass (an autograd.Function so that `lo
 working on the fp32 master parameters) runs, per conv in reverse order: gradient router + BN/ReLU backward reduction,
 split-K wgrad, dgrad — all CUDA kernels behind the C ABI; nothing here calls an ATen compute op on activations.
 """
+import os as _os
+
 import torch
 
 import _lib as L
@@ -17,11 +19,11 @@ NB_FILTER = (32, 64, 128, 256, 512)
 # Node outputs (up to 5 forward + 5 wgrad loaders re-read each) are activated once into a bf16 tensor; False = every
 # loader applies BatchNorm+ReLU itself from the raw conv output.
 MATERIALIZE_NODE_OUTPUTS = True
-import os as _os
 MATERIALIZE_ALL = _os.environ.get("NUNET_MATERIALIZE_ALL", "0") == "1"   # also a block's first conv output (one forward + one wgrad reader)
 # The upsampled skip operand is re-read by the forward conv and by Cout/32 wgrad CTAs per position; blending it in every
 # loader costs 4-8x the arithmetic of writing it once (measured: tools/prof_wgrad.py). False = fused NUNET_SRC_UP* loaders.
 MATERIALIZE_UPSAMPLED = True
+WGRAD_SIDE_STREAM = _os.environ.get("NUNET_WGRAD_SIDE_STREAM", "1") == "1"
 
 
 # --------------------------------------------------------------------------------------------- graphs
@@ -240,6 +242,12 @@ def _backward(model, x, recs, grad_logits):
     ws = st.workspace(dev)
     dp = _world(model)
     grads, dxs = {}, {}
+    main = torch.cuda.current_stream(dev)
+    side = None
+    if WGRAD_SIDE_STREAM and dp is None and not torch.cuda.is_current_stream_capturing():
+        side = st.__dict__.get("side_stream")
+        if side is None:
+            side = st.__dict__["side_stream"] = torch.cuda.Stream(device=dev)
     buckets = dp.buckets if dp is not None else None
     if buckets is not None:
         buckets.begin(dev)
@@ -293,7 +301,16 @@ def _backward(model, x, recs, grad_logits):
         gy = ops.bn_bwd_apply(gz, r.y, k1, k2, k3, out=gz)  # in place: g_z is dead once the BN sums are reduced
         srcs = _sources(s, recs, x)
         dw = galloc(s.conv.weight)
-        ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw)
+        if side is None:
+            ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw)
+        else:
+            # the weight gradient is only needed when backward returns: run it on a second stream so that the HBM-bound
+            # router / BN kernels of the following layers execute while it occupies the tensor pipes
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw)
+            gy.record_stream(side)
+            dw.record_stream(side)
         gdone(s.conv.weight, dw)
         if s.conv.bias is not None:
             # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
@@ -305,6 +322,8 @@ def _backward(model, x, recs, grad_logits):
         for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
             if specs[m].sources[0][0] == s.idx:
                 dxs.pop(m, None)
+    if side is not None:
+        main.wait_stream(side)
     if buckets is not None:
         buckets.finish()
     return grads
