@@ -38,6 +38,13 @@ class GradBuckets(object):
         self.flat = None
         self.pending = None
         self.works = []
+        self.side = None  # optional second CUDA stream some gradients are produced on (engine: wgrad side stream)
+
+    def _launch(self, s, e):
+        if self.side is not None and self.flat.is_cuda:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.side)   # the bucket holds gradients of both streams
+        op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
+        self.works.append((dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True), s, e, op))
 
     def begin(self, device):
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
@@ -55,19 +62,14 @@ class GradBuckets(object):
         b = self.bucket_of[id(p)]
         self.pending[b] -= 1
         if self.pending[b] == 0:
-            s, e = self.bucket_ranges[b]
-            op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
-            w = dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True)
-            self.works.append((w, s, e, op))
+            self._launch(*self.bucket_ranges[b])
 
     def finish(self):
         """Flushes buckets whose parameters produced no gradient (kept zero) and waits (stream-level) for all transfers."""
         for b, left in enumerate(self.pending):
             if left > 0:
                 self.pending[b] = 0
-                s, e = self.bucket_ranges[b]
-                op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
-                self.works.append((dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True), s, e, op))
+                self._launch(*self.bucket_ranges[b])
         ws = dist.get_world_size(self.group)
         for w, s, e, op in self.works:
             w.wait()

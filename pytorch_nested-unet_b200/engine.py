@@ -244,13 +244,14 @@ def _backward(model, x, recs, grad_logits):
     grads, dxs = {}, {}
     main = torch.cuda.current_stream(dev)
     side = None
-    if WGRAD_SIDE_STREAM and dp is None and not torch.cuda.is_current_stream_capturing():
+    if WGRAD_SIDE_STREAM and not torch.cuda.is_current_stream_capturing():
         side = st.__dict__.get("side_stream")
         if side is None:
             side = st.__dict__["side_stream"] = torch.cuda.Stream(device=dev)
     buckets = dp.buckets if dp is not None else None
     if buckets is not None:
         buckets.begin(dev)
+        buckets.side = side
 
     def galloc(p):
         return buckets.view(p) if buckets is not None else torch.empty(p.shape, dtype=torch.float32, device=dev)
