@@ -260,11 +260,15 @@ def run_native(args):
     roof = None
     layer_rows = []
     # every rank runs the extra (untimed) profiling step: under DP it contains collectives
+    import engine
+    side_saved = engine.WGRAD_SIDE_STREAM
+    engine.WGRAD_SIDE_STREAM = False            # per-kernel CUDA events need every launch on the one (launching) stream
     ops.enable_kernel_timing(rank == 0)
     step(x_dev, t_dev)
     torch.cuda.synchronize()
     timing = ops.collect_kernel_timing() if rank == 0 else None
     ops.enable_kernel_timing(False)
+    engine.WGRAD_SIDE_STREAM = side_saved
     barrier()
     if rank == 0:
         conv_ms = sum(v for k, v in timing["by_class"].items() if k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
     float* s_shift = s_scale + p.cin_pad;
     float* s_k2 = s_shift + p.cin_pad;
     float* s_stat = s_k2 + p.cin_pad;  // [8 epilogue warps][2][NT], each slot owned by one thread (deterministic)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 16 * p.NT);
+    uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_stat + 16 * p.NT);  // [8 epilogue warps][32 rows][80 B] transpose scratch
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + kEpilogueWarps * 32 * 80);
     uint64_t* full = bars;                 // [S]  producers + fetcher -> MMA
     uint64_t* empty = bars + p.S;          // [S]  MMA -> producers + fetcher
     uint64_t* acc_full = bars + 2 * p.S;   // [2]  MMA -> epilogue
@@ -189,26 +190,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);
             if (!want_stats) {
-                // plain store path (dgrad, eval): 32 columns per TMEM load -> 64 contiguous bytes per pixel and lane
+                // plain store path (dgrad, eval): 32 columns per TMEM load = 64 bytes per pixel row.  A lane owns a ROW, so a direct
+                // store would touch 32 different 128-byte lines per instruction; the 32x64 B tile is transposed through a padded
+                // per-warp smem scratch so that four lanes write one row's 64 contiguous bytes (8 lines per store instruction).
                 const int nslab32 = p.NT >> 5;
+                uint8_t* scratch = s_epi + (size_t)(warp - kEpilogueWarp0) * (32 * 80);
                 for (int t = 0; t < p.T; ++t) {
                     const PixInfo pi = tab[t * 128 + lq * 32 + lane + p.Wp + 1];
                     for (int cs = half; cs < nslab32; cs += 2) {
                         uint32_t v[32];
                         tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
                         tmem_ld_wait();
-                        if (pi.pix >= 0) {
-                            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pi.pix * p.Cout + n_tile * p.NT + cs * 32);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 o;
-                                o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                                o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                                o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                                o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                                dst[j] = o;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 o;
+                            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(scratch + lane * 80 + j * 16) = o;
                         }
+                        __syncwarp();
+                        __nv_bfloat16* obase = out + n_tile * p.NT + cs * 32 + (lane & 3) * 8;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = i * 8 + (lane >> 2);
+                            const int rpix = __shfl_sync(0xffffffffu, pi.pix, row);
+                            const uint4 o = *reinterpret_cast<const uint4*>(scratch + row * 80 + (lane & 3) * 16);
+                            if (rpix >= 0) *reinterpret_cast<uint4*>(obase + (size_t)rpix * p.Cout) = o;
+                        }
+                        __syncwarp();
                     }
                 }
             } else {
@@ -466,7 +477,7 @@ static int pick_nt(int C) {
 
 static size_t conv_smem_bytes(int T, int NT, int CK, int S, int P, int cin_pad) {
     size_t a = (size_t)(CK / 8) * P * 16, b = (size_t)9 * CK * NT * 2;
-    return S * (a + b) + (size_t)2 * P * 8 + (size_t)cin_pad * 12 + (size_t)16 * NT * 4 + (2 * S + 6) * 8 + 16 + 128;
+    return S * (a + b) + (size_t)2 * P * 8 + (size_t)cin_pad * 12 + (size_t)16 * NT * 4 + 8 * 32 * 80 + (2 * S + 6) * 8 + 16 + 128;
 }
 
 extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* pl) {
