@@ -177,6 +177,8 @@ int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1, const flo
  * as the forward conv (src[]).  part: plan.part_elems fp32 of scratch. */
 typedef struct {
     int32_t KP, S, Pg, cpc, nchunks_total, splits, m_tiles, n_tiles, cin_pad, smem_bytes, triple;
+    /* TMA variant (all sources pre-activated, same resolution): r padded rows of PW pixels per K chunk */
+    int32_t tma, tma_PW, tma_r, tma_S, tma_G, tma_Nt, tma_splits, tma_cpc, tma_chunks, tma_smem_bytes;
     int64_t part_elems;
 } nunet_wgrad_plan_t;
 typedef struct {

@@ -43,7 +43,8 @@ class RouterDesc(C.Structure):
 
 class WgradPlan(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("KP", "S", "Pg", "cpc", "nchunks_total", "splits", "m_tiles", "n_tiles", "cin_pad",
-                                         "smem_bytes", "triple")] + [("part_elems", C.c_int64)]
+                                         "smem_bytes", "triple", "tma", "tma_PW", "tma_r", "tma_S", "tma_G", "tma_Nt", "tma_splits",
+                                         "tma_cpc", "tma_chunks", "tma_smem_bytes")] + [("part_elems", C.c_int64)]
 
 
 class WgradDesc(C.Structure):

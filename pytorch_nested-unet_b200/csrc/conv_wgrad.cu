@@ -252,6 +252,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
 
 using namespace nunet;
 
+int nunet_wgrad_tma_plan(int N, int H, int W, int cin_pad, int Cout, nunet_wgrad_plan_t* pl);
+int nunet_wgrad_tma_launch(const nunet_wgrad_desc_t* d, const nunet_wgrad_plan_t& pl, int cin_real, cudaStream_t stream);
+
 static size_t wgrad_smem_bytes(int KP, int S, int Pg, int planes, int Pg2, int cin_pad) {
     return (size_t)S * (256ull * KP + 64ull * planes * Pg2 + 8ull * Pg) + (size_t)cin_pad * 8 + (2 * S + 1) * 8 + 16 + 128;
 }
@@ -307,6 +310,10 @@ extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t
     pl->triple = triple;
     pl->smem_bytes = (int)wgrad_smem_bytes(KP, S, pl->Pg, triple ? 3 : 1, triple ? KP + 2 * (W + 2) : pl->Pg, cin_pad);
     pl->part_elems = (int64_t)splits * n_tiles * 9 * cin_pad * 32;
+    if (nunet_wgrad_tma_plan(N, H, W, cin_pad, Cout, pl) == 0) {
+        const int64_t pe = (int64_t)pl->tma_splits * 9 * cin_pad * Cout;
+        if (pe > pl->part_elems) pl->part_elems = pe;
+    }
     return NUNET_OK;
 }
 
@@ -342,6 +349,14 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
     nunet_wgrad_plan_t pl;
     int rc = nunet_conv3x3_wgrad_plan(d->N, d->H, d->W, cin, d->Cout, &pl);
     if (rc) return rc;
+    if (pl.tma) {
+        bool all_act = true;
+        for (int i = 0; i < d->num_src; ++i) all_act = all_act && d->src[i].kind == NUNET_SRC_ACT;
+        if (all_act) {
+            const int trc = nunet_wgrad_tma_launch(d, pl, cin_real, (cudaStream_t)stream);
+            if (trc >= 0) return trc;   // < 0: tensor-map encoding unavailable -> cp.async kernel below
+        }
+    }
     WgradParams p{};
     p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
     p.Q = ((long long)d->N * (d->H + 1) + 1) * (d->W + 2);

@@ -7,10 +7,11 @@
 
 namespace nunet {
 
-// bf16 NHWC activation tensor [N,H,W,C] viewed as (C, W, H, N); box = (box_c channels, box_w pixels, 1, 1).
+// bf16 NHWC activation tensor [N,H,W,C] viewed as (C, W, H, N); box = (box_c channels, box_w pixels, box_h rows, box_n images).
 // Out-of-bounds box elements (x = -1, x = W, y = -1, y = H, n outside) are zero-filled: exactly the conv's zero padding
 // and the separator rows of the flattened padded geometry.  swizzle_bytes in {64, 128} must equal box_c * 2.
-static inline int encode_nhwc_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int box_w, int swizzle_bytes) {
+static inline int encode_nhwc_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c, int box_w, int swizzle_bytes,
+                                  int box_h = 1, int box_n = 1) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn fn = nullptr;
@@ -22,7 +23,7 @@ static inline int encode_nhwc_map(CUtensorMap* map, const void* base, int N, int
     }
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -156,6 +156,15 @@ WG_CASES = [
     (2, 8, 8, [("pool_act", 64)], 128),
     (8, 96, 96, [("same_act", 32), ("up_act", 64)], 32),
     (2, 6, 6, [("same_act", 256), ("up_act", 512)], 256),
+    # all sources pre-activated at the conv's resolution: the TMA-fed MN-major kernel (conv_wgrad_tma.cu)
+    (2, 32, 32, [("same_act", 32), ("same_act", 32), ("same_act", 32)], 32),
+    (8, 96, 96, [("same_act", 32), ("same_act", 64)], 32),
+    (3, 48, 80, [("same_act", 32)] * 5, 32),
+    (2, 16, 16, [("same_act", 64), ("same_act", 64), ("same_act", 128)], 64),
+    (2, 24, 24, [("same_act", 128), ("same_act", 256)], 128),
+    (3, 12, 20, [("same_act", 256), ("same_act", 512)], 256),
+    (2, 6, 6, [("same_act", 512)], 512),
+    (5, 6, 6, [("same_act", 256)], 512),
 ]
 
 

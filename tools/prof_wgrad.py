@@ -10,9 +10,10 @@ rd.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_ulonglong * 16)()
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
-CASES = [(256, 96, 96, [("act", 32)], 32), (256, 96, 96, [("same", 32)], 32), (256, 96, 96, [("act", 32)] * 4 + [("up_act", 64)], 32),
-         (256, 48, 48, [("act", 64)] * 3 + [("up_act", 128)], 64), (256, 24, 24, [("act", 128)] * 2 + [("up_act", 256)], 128),
-         (256, 12, 12, [("act", 256), ("up_act", 512)], 256), (256, 6, 6, [("same", 512)], 512)]
+CASES = [(256, 96, 96, [("same", 32)], 32), (256, 96, 96, [("act", 32)] * 4 + [("act", 64)], 32),
+         (256, 48, 48, [("same", 64)], 64), (256, 48, 48, [("act", 64)] * 3 + [("act", 128)], 64), (256, 24, 24, [("same", 128)], 128),
+         (256, 24, 24, [("act", 128)] * 2 + [("act", 256)], 128),
+         (256, 12, 12, [("act", 256), ("act", 512)], 256), (256, 6, 6, [("same", 512)], 512)]
 for N, H, W, srcs, Cout in CASES:
     sources = []
     for k, Cc in srcs:
@@ -33,5 +34,5 @@ for N, H, W, srcs, Cout in CASES:
     nct = plan.splits * plan.m_tiles * plan.n_tiles
     v = [x / nct / 1e3 for x in buf]
     ms = e0.elapsed_time(e1); fl = 2.0 * N * H * W * cin * Cout * 9
-    print("wgrad %dx%d cin %d cout %d: %.3f ms %.0f TF/s | KP=%d S=%d triple=%d cpc=%d ctas=%d (%.1f/SM)" % (H, W, cin, Cout, ms, fl / ms / 1e9, plan.KP, plan.S, plan.triple, plan.cpc, nct, nct / 148.0))
+    print("wgrad %dx%d cin %d cout %d: %.3f ms %.0f TF/s | KP=%d S=%d cpc=%d ctas=%d (%.1f/SM) m_tiles=%d n_tiles=%d" % (H, W, cin, Cout, ms, fl / ms / 1e9, plan.KP, plan.S, plan.cpc, nct, nct / 148.0, plan.m_tiles, plan.n_tiles))
     print("   kcycles/CTA producer: wait_empty %.0f table %.0f gy %.0f x %.0f wait_copy %.0f | mma: wait_full %.0f issue %.0f" % (v[0], v[1], v[2], v[3], v[4], v[8], v[9]))
