@@ -189,7 +189,13 @@ typedef struct {
     const void* gy; /* bf16 NHWC [N,H,W,Cout]: g_y = k1*g_z + k2*y + k3 from nunet_bn_bwd_apply */
     float* part;
     float* dw;
+    int32_t cin_real; /* 0: sum of the sources' channels; else the leading channels that exist in dw (zero-padded stem input) */
 } nunet_wgrad_desc_t;
+/* 2x2/stride-2 max-pool of an activated bf16 NHWC tensor (nn.MaxPool2d(2,2), finished/archs1.py:80 applied to a node output):
+ * out [N,H/2,W/2,C]. */
+int nunet_maxpool2x2(const void* in, int32_t N, int32_t H, int32_t W, int32_t C, void* out, void* stream);
+/* fp32 NCHW network input [N,C,H,W], C <= 32 -> bf16 NHWC [N,H,W,32] with zero channels >= C (stem conv operand). */
+int nunet_input_to_nhwc32(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* out, void* stream);
 int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* plan);
 int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
 

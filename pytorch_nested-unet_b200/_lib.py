@@ -49,7 +49,7 @@ class WgradPlan(C.Structure):
 
 class WgradDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_src", C.c_int32), ("src", Src * MAX_SRC),
-                ("Cout", C.c_int32), ("gy", C.c_void_p), ("part", C.c_void_p), ("dw", C.c_void_p)]
+                ("Cout", C.c_int32), ("gy", C.c_void_p), ("part", C.c_void_p), ("dw", C.c_void_p), ("cin_real", C.c_int32)]
 
 
 class NunetError(RuntimeError):
@@ -85,6 +85,8 @@ _SIGS = {
     "nunet_bn_apply": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_bwd_apply": ([C.c_void_p] * 5 + [C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_upsample2x": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_maxpool2x2": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_input_to_nhwc32": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
 }
 

@@ -242,6 +242,52 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
     }
 }
 
+// 2x2 max-pool (stride 2) of an activated bf16 NHWC tensor: out[N,H/2,W/2,C].  Materialised once for the backbone nodes so
+// that the pooled consumer's forward and weight-gradient convolutions run in pure copy / TMA mode.
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const uint4* __restrict__ in, int N, int H, int W, int cgs, uint4* __restrict__ out) {
+    const int h = H >> 1, w = W >> 1;
+    const int cg_shift = 31 - __clz(cgs);
+    const unsigned items = (unsigned)N * h * w * cgs;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+        const int cg = it & (cgs - 1);
+        unsigned pix = it >> cg_shift;
+        const int x = pix % w; pix /= w;
+        const int y = pix % h;
+        const int n = pix / h;
+        const size_t base = (((size_t)n * H + 2 * y) * W + 2 * x) * cgs + cg;
+        const uint4 r0 = __ldg(in + base), r1 = __ldg(in + base + cgs), r2 = __ldg(in + base + (size_t)W * cgs), r3 = __ldg(in + base + (size_t)W * cgs + cgs);
+        const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&r0), *b = reinterpret_cast<const __nv_bfloat162*>(&r1),
+                             *c = reinterpret_cast<const __nv_bfloat162*>(&r2), *d = reinterpret_cast<const __nv_bfloat162*>(&r3);
+        uint4 o;
+        __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = __hmax2(__hmax2(a[i], b[i]), __hmax2(c[i], d[i]));
+        out[it] = o;
+    }
+}
+
+// Network input fp32 NCHW [N,C,H,W] (C <= 32) -> bf16 NHWC [N,H,W,32], channels >= C zero: the stem conv then runs as a
+// pre-activated 32-channel copy-mode source (forward) and through the TMA weight-gradient kernel.
+__global__ void __launch_bounds__(256) input_to_nhwc32_kernel(const float* __restrict__ x, int N, int C, long long HW, uint4* __restrict__ out) {
+    const long long items = (long long)N * HW * 4;   // 16-byte groups of 8 channels
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(it & 3);
+        const long long pix = it >> 2;
+        const long long n = pix / HW, hw = pix - n * HW;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = cg * 8 + e;
+            v[e] = (c < C) ? __ldg(x + ((size_t)n * C + c) * HW + hw) : 0.f;
+        }
+        uint4 o;
+        __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        out[it] = o;
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -336,5 +382,24 @@ extern "C" int nunet_upsample2x(const void* in, int32_t N, int32_t h, int32_t w,
     long long blocks = (items + 511) / 512;
     if (blocks > 148 * 16) blocks = 148 * 16;
     upsample2x_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, h, w, C / 8, (__nv_bfloat16*)out);
+    return cuda_rc();
+}
+
+extern "C" int nunet_maxpool2x2(const void* in, int32_t N, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
+    if (!in || !out || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 8 || C % 8 != 0 || ((C / 8) & (C / 8 - 1)) != 0) return NUNET_E_BADARG;
+    const long long items = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    if (items >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    maxpool2x2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)in, N, H, W, C / 8, (uint4*)out);
+    return cuda_rc();
+}
+
+extern "C" int nunet_input_to_nhwc32(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* out, void* stream) {
+    if (!x || !out || N < 1 || C < 1 || C > 32 || H < 1 || W < 1) return NUNET_E_BADARG;
+    const long long items = (long long)N * H * W * 4;
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    input_to_nhwc32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, N, C, (long long)H * W, (uint4*)out);
     return cuda_rc();
 }

@@ -346,6 +346,8 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
             cin += s.C; cin_real += s.C;
         }
     }
+    if (d->cin_real < 0 || d->cin_real > cin_real) return NUNET_E_BADARG;
+    if (d->cin_real > 0) cin_real = d->cin_real;
     nunet_wgrad_plan_t pl;
     int rc = nunet_conv3x3_wgrad_plan(d->N, d->H, d->W, cin, d->Cout, &pl);
     if (rc) return rc;

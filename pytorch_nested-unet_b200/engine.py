@@ -19,7 +19,14 @@ NB_FILTER = (32, 64, 128, 256, 512)
 # Node outputs (up to 5 forward + 5 wgrad loaders re-read each) are activated once into a bf16 tensor; False = every
 # loader applies BatchNorm+ReLU itself from the raw conv output.
 MATERIALIZE_NODE_OUTPUTS = True
-MATERIALIZE_ALL = _os.environ.get("NUNET_MATERIALIZE_ALL", "0") == "1"   # also a block's first conv output (one forward + one wgrad reader)
+# Also a block's first conv output (one forward + one wgrad reader): every conv then runs in copy mode and every weight
+# gradient through the TMA-fed kernel (conv_wgrad_tma.cu), which more than pays for the extra write + read.
+MATERIALIZE_ALL = _os.environ.get("NUNET_MATERIALIZE_ALL", "1") == "1"
+# 2x2 max-pooled backbone outputs are written once (quarter size) instead of being pooled in the consumer's loaders.
+MATERIALIZE_POOLED = _os.environ.get("NUNET_MATERIALIZE_POOLED", "1") == "1"
+# The fp32 NCHW network input is repacked once per step to bf16 NHWC with 32 (zero-padded) channels: the stem conv becomes a
+# plain 32-channel copy-mode layer in forward and weight gradient.
+PACK_INPUT = _os.environ.get("NUNET_PACK_INPUT", "1") == "1"
 # The upsampled skip operand is re-read by the forward conv and by Cout/32 wgrad CTAs per position; blending it in every
 # loader costs 4-8x the arithmetic of writing it once (measured: tools/prof_wgrad.py). False = fused NUNET_SRC_UP* loaders.
 MATERIALIZE_UPSAMPLED = True
@@ -84,7 +91,7 @@ def build_specs(model):
                         s.sources.append((pi, _KIND[kind], specs[pi].cout))
             else:
                 s.sources.append((s.idx - 1, L.SRC_SAME, specs[s.idx - 1].cout))
-            s.cin_pad = 16 if s.sources[0][1] == L.SRC_INPUT else sum(c for _, _, c in s.sources)
+            s.cin_pad = (32 if PACK_INPUT else 16) if s.sources[0][1] == L.SRC_INPUT else sum(c for _, _, c in s.sources)
             if s.sources[0][1] == L.SRC_INPUT and s.cin_real > 16:
                 raise L.NunetError("input_channels > 16 is not supported by the stem loader")
             if s.sources[0][1] != L.SRC_INPUT and s.cin_pad != s.cin_real:
@@ -145,20 +152,22 @@ def _world(model):
 
 
 class _Record(object):
-    __slots__ = ("y", "a", "a_up", "scale", "shift", "mean", "invstd", "h", "w")
+    __slots__ = ("y", "a", "a_up", "a_pool", "scale", "shift", "mean", "invstd", "h", "w")
 
 
-def _sources(spec, recs, x):
+def _sources(spec, recs, x, x32=None):
     """Loader descriptors of a conv: node outputs are read from their materialised activation (copy / pool / upsample
     loaders without BN math), a block's first conv output through the fused BN+ReLU loader."""
     srcs = []
     for pi, kind, c in spec.sources:
         if pi < 0:
-            srcs.append(ops.Source(kind, x, c))
+            srcs.append(ops.Source(L.SRC_ACT, x32, 32) if x32 is not None else ops.Source(kind, x, c))
         else:
             r = recs[pi]
             if kind == L.SRC_UP and r.a_up is not None:
                 srcs.append(ops.Source(L.SRC_ACT, r.a_up, c))
+            elif kind == L.SRC_POOL and r.a_pool is not None:
+                srcs.append(ops.Source(L.SRC_ACT, r.a_pool, c))
             elif r.a is not None:
                 srcs.append(ops.Source(L.ACT_KIND[kind], r.a, c))
             else:
@@ -183,14 +192,15 @@ def _forward(model, x, train):
     ws = st.workspace(dev)
     dp = _world(model)
     recs = []
+    x32 = ops.input_to_nhwc32(x) if PACK_INPUT else None
     for s in specs:
         h, w = H >> s.level, W >> s.level
-        srcs = _sources(s, recs, x)
+        srcs = _sources(s, recs, x, x32)
         plan = ops.conv_plan(N, h, w, s.cin_pad, s.cout)
         wp = st.pack(s, plan, L.PACK_FWD)
         y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
         r = _Record()
-        r.y, r.h, r.w, r.a, r.a_up = y, h, w, None, None
+        r.y, r.h, r.w, r.a, r.a_up, r.a_pool = y, h, w, None, None, None
         r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
         r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
         bn = s.bn
@@ -219,6 +229,8 @@ def _forward(model, x, train):
             r.a = ops.bn_apply(y, r.scale, r.shift)
             if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
                 r.a_up = ops.upsample2x(r.a)
+            if MATERIALIZE_POOLED and any(k == L.SRC_POOL for _, _, k in s.consumers):
+                r.a_pool = ops.maxpool2x2(r.a)
         recs.append(r)
     if train:
         nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]
@@ -230,13 +242,14 @@ def _forward(model, x, train):
             r = recs[s.idx]
             K = s.head.out_channels
             logits.append((s.idx, ops.head_fwd(r.y, r.scale, r.shift, s.head.weight.detach().view(K, -1), s.head.bias.detach(), N, r.h, r.w)))
-    return x, recs, logits
+    return (x, x32), recs, logits
 
 
-def _backward(model, x, recs, grad_logits):
+def _backward(model, xs, recs, grad_logits):
     """grad_logits: {layer idx: dlogits fp32 NCHW}. Returns {id(param): grad}."""
     st = _state(model)
     specs = st.specs
+    x, x32 = xs
     N, _, H, W = x.shape
     dev = x.device
     ws = st.workspace(dev)
@@ -300,16 +313,17 @@ def _backward(model, x, recs, grad_logits):
         gdone(s.bn.weight, dgamma)
         gdone(s.bn.bias, dbeta)
         gy = ops.bn_bwd_apply(gz, r.y, k1, k2, k3, out=gz)  # in place: g_z is dead once the BN sums are reduced
-        srcs = _sources(s, recs, x)
+        srcs = _sources(s, recs, x, x32)
         dw = galloc(s.conv.weight)
+        creal = s.cin_real if (s.sources[0][0] < 0 and x32 is not None) else 0
         if side is None:
-            ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw)
+            ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw, cin_real=creal)
         else:
             # the weight gradient is only needed when backward returns: run it on a second stream so that the HBM-bound
             # router / BN kernels of the following layers execute while it occupies the tensor pipes
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw)
+                ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw, cin_real=creal)
             gy.record_stream(side)
             dw.record_stream(side)
         gdone(s.conv.weight, dw)

@@ -170,6 +170,24 @@ def upsample2x(a, out=None):
     return out
 
 
+def maxpool2x2(a, out=None):
+    """bf16 NHWC [N,H,W,C] -> [N,H/2,W/2,C] (nn.MaxPool2d(2, 2) of an activated node output)."""
+    N, H, W, Cc = a.shape
+    if out is None:
+        out = torch.empty((N, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=a.device)
+    _call("maxpool2x2", 1, None, "nunet_maxpool2x2", L.lib().nunet_maxpool2x2, _ptr(a), N, H, W, Cc, _ptr(out), _stream())
+    return out
+
+
+def input_to_nhwc32(x, out=None):
+    """fp32 NCHW network input -> bf16 NHWC with 32 channels (zero-padded)."""
+    N, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((N, H, W, 32), dtype=torch.bfloat16, device=x.device)
+    _call("input_pack", 1, None, "nunet_input_to_nhwc32", L.lib().nunet_input_to_nhwc32, _ptr(x), N, Cc, H, W, _ptr(out), _stream())
+    return out
+
+
 def bn_fold_eval(gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift):
     _call("bn_fold", 1, None, "nunet_bn_fold_eval", L.lib().nunet_bn_fold_eval, gamma.numel(), _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
                                        _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), _stream())
@@ -293,7 +311,7 @@ def bn_bwd_apply(gz, y, k1, k2, k3, out=None):
     return out
 
 
-def conv3x3_wgrad(N, H, W, sources, Cout, gy, dw, part=None):
+def conv3x3_wgrad(N, H, W, sources, Cout, gy, dw, part=None, cin_real=0):
     """dw: fp32 [Cout, Cin_real, 3, 3] (overwritten); gy from bn_bwd_apply."""
     cin = sum(s.cpad for s in sources)
     plan = wgrad_plan(N, H, W, cin, Cout)
@@ -309,5 +327,6 @@ def conv3x3_wgrad(N, H, W, sources, Cout, gy, dw, part=None):
         d.src[i].kind = s.kind
     d.gy = gy.data_ptr()
     d.part, d.dw = part.data_ptr(), dw.data_ptr()
+    d.cin_real = cin_real
     _call("conv_wgrad", 2, (N, H, W, cin, Cout), "nunet_conv3x3_wgrad", L.lib().nunet_conv3x3_wgrad, C.byref(d), _stream())
     return dw
