@@ -82,6 +82,15 @@ enum { NUNET_PACK_FWD = 0, NUNET_PACK_DGRAD = 1 };
  * taps flipped (transposed convolution).  `plan` is the plan of the conv that will consume the pack. */
 int nunet_pack_weights(const float* w_oihw, int32_t Cout, int32_t Cin, int32_t mode, const nunet_conv_plan_t* plan,
                        void* wpack, void* stream);
+/* Same for up to any number of layers in one launch per NUNET_MAX_PACK_JOBS jobs (jobs: host array; NT/CK/nchunks/n_tiles from
+ * the layer's nunet_conv_plan_t, out: plan.wpack_elems bf16). */
+#define NUNET_MAX_PACK_JOBS 64
+typedef struct {
+    const float* w;
+    void* out;
+    int32_t Cout, Cin, mode, NT, CK, nchunks, n_tiles, pad_;
+} nunet_pack_job_t;
+int nunet_pack_weights_batched(const nunet_pack_job_t* jobs, int32_t njobs, void* stream);
 
 /* Reduce the per-CTA partial statistics and emit the BN apply coefficients (nn.BatchNorm2d train-mode forward,
  * finished/archs1.py:19,21): mean/var over count = N*H*W, scale = gamma*rsqrt(var+eps), shift = beta - mean*scale,

@@ -52,6 +52,10 @@ class WgradDesc(C.Structure):
                 ("Cout", C.c_int32), ("gy", C.c_void_p), ("part", C.c_void_p), ("dw", C.c_void_p), ("cin_real", C.c_int32)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p)] + [(n, C.c_int32) for n in ("Cout", "Cin", "mode", "NT", "CK", "nchunks", "n_tiles", "pad_")]
+
+
 class NunetError(RuntimeError):
     pass
 
@@ -63,6 +67,7 @@ _SIGS = {
     "nunet_conv3x3_plan": ([C.c_int32] * 5 + [C.POINTER(ConvPlan)], C.c_int),
     "nunet_conv3x3_fwd": ([C.POINTER(ConvDesc), C.c_void_p], C.c_int),
     "nunet_pack_weights": ([C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ConvPlan), C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_pack_weights_batched": ([C.c_void_p, C.c_int32, C.c_void_p], C.c_int),
     "nunet_bn_workspace_bytes": ([C.c_int32], C.c_int),
     "nunet_bn_finalize_train": ([C.c_void_p, C.c_int32, C.c_int32, C.c_double] + [C.c_void_p] * 5 + [C.c_float, C.c_float]
                                 + [C.c_void_p] * 8, C.c_int),

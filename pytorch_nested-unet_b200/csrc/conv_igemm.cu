@@ -434,33 +434,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // wpack[n_tile][chunk][tap][kg][NT][8]  (bf16);  FWD: n = co, k = ci ; DGRAD: n = ci, k = co, taps flipped.
+__device__ __forceinline__ void pack_group(const float* __restrict__ w, int Cout, int Cin, int mode, int NT, int CK, int nchunks,
+                                           __nv_bfloat16* __restrict__ out, size_t g) {
+    const int cgs = CK >> 3;
+    size_t r = g;
+    const int nl = (int)(r % NT); r /= NT;
+    const int kg = (int)(r % cgs); r /= cgs;
+    const int tap = (int)(r % 9); r /= 9;
+    const int chunk = (int)(r % nchunks); r /= nchunks;
+    const int nt = (int)r;
+    const int n = nt * NT + nl;
+    const int k0 = chunk * CK + kg * 8;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        float f = 0.f;
+        if (mode == NUNET_PACK_FWD) {
+            if (n < Cout && k < Cin) f = w[((size_t)n * Cin + k) * 9 + tap];
+        } else {
+            if (n < Cin && k < Cout) f = w[((size_t)k * Cin + n) * 9 + (8 - tap)];
+        }
+        v[e] = __float2bfloat16_rn(f);
+    }
+    *reinterpret_cast<uint4*>(out + g * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int mode, int NT, int CK, int nchunks,
                                     int n_tiles, __nv_bfloat16* __restrict__ out) {
-    const int cgs = CK >> 3;
-    const size_t total = (size_t)n_tiles * nchunks * 9 * cgs * NT;  // 16-byte groups
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
-        size_t r = g;
-        const int nl = (int)(r % NT); r /= NT;
-        const int kg = (int)(r % cgs); r /= cgs;
-        const int tap = (int)(r % 9); r /= 9;
-        const int chunk = (int)(r % nchunks); r /= nchunks;
-        const int nt = (int)r;
-        const int n = nt * NT + nl;
-        const int k0 = chunk * CK + kg * 8;
-        __nv_bfloat16 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = k0 + e;
-            float f = 0.f;
-            if (mode == NUNET_PACK_FWD) {
-                if (n < Cout && k < Cin) f = w[((size_t)n * Cin + k) * 9 + tap];
-            } else {
-                if (n < Cin && k < Cout) f = w[((size_t)k * Cin + n) * 9 + (8 - tap)];
-            }
-            v[e] = __float2bfloat16_rn(f);
-        }
-        *reinterpret_cast<uint4*>(out + g * 8) = *reinterpret_cast<const uint4*>(v);
-    }
+    const size_t total = (size_t)n_tiles * nchunks * 9 * (CK >> 3) * NT;  // 16-byte groups
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x)
+        pack_group(w, Cout, Cin, mode, NT, CK, nchunks, out, g);
+}
+
+// All layers of a step in ONE launch (the optimizer touches every weight every step; 60 separate ~8 us launches otherwise).
+struct PackBatch {
+    nunet_pack_job_t jobs[NUNET_MAX_PACK_JOBS];
+    int start[NUNET_MAX_PACK_JOBS + 1];   // first block of each job (blocks of 256 groups)
+    int njobs;
+};
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const __grid_constant__ PackBatch b) {
+    int j = 0;
+    while (j + 1 < b.njobs && (int)blockIdx.x >= b.start[j + 1]) ++j;
+    const nunet_pack_job_t& jb = b.jobs[j];
+    const size_t total = (size_t)jb.n_tiles * jb.nchunks * 9 * (jb.CK >> 3) * jb.NT;
+    const size_t g = (size_t)(blockIdx.x - b.start[j]) * 256 + threadIdx.x;
+    if (g < total) pack_group(jb.w, jb.Cout, jb.Cin, jb.mode, jb.NT, jb.CK, jb.nchunks, reinterpret_cast<__nv_bfloat16*>(jb.out), g);
 }
 
 }  // namespace nunet
@@ -632,4 +651,28 @@ extern "C" int nunet_pack_weights(const float* w, int32_t Cout, int32_t Cin, int
                                                                    reinterpret_cast<__nv_bfloat16*>(wpack));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+}
+
+extern "C" int nunet_pack_weights_batched(const nunet_pack_job_t* jobs, int32_t njobs, void* stream) {
+    if (!jobs || njobs < 1) return NUNET_E_BADARG;
+    for (int j0 = 0; j0 < njobs; j0 += NUNET_MAX_PACK_JOBS) {
+        PackBatch b{};
+        const int nj = njobs - j0 < NUNET_MAX_PACK_JOBS ? njobs - j0 : NUNET_MAX_PACK_JOBS;
+        int blocks = 0;
+        for (int j = 0; j < nj; ++j) {
+            const nunet_pack_job_t& jb = jobs[j0 + j];
+            if (!jb.w || !jb.out || (jb.mode != NUNET_PACK_FWD && jb.mode != NUNET_PACK_DGRAD) || jb.NT < 1 || jb.CK < 8 || jb.nchunks < 1 || jb.n_tiles < 1)
+                return NUNET_E_BADARG;
+            b.jobs[j] = jb;
+            b.start[j] = blocks;
+            const size_t total = (size_t)jb.n_tiles * jb.nchunks * 9 * (jb.CK >> 3) * jb.NT;
+            blocks += (int)((total + 255) / 256);
+        }
+        b.start[nj] = blocks;
+        b.njobs = nj;
+        pack_weights_batched_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    }
+    return NUNET_OK;
 }

@@ -172,47 +172,64 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 
 // ---------------------------------------------------------------------------------------------- head parameter grads
 // dWh[k][c] = sum_pix dlogit[n,k,pix] * a[pix,c] ; dbh[k] = sum dlogit.  part: [gridDim.x][K][33]
+template <int KT>
 __global__ void __launch_bounds__(256) head_bwd_params_partial_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                                       const float* __restrict__ shift, const float* __restrict__ dlogits,
                                                                       int K, int NP, int HW, float* __restrict__ part) {
     // thread = (pixel lane pl = tid/4, channel group cg = tid%4); each thread owns 8 channels
     const int cg = threadIdx.x & 3;
-    float sc[8], sh[8], acc[kMaxClasses][8], accb[kMaxClasses];
+    float sc[8], sh[8], acc[KT][8], accb[KT];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = scale[cg * 8 + i]; sh[i] = shift[cg * 8 + i]; }
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int k = 0; k < KT; ++k) {
         accb[k] = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     }
-    for (int pix = blockIdx.x * 64 + (threadIdx.x >> 2); pix < NP; pix += gridDim.x * 64) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(y + (size_t)pix * 32 + cg * 8));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-        float a[8];
+    constexpr int U = 4;   // pixels in flight per thread (the loop is latency-bound otherwise: one 16-byte load per iteration)
+    const int pstride = gridDim.x * 64;
+    for (int pix0 = blockIdx.x * 64 + (threadIdx.x >> 2); pix0 < NP; pix0 += U * pstride) {
+        uint4 r[U];
+        float dl[U][KT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 t = __bfloat1622float2(h[i]);
-            a[2 * i] = fmaxf(fmaf(t.x, sc[2 * i], sh[2 * i]), 0.f);
-            a[2 * i + 1] = fmaxf(fmaf(t.y, sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+        for (int u = 0; u < U; ++u) {
+            const int pix = pix0 + u * pstride;
+            if (pix < NP) {
+                r[u] = __ldg(reinterpret_cast<const uint4*>(y + (size_t)pix * 32 + cg * 8));
+                const int n = pix / HW, rem = pix - n * HW;
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+                    if (k < K) dl[u][k] = __ldg(dlogits + ((size_t)n * K + k) * HW + rem);
+            }
         }
-        const int n = pix / HW, rem = pix - n * HW;
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
-            if (k < K) {
-                const float dl = dlogits[((size_t)n * K + k) * HW + rem];
-                accb[k] += dl;
+        for (int u = 0; u < U; ++u) {
+            if (pix0 + u * pstride >= NP) continue;
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r[u]);
+            float a[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(dl, a[i], acc[k][i]);
+            for (int i = 0; i < 4; ++i) {
+                const float2 t = __bfloat1622float2(h[i]);
+                a[2 * i] = fmaxf(fmaf(t.x, sc[2 * i], sh[2 * i]), 0.f);
+                a[2 * i + 1] = fmaxf(fmaf(t.y, sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                if (k < K) {
+                    accb[k] += dl[u][k];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(dl[u][k], a[i], acc[k][i]);
+                }
             }
         }
     }
-    __shared__ float red[8][kMaxClasses][33];
-    for (int i = threadIdx.x; i < 8 * kMaxClasses * 33; i += blockDim.x) (&red[0][0][0])[i] = 0.f;
+    __shared__ float red[8][KT][33];
+    for (int i = threadIdx.x; i < 8 * KT * 33; i += blockDim.x) (&red[0][0][0])[i] = 0.f;
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int k = 0; k < KT; ++k) {
         if (k < K) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -297,7 +314,7 @@ extern "C" int nunet_loss_bwd(const float* logits, const float* target, const do
     return cuda_rc();
 }
 
-extern "C" int nunet_head_bwd_params_rows(void) { return 148 * 2; }
+extern "C" int nunet_head_bwd_params_rows(void) { return 148 * 4; }
 
 extern "C" int nunet_head_bwd_params(const void* y, const float* scale, const float* shift, const float* dlogits, int32_t N, int32_t H,
                                      int32_t W, int32_t K, float* part, float* dwh, float* dbh, int32_t accumulate, void* stream) {
@@ -305,8 +322,12 @@ extern "C" int nunet_head_bwd_params(const void* y, const float* scale, const fl
     const long long NP = (long long)N * H * W;
     if (NP >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
     const int rows = clampi((NP + 63) / 64, 1, nunet_head_bwd_params_rows());
-    head_bwd_params_partial_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, scale, shift, dlogits, K, (int)NP,
-                                                                          H * W, part);
+    if (K == 1)
+        head_bwd_params_partial_kernel<1><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, scale, shift, dlogits, K, (int)NP, H * W, part);
+    else if (K <= 4)
+        head_bwd_params_partial_kernel<4><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, scale, shift, dlogits, K, (int)NP, H * W, part);
+    else
+        head_bwd_params_partial_kernel<8><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, scale, shift, dlogits, K, (int)NP, H * W, part);
     head_bwd_params_finalize_kernel<<<K, 64, 0, (cudaStream_t)stream>>>(part, rows, K, dwh, dbh, accumulate);
     return cuda_rc();
 }

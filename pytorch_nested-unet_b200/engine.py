@@ -138,6 +138,33 @@ class _State(object):
         return out
 
 
+    def pack_all(self, N, H, W, want_dgrad):
+        """Re-packs every stale weight image of the step (forward and dgrad) with one batched launch."""
+        items, keys = [], []
+        for s in self.specs:
+            h, w = H >> s.level, W >> s.level
+            modes = [(L.PACK_FWD, ops.conv_plan(N, h, w, s.cin_pad, s.cout))]
+            if want_dgrad and s.sources[0][0] >= 0:
+                modes.append((L.PACK_DGRAD, ops.conv_plan(N, h, w, s.cout, s.cin_pad)))
+            wt = s.conv.weight
+            if wt.dtype != torch.float32 or not wt.is_contiguous():
+                continue   # the per-layer path converts
+            for mode, plan in modes:
+                key = (s.idx, mode)
+                tag = (wt._version, wt.data_ptr(), plan.NT, plan.CK)
+                hit = self.packs.get(key)
+                if hit is not None and hit[0] == tag:
+                    continue
+                out = hit[1] if (hit is not None and hit[1].numel() == plan.wpack_elems and hit[1].device == wt.device) else \
+                    torch.empty(plan.wpack_elems, dtype=torch.bfloat16, device=wt.device)
+                items.append((wt.detach(), mode, plan, out))
+                keys.append((key, tag, out))
+        if items:
+            ops.pack_weights_batched(items)
+            for key, tag, out in keys:
+                self.packs[key] = (tag, out)
+
+
 def _state(model):
     st = model.__dict__.get("_nunet_state")
     if st is None:
@@ -192,6 +219,7 @@ def _forward(model, x, train):
     ws = st.workspace(dev)
     dp = _world(model)
     recs = []
+    st.pack_all(N, H, W, train and torch.is_grad_enabled())
     x32 = ops.input_to_nhwc32(x) if PACK_INPUT else None
     for s in specs:
         h, w = H >> s.level, W >> s.level

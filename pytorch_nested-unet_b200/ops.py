@@ -99,6 +99,18 @@ def pack_weights(w_oihw, mode, plan, out=None):
     return out
 
 
+def pack_weights_batched(items):
+    """items: [(fp32 OIHW weight, mode, plan, out bf16)] -> all packed by one launch per 64 layers."""
+    jobs = (L.PackJob * len(items))()
+    for j, (w, mode, plan, out) in zip(jobs, items):
+        require_cuda(w, "weight")
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            raise L.NunetError("pack_weights_batched expects contiguous fp32 OIHW weights")
+        j.w, j.out, j.Cout, j.Cin, j.mode = w.data_ptr(), out.data_ptr(), w.shape[0], w.shape[1], mode
+        j.NT, j.CK, j.nchunks, j.n_tiles = plan.NT, plan.CK, plan.nchunks, plan.n_tiles
+    _call("pack", (len(items) + 63) // 64, None, "nunet_pack_weights_batched", L.lib().nunet_pack_weights_batched, C.cast(jobs, C.c_void_p), len(items), _stream())
+
+
 def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False, cls=None):
     """Launches the fused implicit-GEMM conv. Returns (out bf16 [N,H,W,Cout], stat_part [grid_m,2,Cout] or None)."""
     cin = sum(s.cpad for s in sources)
