@@ -34,8 +34,8 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
     ap.add_argument("--size", type=int, default=96)
@@ -261,14 +261,15 @@ def run_native(args):
     layer_rows = []
     # every rank runs the extra (untimed) profiling step: under DP it contains collectives
     import engine
-    side_saved = engine.WGRAD_SIDE_STREAM
+    side_saved, lvl_saved = engine.WGRAD_SIDE_STREAM, engine.LEVEL_STREAMS
     engine.WGRAD_SIDE_STREAM = False            # per-kernel CUDA events need every launch on the one (launching) stream
+    engine.LEVEL_STREAMS = False
     ops.enable_kernel_timing(rank == 0)
     step(x_dev, t_dev)
     torch.cuda.synchronize()
     timing = ops.collect_kernel_timing() if rank == 0 else None
     ops.enable_kernel_timing(False)
-    engine.WGRAD_SIDE_STREAM = side_saved
+    engine.WGRAD_SIDE_STREAM, engine.LEVEL_STREAMS = side_saved, lvl_saved
     barrier()
     if rank == 0:
         conv_ms = sum(v for k, v in timing["by_class"].items() if k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))

@@ -38,11 +38,13 @@ class GradBuckets(object):
         self.flat = None
         self.pending = None
         self.works = []
-        self.side = None  # optional second CUDA stream some gradients are produced on (engine: wgrad side stream)
+        self.side = None  # CUDA stream(s) other than the caller's that gradients are produced on (engine: level / wgrad streams)
 
     def _launch(self, s, e):
         if self.side is not None and self.flat.is_cuda:
-            torch.cuda.current_stream(self.flat.device).wait_stream(self.side)   # the bucket holds gradients of both streams
+            cur = torch.cuda.current_stream(self.flat.device)   # the bucket holds gradients produced on the engine's other streams
+            for st_ in (self.side if isinstance(self.side, (list, tuple)) else [self.side]):
+                cur.wait_stream(st_)
         op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
         self.works.append((dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True), s, e, op))
 

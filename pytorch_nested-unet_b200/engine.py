@@ -31,6 +31,12 @@ PACK_INPUT = _os.environ.get("NUNET_PACK_INPUT", "1") == "1"
 # loader costs 4-8x the arithmetic of writing it once (measured: tools/prof_wgrad.py). False = fused NUNET_SRC_UP* loaders.
 MATERIALIZE_UPSAMPLED = True
 WGRAD_SIDE_STREAM = _os.environ.get("NUNET_WGRAD_SIDE_STREAM", "1") == "1"
+# Training steps run every resolution level of the nested graph on its own CUDA stream (+ one weight-gradient stream per
+# level): nodes of one anti-diagonal are independent, so the HBM-bound kernels of one level (BN apply, upsample, gradient
+# router) execute while another level's convolution holds the tensor pipes.  Cross-level edges (pool / upsample in forward,
+# their dgrad slices in backward) are CUDA events; all streams fork from and join the caller's stream at the step boundaries,
+# and every tensor of the step stays referenced until the join is enqueued, so no block is recycled under a reader.
+LEVEL_STREAMS = _os.environ.get("NUNET_LEVEL_STREAMS", "1") == "1"
 
 
 # --------------------------------------------------------------------------------------------- graphs
@@ -109,6 +115,42 @@ def build_specs(model):
     return specs
 
 
+class _Streams(object):
+    """One compute stream, one weight-gradient stream and one BN scratch per resolution level."""
+
+    def __init__(self, device):
+        self.device = device
+        self.lvl = [torch.cuda.Stream(device=device) for _ in NB_FILTER]
+        self.wg = [torch.cuda.Stream(device=device) for _ in NB_FILTER]
+        self.ws = [ops.BnWorkspace(device) for _ in NB_FILTER]
+
+    def all(self, with_wg):
+        return self.lvl + (self.wg if with_wg else [])
+
+    def fork(self, main, with_wg=False):
+        for st_ in self.all(with_wg):
+            st_.wait_stream(main)
+
+    def join(self, main, with_wg=False):
+        for st_ in self.all(with_wg):
+            main.wait_stream(st_)
+
+
+class _NoCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def _use_level_streams(train):
+    return LEVEL_STREAMS and train and not torch.cuda.is_current_stream_capturing()
+
+
 class _State(object):
     """Per-model engine state: layer specs, packed-weight cache, BN scratch."""
 
@@ -137,6 +179,12 @@ class _State(object):
         self.packs[key] = (tag, out)
         return out
 
+
+    def streams(self, device):
+        ms = self.__dict__.get("_ms")
+        if ms is None or ms.device != device:
+            ms = self.__dict__["_ms"] = _Streams(device)
+        return ms
 
     def pack_all(self, N, H, W, want_dgrad):
         """Re-packs every stale weight image of the step (forward and dgrad) with one batched launch."""
@@ -202,6 +250,48 @@ def _sources(spec, recs, x, x32=None):
     return srcs
 
 
+def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
+    """One conv + BatchNorm (+ the materialised operands its consumers read) on the current stream."""
+    h, w = H >> s.level, W >> s.level
+    srcs = _sources(s, recs, x, x32)
+    plan = ops.conv_plan(N, h, w, s.cin_pad, s.cout)
+    wp = st.pack(s, plan, L.PACK_FWD)
+    y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
+    r = _Record()
+    r.y, r.h, r.w, r.a, r.a_up, r.a_pool = y, h, w, None, None, None
+    r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
+    r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
+    bn = s.bn
+    if train:
+        r.mean = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        r.invstd = torch.empty(s.cout, dtype=torch.float32, device=dev)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+        track = bn.track_running_stats and bn.running_mean is not None
+        rm = bn.running_mean if track else None
+        rv = bn.running_var if track else None
+        count = float(N * h * w)
+        if dp is None or not dp.sync_bn:
+            ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
+                                  r.mean, r.invstd)
+        else:
+            sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
+            ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
+                                  r.mean, r.invstd, sums_out=sums, finalize=False)
+            dp.all_reduce_sum(sums)
+            ops.bn_finalize_from_sums(sums, count * dp.world_size, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps,
+                                      r.scale, r.shift, r.mean, r.invstd)
+    else:
+        r.mean = r.invstd = None
+        ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
+    if (s.which == 2 or MATERIALIZE_ALL) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
+        r.a = ops.bn_apply(y, r.scale, r.shift)
+        if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
+            r.a_up = ops.upsample2x(r.a)
+        if MATERIALIZE_POOLED and any(k == L.SRC_POOL for _, _, k in s.consumers):
+            r.a_pool = ops.maxpool2x2(r.a)
+    return r
+
+
 def _forward(model, x, train):
     st = _state(model)
     specs = st.specs
@@ -221,45 +311,22 @@ def _forward(model, x, train):
     recs = []
     st.pack_all(N, H, W, train and torch.is_grad_enabled())
     x32 = ops.input_to_nhwc32(x) if PACK_INPUT else None
+    ms = st.streams(dev) if _use_level_streams(train) else None
+    main = torch.cuda.current_stream(dev)
+    done = {}   # layer idx of a node output -> event recorded after the node's last forward launch
+    if ms is not None:
+        ms.fork(main)
     for s in specs:
-        h, w = H >> s.level, W >> s.level
-        srcs = _sources(s, recs, x, x32)
-        plan = ops.conv_plan(N, h, w, s.cin_pad, s.cout)
-        wp = st.pack(s, plan, L.PACK_FWD)
-        y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
-        r = _Record()
-        r.y, r.h, r.w, r.a, r.a_up, r.a_pool = y, h, w, None, None, None
-        r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
-        r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
-        bn = s.bn
-        if train:
-            r.mean = torch.empty(s.cout, dtype=torch.float32, device=dev)
-            r.invstd = torch.empty(s.cout, dtype=torch.float32, device=dev)
-            momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
-            track = bn.track_running_stats and bn.running_mean is not None
-            rm = bn.running_mean if track else None
-            rv = bn.running_var if track else None
-            count = float(N * h * w)
-            if dp is None or not dp.sync_bn:
-                ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
-                                      r.mean, r.invstd)
-            else:
-                sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
-                ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
-                                      r.mean, r.invstd, sums_out=sums, finalize=False)
-                dp.all_reduce_sum(sums)
-                ops.bn_finalize_from_sums(sums, count * dp.world_size, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps,
-                                          r.scale, r.shift, r.mean, r.invstd)
-        else:
-            r.mean = r.invstd = None
-            ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
-        if (s.which == 2 or MATERIALIZE_ALL) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
-            r.a = ops.bn_apply(y, r.scale, r.shift)
-            if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
-                r.a_up = ops.upsample2x(r.a)
-            if MATERIALIZE_POOLED and any(k == L.SRC_POOL for _, _, k in s.consumers):
-                r.a_pool = ops.maxpool2x2(r.a)
-        recs.append(r)
+        lvl_stream = ms.lvl[s.level] if ms is not None else None
+        with (torch.cuda.stream(lvl_stream) if ms is not None else _NOCTX):
+            if ms is not None and s.which == 1:
+                for pi, _, _ in s.sources:
+                    if pi >= 0 and specs[pi].level != s.level:
+                        lvl_stream.wait_event(done[pi])
+            recs.append(_forward_layer(s, recs, x, x32, N, H, W, train, dp, ms.ws[s.level] if ms is not None else ws, dev, st))
+            if ms is not None and s.which == 2:
+                done[s.idx] = torch.cuda.Event()
+                done[s.idx].record(lvl_stream)
     if train:
         nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]
         if nbt:
@@ -269,7 +336,10 @@ def _forward(model, x, train):
         if s.head is not None:
             r = recs[s.idx]
             K = s.head.out_channels
-            logits.append((s.idx, ops.head_fwd(r.y, r.scale, r.shift, s.head.weight.detach().view(K, -1), s.head.bias.detach(), N, r.h, r.w)))
+            with (torch.cuda.stream(ms.lvl[s.level]) if ms is not None else _NOCTX):
+                logits.append((s.idx, ops.head_fwd(r.y, r.scale, r.shift, s.head.weight.detach().view(K, -1), s.head.bias.detach(), N, r.h, r.w)))
+    if ms is not None:
+        ms.join(main)
     return (x, x32), recs, logits
 
 
@@ -284,15 +354,20 @@ def _backward(model, xs, recs, grad_logits):
     dp = _world(model)
     grads, dxs = {}, {}
     main = torch.cuda.current_stream(dev)
+    ms = st.streams(dev) if _use_level_streams(True) else None
     side = None
-    if WGRAD_SIDE_STREAM and not torch.cuda.is_current_stream_capturing():
+    if ms is None and WGRAD_SIDE_STREAM and not torch.cuda.is_current_stream_capturing():
         side = st.__dict__.get("side_stream")
         if side is None:
             side = st.__dict__["side_stream"] = torch.cuda.Stream(device=dev)
     buckets = dp.buckets if dp is not None else None
     if buckets is not None:
         buckets.begin(dev)
-        buckets.side = side
+        buckets.side = ms.all(True) if ms is not None else side
+    keep = []      # level streams: every cross-stream tensor of the pass stays referenced until the final join is enqueued
+    dx_done = {}   # layer idx -> event recorded after its dgrad
+    if ms is not None:
+        ms.fork(main, with_wg=True)
 
     def galloc(p):
         return buckets.view(p) if buckets is not None else torch.empty(p.shape, dtype=torch.float32, device=dev)
@@ -305,70 +380,93 @@ def _backward(model, xs, recs, grad_logits):
     for s in reversed(specs):
         r = recs[s.idx]
         h, w = r.h, r.w
-        cons = []
-        for (m, off, kind) in s.consumers:
-            if kind == L.SRC_UP:   # transposed bilinear gather in its own tiled kernel; the router then sees a dense SAME slice
-                cons.append(ops.Consumer(ops.up_transpose(dxs[m], specs[m].cin_pad, off, N, h, w, s.cout), s.cout, 0, L.SRC_SAME))
+        S = ms.lvl[s.level] if ms is not None else None
+        ready = []   # (param, grad) finished by this layer; announced on the caller's stream (bucket all-reduce launches there)
+        with (torch.cuda.stream(S) if ms is not None else _NOCTX):
+            if ms is not None:
+                for (m, _, _) in s.consumers:
+                    if specs[m].level != s.level:
+                        S.wait_event(dx_done[m])
+            cons = []
+            for (m, off, kind) in s.consumers:
+                if kind == L.SRC_UP:   # transposed bilinear gather in its own tiled kernel; the router then sees a dense SAME slice
+                    cons.append(ops.Consumer(ops.up_transpose(dxs[m], specs[m].cin_pad, off, N, h, w, s.cout), s.cout, 0, L.SRC_SAME))
+                else:
+                    cons.append(ops.Consumer(dxs[m], specs[m].cin_pad, off, kind))
+            dl = wh = None
+            if s.head is not None:
+                dl = grad_logits.get(s.idx)
+                if dl is not None:
+                    K = s.head.out_channels
+                    wh = s.head.weight.detach().view(K, -1)
+                    dwh, dbh = galloc(s.head.weight), galloc(s.head.bias)
+                    ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
+                    ready += [(s.head.weight, dwh), (s.head.bias, dbh)]
+            if not cons and dl is None:
+                dl = torch.zeros((N, 1, h, w), dtype=torch.float32, device=dev)
+                wh = torch.zeros((1, s.cout), dtype=torch.float32, device=dev)
+            gz, rpart = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh)
+            dgamma, dbeta = galloc(s.bn.weight), galloc(s.bn.bias)
+            k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
+            count = float(N * h * w)
+            lws = ms.ws[s.level] if ms is not None else ws
+            if dp is None or not dp.sync_bn:
+                ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, lws, dgamma, dbeta, k1, k2, k3)
             else:
-                cons.append(ops.Consumer(dxs[m], specs[m].cin_pad, off, kind))
-        dl = wh = None
-        if s.head is not None:
-            dl = grad_logits.get(s.idx)
-            if dl is not None:
-                K = s.head.out_channels
-                wh = s.head.weight.detach().view(K, -1)
-                dwh, dbh = galloc(s.head.weight), galloc(s.head.bias)
-                ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
-                gdone(s.head.weight, dwh)
-                gdone(s.head.bias, dbh)
-        if not cons and dl is None:
-            dl = torch.zeros((N, 1, h, w), dtype=torch.float32, device=dev)
-            wh = torch.zeros((1, s.cout), dtype=torch.float32, device=dev)
-        gz, rpart = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh)
-        dgamma, dbeta = galloc(s.bn.weight), galloc(s.bn.bias)
-        k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
-        count = float(N * h * w)
-        if dp is None or not dp.sync_bn:
-            ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, ws, dgamma, dbeta, k1, k2, k3)
-        else:
-            sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
-            ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, ws, dgamma, dbeta, k1, k2, k3, sums_out=sums, finalize=False)
-            dp.all_reduce_sum(sums)
-            # local gradients are those of the LOCAL mean loss (= world_size x the global-loss gradient); the all-reduced sums
-            # therefore give world_size x dgamma/dbeta on every rank: scale by 1/world so the later AVG keeps the true value
-            ops.bn_backward_from_sums(sums, count * dp.world_size, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3,
-                                      grad_scale=1.0 / dp.world_size)
-        gdone(s.bn.weight, dgamma)
-        gdone(s.bn.bias, dbeta)
-        gy = ops.bn_bwd_apply(gz, r.y, k1, k2, k3, out=gz)  # in place: g_z is dead once the BN sums are reduced
-        srcs = _sources(s, recs, x, x32)
-        dw = galloc(s.conv.weight)
-        creal = s.cin_real if (s.sources[0][0] < 0 and x32 is not None) else 0
-        if side is None:
-            ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw, cin_real=creal)
-        else:
-            # the weight gradient is only needed when backward returns: run it on a second stream so that the HBM-bound
-            # router / BN kernels of the following layers execute while it occupies the tensor pipes
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
+                sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
+                ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, lws, dgamma, dbeta, k1, k2, k3, sums_out=sums, finalize=False)
+                dp.all_reduce_sum(sums)
+                # local gradients are those of the LOCAL mean loss (= world_size x the global-loss gradient); the all-reduced sums
+                # therefore give world_size x dgamma/dbeta on every rank: scale by 1/world so the later AVG keeps the true value
+                ops.bn_backward_from_sums(sums, count * dp.world_size, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3,
+                                          grad_scale=1.0 / dp.world_size)
+            ready += [(s.bn.weight, dgamma), (s.bn.bias, dbeta)]
+            gy = ops.bn_bwd_apply(gz, r.y, k1, k2, k3, out=gz)  # in place: g_z is dead once the BN sums are reduced
+            srcs = _sources(s, recs, x, x32)
+            dw = galloc(s.conv.weight)
+            creal = s.cin_real if (s.sources[0][0] < 0 and x32 is not None) else 0
+            if ms is not None:
+                # weight gradients are only needed when backward returns: each level has a second stream for them
+                gy_ready = torch.cuda.Event()
+                gy_ready.record(S)
+                ms.wg[s.level].wait_event(gy_ready)
+                with torch.cuda.stream(ms.wg[s.level]):
+                    ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw, cin_real=creal)
+                keep.append(gy)
+            elif side is None:
                 ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw, cin_real=creal)
-            gy.record_stream(side)
-            dw.record_stream(side)
-        gdone(s.conv.weight, dw)
-        if s.conv.bias is not None:
-            # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
-            gdone(s.conv.bias, galloc(s.conv.bias) if buckets is not None else torch.zeros_like(s.conv.bias))
-        if s.sources[0][0] >= 0:
-            plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
-            wpd = st.pack(s, plan, L.PACK_DGRAD)
-            dxs[s.idx], _ = ops.conv3x3(N, h, w, [ops.Source(L.SRC_ACT, gy, s.cout)], s.cin_pad, wpd, cls="conv_dgrad")
-        for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
-            if specs[m].sources[0][0] == s.idx:
-                dxs.pop(m, None)
+            else:
+                # run it on a second stream so that the HBM-bound router / BN kernels of the following layers execute while
+                # it occupies the tensor pipes
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.conv3x3_wgrad(N, h, w, srcs, s.cout, gy, dw, cin_real=creal)
+                gy.record_stream(side)
+                dw.record_stream(side)
+            ready.append((s.conv.weight, dw))
+            if s.conv.bias is not None:
+                # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
+                ready.append((s.conv.bias, galloc(s.conv.bias) if buckets is not None else torch.zeros_like(s.conv.bias)))
+            if s.sources[0][0] >= 0:
+                plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
+                wpd = st.pack(s, plan, L.PACK_DGRAD)
+                dxs[s.idx], _ = ops.conv3x3(N, h, w, [ops.Source(L.SRC_ACT, gy, s.cout)], s.cin_pad, wpd, cls="conv_dgrad")
+                if ms is not None:
+                    dx_done[s.idx] = torch.cuda.Event()
+                    dx_done[s.idx].record(S)
+        for p_, g_ in ready:
+            gdone(p_, g_)
+        if ms is None:
+            for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
+                if specs[m].sources[0][0] == s.idx:
+                    dxs.pop(m, None)
+    if ms is not None:
+        ms.join(main, with_wg=True)
     if side is not None:
         main.wait_stream(side)
     if buckets is not None:
         buckets.finish()
+    del keep
     return grads
 
 
