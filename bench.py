@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="also write profiles/layers_latest.json")
+    ap.add_argument("--kernels-only", action="store_true", help="profiler runs (ncu): only the warm-up and the timed device-resident steps")
     return ap.parse_args()
 
 
@@ -229,15 +230,28 @@ def run_native(args):
     barrier()
     launches = ops.launch_count()
     ms = e0.elapsed_time(e1)
-    # ---- end-to-end: pinned host batch -> device every step, loss + IoU read back every step
-    for _ in range(2):
-        step(x_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True))
+    if args.kernels_only:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        if rank == 0:
+            print(json.dumps({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- end-to-end through the public API (train.py's loop): every step copies its batch from pinned host memory (the copy
+    #      of batch i+1 is issued on utils.DevicePrefetcher's copy stream before batch i is consumed, as train.py does) and
+    #      reads the loss and the two IoU counts back to the host
+    import utils as nunet_utils
+
+    def host_batches(k):
+        for _ in range(k):
+            yield x_host, t_host, None
+    for xb, tb, _ in nunet_utils.DevicePrefetcher(host_batches(2), dev):
+        step(xb, tb)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        xb = x_host.to(dev, non_blocking=True)
-        tb = t_host.to(dev, non_blocking=True)
+    for xb, tb, _ in nunet_utils.DevicePrefetcher(host_batches(args.steps), dev):
         loss, counts = step(xb, tb)
         lv = loss.item()
         i_, u_ = counts.tolist()
@@ -277,17 +291,20 @@ def run_native(args):
         _, train_fl = conv_flops_per_image(args.arch, S)
         tflops = train_fl * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         traffic = None
-        try:  # DRAM bytes of the same kernels, from the committed ncu pass (profiles/r01_traffic.json; batch 256 @96x96 only)
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        try:  # DRAM bytes of the same kernels, from the committed ncu pass (profiles/r01b_traffic.json; batch 256 @96x96 only)
+            tfile = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+            if not os.path.exists(tfile):
+                tfile = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            with open(tfile) as f:
                 tj = json.load(f)
             if tj.get("batch") == B and tj.get("size") == S and args.arch == "NestedUNet" and ds:
                 traffic = tj["conv_dram_bytes_per_step"]
         except Exception:
             pass
         roof = {"bound": "tensor", "achieved": tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tflops / pk["tc_sustained"],
-                "traffic": traffic, "traffic_note": "dram__bytes_read+write summed over the step's conv launches (ncu, profiles/r01_ncu_dram_bytes.csv); "
+                "traffic": traffic, "traffic_note": "dram__bytes_read+write summed over the step's conv launches (ncu, profiles/r01b_ncu_launches_step.csv); "
                                                     "the unit of `achieved` is likewise one step's conv launches",
-                "algorithmic_flops_per_step": train_fl * B, "kernel": "conv3x3_igemm_kernel + conv3x3_wgrad_kernel (all 89 conv launches of one step)",
+                "algorithmic_flops_per_step": train_fl * B, "kernel": "conv3x3_igemm_kernel (forward, dgrad) + conv3x3_wgrad_tma_kernel: all 89 conv launches of one step",
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "kernel_ms_per_step": conv_ms, "all_kernels_ms_per_step": total_ms,
                 "class_ms": {k: round(v, 4) for k, v in sorted(timing["by_class"].items())}}
@@ -325,10 +342,16 @@ def run_native(args):
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

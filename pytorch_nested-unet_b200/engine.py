@@ -97,7 +97,7 @@ def build_specs(model):
                         s.sources.append((pi, _KIND[kind], specs[pi].cout))
             else:
                 s.sources.append((s.idx - 1, L.SRC_SAME, specs[s.idx - 1].cout))
-            s.cin_pad = (32 if PACK_INPUT else 16) if s.sources[0][1] == L.SRC_INPUT else sum(c for _, _, c in s.sources)
+            s.cin_pad = 16 if s.sources[0][1] == L.SRC_INPUT else sum(c for _, _, c in s.sources)   # stem: 32 when the input is repacked
             if s.sources[0][1] == L.SRC_INPUT and s.cin_real > 16:
                 raise L.NunetError("input_channels > 16 is not supported by the stem loader")
             if s.sources[0][1] != L.SRC_INPUT and s.cin_pad != s.cin_real:
@@ -147,8 +147,20 @@ class _NoCtx(object):
 _NOCTX = _NoCtx()
 
 
+def _tma_width(w):
+    """The TMA-fed kernels take rows of up to 254 pixels (box dimension limit 256 incl. padding)."""
+    return w + 2 <= 256
+
+
+def _cin_pad(s, packed_input):
+    return 32 if (packed_input and s.sources[0][1] == L.SRC_INPUT) else s.cin_pad
+
+
+_CAPTURING_TRAIN = False   # set while a training-step graph is being captured (fork/join of the level streams is capturable)
+
+
 def _use_level_streams(train):
-    return LEVEL_STREAMS and train and not torch.cuda.is_current_stream_capturing()
+    return LEVEL_STREAMS and train and (_CAPTURING_TRAIN or not torch.cuda.is_current_stream_capturing())
 
 
 class _State(object):
@@ -172,7 +184,7 @@ class _State(object):
         key = (spec.idx, mode)
         tag = (w._version, w.data_ptr(), plan.NT, plan.CK)
         hit = self.packs.get(key)
-        if hit is not None and hit[0] == tag:
+        if hit is not None and (hit[0] == tag or (_CAPTURING_TRAIN and hit[0][1:] == tag[1:])):
             return hit[1]
         out = hit[1] if (hit is not None and hit[1].numel() == plan.wpack_elems and hit[1].device == w.device) else None
         out = ops.pack_weights(w, mode, plan, out)
@@ -186,12 +198,12 @@ class _State(object):
             ms = self.__dict__["_ms"] = _Streams(device)
         return ms
 
-    def pack_all(self, N, H, W, want_dgrad):
+    def pack_all(self, N, H, W, want_dgrad, packed_input):
         """Re-packs every stale weight image of the step (forward and dgrad) with one batched launch."""
         items, keys = [], []
         for s in self.specs:
             h, w = H >> s.level, W >> s.level
-            modes = [(L.PACK_FWD, ops.conv_plan(N, h, w, s.cin_pad, s.cout))]
+            modes = [(L.PACK_FWD, ops.conv_plan(N, h, w, _cin_pad(s, packed_input), s.cout))]
             if want_dgrad and s.sources[0][0] >= 0:
                 modes.append((L.PACK_DGRAD, ops.conv_plan(N, h, w, s.cout, s.cin_pad)))
             wt = s.conv.weight
@@ -201,7 +213,7 @@ class _State(object):
                 key = (s.idx, mode)
                 tag = (wt._version, wt.data_ptr(), plan.NT, plan.CK)
                 hit = self.packs.get(key)
-                if hit is not None and hit[0] == tag:
+                if hit is not None and hit[0] == tag and not _CAPTURING_TRAIN:   # a captured step always re-packs (replayed after every update)
                     continue
                 out = hit[1] if (hit is not None and hit[1].numel() == plan.wpack_elems and hit[1].device == wt.device) else \
                     torch.empty(plan.wpack_elems, dtype=torch.bfloat16, device=wt.device)
@@ -254,7 +266,7 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
     """One conv + BatchNorm (+ the materialised operands its consumers read) on the current stream."""
     h, w = H >> s.level, W >> s.level
     srcs = _sources(s, recs, x, x32)
-    plan = ops.conv_plan(N, h, w, s.cin_pad, s.cout)
+    plan = ops.conv_plan(N, h, w, _cin_pad(s, x32 is not None), s.cout)
     wp = st.pack(s, plan, L.PACK_FWD)
     y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
     r = _Record()
@@ -283,16 +295,17 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
     else:
         r.mean = r.invstd = None
         ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
-    if (s.which == 2 or MATERIALIZE_ALL) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
+    # a block's first conv output and the pooled operand are only worth materialising where the TMA-fed kernels take them
+    if (s.which == 2 or (MATERIALIZE_ALL and _tma_width(w))) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
         r.a = ops.bn_apply(y, r.scale, r.shift)
         if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
             r.a_up = ops.upsample2x(r.a)
-        if MATERIALIZE_POOLED and any(k == L.SRC_POOL for _, _, k in s.consumers):
+        if MATERIALIZE_POOLED and _tma_width(w // 2) and any(k == L.SRC_POOL for _, _, k in s.consumers):
             r.a_pool = ops.maxpool2x2(r.a)
     return r
 
 
-def _forward(model, x, train):
+def _forward(model, x, train, want_dgrad=False):
     st = _state(model)
     specs = st.specs
     if x.dim() != 4:
@@ -309,8 +322,9 @@ def _forward(model, x, train):
     ws = st.workspace(dev)
     dp = _world(model)
     recs = []
-    st.pack_all(N, H, W, train and torch.is_grad_enabled())
-    x32 = ops.input_to_nhwc32(x) if PACK_INPUT else None
+    packed_input = PACK_INPUT and _tma_width(W)
+    st.pack_all(N, H, W, want_dgrad, packed_input)
+    x32 = ops.input_to_nhwc32(x) if packed_input else None
     ms = st.streams(dev) if _use_level_streams(train) else None
     main = torch.cuda.current_stream(dev)
     done = {}   # layer idx of a node output -> event recorded after the node's last forward launch
@@ -343,8 +357,9 @@ def _forward(model, x, train):
     return (x, x32), recs, logits
 
 
-def _backward(model, xs, recs, grad_logits):
-    """grad_logits: {layer idx: dlogits fp32 NCHW}. Returns {id(param): grad}."""
+def _backward(model, xs, recs, grad_logits, grad_alloc=None):
+    """grad_logits: {layer idx: dlogits fp32 NCHW}. Returns {id(param): grad}.  grad_alloc(p): where p's gradient is written
+    (captured steps: views of one flat buffer); default: a fresh tensor, or the data-parallel bucket view."""
     st = _state(model)
     specs = st.specs
     x, x32 = xs
@@ -370,6 +385,8 @@ def _backward(model, xs, recs, grad_logits):
         ms.fork(main, with_wg=True)
 
     def galloc(p):
+        if grad_alloc is not None:
+            return grad_alloc(p)
         return buckets.view(p) if buckets is not None else torch.empty(p.shape, dtype=torch.float32, device=dev)
 
     def gdone(p, g):
@@ -446,7 +463,7 @@ def _backward(model, xs, recs, grad_logits):
             ready.append((s.conv.weight, dw))
             if s.conv.bias is not None:
                 # train-mode BatchNorm subtracts the batch mean: the conv bias has an exactly zero gradient
-                ready.append((s.conv.bias, galloc(s.conv.bias) if buckets is not None else torch.zeros_like(s.conv.bias)))
+                ready.append((s.conv.bias, galloc(s.conv.bias) if (buckets is not None or grad_alloc is not None) else torch.zeros_like(s.conv.bias)))
             if s.sources[0][0] >= 0:
                 plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
                 wpd = st.pack(s, plan, L.PACK_DGRAD)
@@ -470,27 +487,135 @@ def _backward(model, xs, recs, grad_logits):
     return grads
 
 
+# ------------------------------------------------------------------------------------------------ captured training steps
+# A training step is ~380 launches on ten streams; at small batch (and on the host-synchronised end-to-end path) enqueueing
+# them costs more than running them.  After one eager step per (input shape, parameter set), forward and backward are each
+# captured into a CUDA graph (same kernels, same per-stream order: bitwise identical results) and replayed: two graph
+# launches per step.  The optimizer stays outside (it updates the fp32 masters in place; the graph re-packs them).
+GRAPH_TRAIN = _os.environ.get("NUNET_GRAPH_TRAIN", "1") == "1"
+
+
+class _TrainGraph(object):
+    __slots__ = ("seen", "pool", "x", "fwd", "outs", "recs", "xs", "head_layers", "launches_f", "bwd", "gl", "flat", "views", "launches_b",
+                 "packs", "failed", "gen", "bwd_gen")
+
+    def __init__(self):
+        self.seen, self.fwd, self.bwd, self.failed, self.packs = 0, None, None, False, {}
+        self.gen = self.bwd_gen = 0   # forward replays / the last one whose backward ran
+
+
+def _train_graph(model, x, params):
+    """The graph slot of this (shape, parameter set), or None when the step has to run eagerly."""
+    if not GRAPH_TRAIN or _world(model) is not None or ops.kernel_timing_enabled():
+        return None
+    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous()):
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    st = _state(model)
+    if any(s.bn.momentum is None for s in st.specs):      # cumulative moving average: the factor changes every step
+        return None
+    graphs = st.__dict__.setdefault("train_graphs", {})
+    key = (tuple(x.shape), x.device.index, tuple(p.data_ptr() for p in params), tuple(p.requires_grad for p in params))
+    tg = graphs.get(key)
+    if tg is None:
+        if len(graphs) >= 4:                               # each slot pins one step's activations
+            graphs.pop(next(iter(graphs)))
+        tg = graphs[key] = _TrainGraph()
+    tg.seen += 1
+    if tg.seen <= 1 or tg.failed:
+        return None
+    if tg.gen != tg.bwd_gen:      # the previous captured forward still waits for its backward: its activations must survive
+        return None
+    return tg
+
+
+def _capture(tg, model, fn):
+    """Runs fn() under stream capture with the slot's private memory pool and packed-weight cache."""
+    global _CAPTURING_TRAIN
+    st = _state(model)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    saved_packs, st.packs = st.packs, tg.packs
+    _CAPTURING_TRAIN = True
+    n0 = ops.launch_count()
+    try:
+        with torch.cuda.graph(g, pool=tg.pool, capture_error_mode="thread_local"):
+            res = fn()
+    finally:
+        _CAPTURING_TRAIN = False
+        st.packs = saved_packs
+    launches = ops.launch_count() - n0
+    ops.add_launches(-launches)       # nothing ran yet: replays are what gets counted
+    return g, res, launches
+
+
 class _NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, *params):
-        x, recs, logits = _forward(model, x, True)
-        ctx.model, ctx.x, ctx.recs = model, x, recs
-        ctx.head_layers = [i for i, _ in logits]
-        ctx.params = params
-        return tuple(t for _, t in logits)
+        tg = _train_graph(model, x, params)
+        ctx.model, ctx.params, ctx.tg = model, params, tg
+        if tg is None:
+            x, recs, logits = _forward(model, x, True, want_dgrad=True)
+            ctx.x, ctx.recs = x, recs
+            ctx.head_layers = [i for i, _ in logits]
+            return tuple(t for _, t in logits)
+        if tg.fwd is None:
+            tg.pool = torch.cuda.graph_pool_handle()
+            tg.x = x.clone()
+            tg.fwd, (tg.xs, tg.recs, logits), tg.launches_f = _capture(tg, model, lambda: _forward(model, tg.x, True, want_dgrad=True))
+            tg.head_layers = [i for i, _ in logits]
+            tg.outs = tuple(t for _, t in logits)
+        tg.x.copy_(x)
+        tg.fwd.replay()
+        ops.add_launches(tg.launches_f)
+        tg.gen += 1
+        ctx.gen = tg.gen
+        ctx.head_layers = tg.head_layers
+        return tuple(t.clone() for t in tg.outs)
 
     @staticmethod
     def backward(ctx, *grad_logits):
-        gl = {}
-        for i, g in zip(ctx.head_layers, grad_logits):
-            if g is not None:
-                gl[i] = g.contiguous().float()
-        grads = _backward(ctx.model, ctx.x, ctx.recs, gl)
-        ctx.recs = None
+        tg = ctx.tg
+        if tg is None:
+            gl = {}
+            for i, g in zip(ctx.head_layers, grad_logits):
+                if g is not None:
+                    gl[i] = g.contiguous().float()
+            grads = _backward(ctx.model, ctx.x, ctx.recs, gl)
+            ctx.recs = None
+            return (None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        if tg.bwd is None:
+            dev = tg.x.device
+            st = _state(ctx.model)
+            tg.gl = {i: torch.zeros_like(o) for i, o in zip(tg.head_layers, tg.outs)}
+            offs, total = {}, 0
+            for p in ctx.params:
+                offs[id(p)] = (total, p.numel(), tuple(p.shape))
+                total += (p.numel() + 31) // 32 * 32
+            tg.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+
+            def alloc(p):
+                o, n, shape = offs[id(p)]
+                return tg.flat[o:o + n].view(shape)
+            tg.views = offs
+            tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, lambda: _backward(ctx.model, tg.xs, tg.recs, tg.gl, grad_alloc=alloc))
+        for i, g in zip(tg.head_layers, grad_logits):
+            if g is None:
+                tg.gl[i].zero_()
+            else:
+                tg.gl[i].copy_(g)
+        tg.bwd.replay()
+        ops.add_launches(tg.launches_b)
+        tg.bwd_gen = ctx.gen
+        flat = tg.flat.clone()            # the caller owns its gradients; the graph's buffer is rewritten by the next replay
         out = []
         for p in ctx.params:
-            g = grads.get(id(p)) if p.requires_grad else None
-            out.append(g)
+            if p.requires_grad:
+                o, n, shape = tg.views[id(p)]
+                out.append(flat[o:o + n].view(shape))
+            else:
+                out.append(None)
         return (None, None) + tuple(out)
 
 

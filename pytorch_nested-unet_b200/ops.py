@@ -33,6 +33,16 @@ def launch_count():
     return _LAUNCHES
 
 
+def add_launches(n):
+    """CUDA-graph replays launch the kernels that were counted while the graph was captured."""
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def kernel_timing_enabled():
+    return _TIMING is not None
+
+
 def enable_kernel_timing(on):
     """Per-launch CUDA-event timing on the launching (current) stream; used by bench.py for the roofline figures."""
     global _TIMING

@@ -32,3 +32,43 @@ class AverageMeter(object):
         self.sum += val * n
         self.count += n
         self.avg = self.sum / self.count
+
+
+class DevicePrefetcher(object):
+    """Wraps a loader of (tensor, ..., meta) host batches: the host->device copy of batch i+1 is issued on a copy stream
+    before batch i is handed out, so it overlaps batch i's step (the reference's loop copies synchronously, trains.py:113-114).
+    Pinned host tensors (DataLoader(pin_memory=True)) make the copy truly asynchronous; pageable ones still work."""
+
+    def __init__(self, loader, device=None):
+        self.loader, self.device = loader, device
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        copy_stream = torch.cuda.Stream(device=dev)
+        it = iter(self.loader)
+
+        def load():
+            try:
+                batch = next(it)
+            except StopIteration:
+                return None
+            with torch.cuda.stream(copy_stream):
+                out = tuple(b.to(dev, non_blocking=True) if torch.is_tensor(b) else b for b in batch)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            return out, ev
+
+        nxt = load()
+        while nxt is not None:
+            out, ev = nxt
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            for b in out:
+                if torch.is_tensor(b):
+                    b.record_stream(cur)
+            nxt = load()
+            yield out

@@ -20,7 +20,7 @@ def test_engine_specs_match_reference_graph():
     s = by[("0_4", 1)]
     assert s.cin_pad == 192 and s.cout == 32 and [k for _, k, _ in s.sources] == [L.SRC_SAME] * 4 + [L.SRC_UP]
     assert [c for _, _, c in s.sources] == [32, 32, 32, 32, 64]
-    assert by[("0_0", 1)].cin_pad == (32 if engine.PACK_INPUT else 16) and by[("0_0", 1)].sources[0][1] == L.SRC_INPUT
+    assert by[("0_0", 1)].cin_pad == 16 and by[("0_0", 1)].sources[0][1] == L.SRC_INPUT
     assert by[("3_0", 1)].sources == [(by[("2_0", 2)].idx, L.SRC_POOL, 128)]
     # x0_0 is consumed by conv1_0 (pool) and conv0_1..conv0_4 (same, channel offset 0)
     cons = by[("0_0", 2)].consumers

@@ -140,3 +140,52 @@ def test_state_dict_keys_match_reference_layout():
     assert sum(p.numel() for p in m.parameters()) == 9163428
     assert sum(p.numel() for p in archs.NestedUNet(1, 3, False).parameters()) == 9163329
     assert sum(p.numel() for p in archs.UNet(1, 3).parameters()) == 7852545
+
+
+@pytest.mark.parametrize("arch,ds", [("NestedUNet", True), ("UNet", False)])
+def test_captured_and_multistream_steps_are_bitwise_equal_to_the_single_stream_step(arch, ds):
+    """The CUDA-graph replay of a training step (engine.GRAPH_TRAIN) and the per-level stream schedule (engine.LEVEL_STREAMS)
+    launch the same kernels in the same per-stream order as the plain single-stream step: logits, loss, running statistics
+    and the parameters after four SGD steps must be bitwise identical."""
+    import archs
+    import engine
+    import losses
+
+    def run(graph, streams, side):
+        saved = engine.GRAPH_TRAIN, engine.LEVEL_STREAMS, engine.WGRAD_SIDE_STREAM
+        engine.GRAPH_TRAIN, engine.LEVEL_STREAMS, engine.WGRAD_SIDE_STREAM = graph, streams, side
+        try:
+            torch.manual_seed(0)
+            model = getattr(archs, arch)(1, 3, ds).to(DEV).train()
+            crit = losses.BCEDiceLoss()
+            opt = torch.optim.SGD(model.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)
+            g = torch.Generator(device=DEV).manual_seed(5)
+            res = []
+            for step in range(4):
+                x = torch.randn(4, 3, 64, 48, generator=g, device=DEV)
+                t = (torch.rand(4, 1, 64, 48, generator=g, device=DEV) > 0.5).float()
+                out = model(x)
+                outs = out if isinstance(out, list) else [out]
+                loss = sum(crit(o, t) for o in outs) / len(outs)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                res.append((outs[-1].detach().clone(), loss.detach().clone()))
+            torch.cuda.synchronize()
+            st = engine._state(model)
+            captured = sum(1 for tg in st.__dict__.get("train_graphs", {}).values() if tg.fwd is not None and tg.bwd is not None)
+            return res, [p.detach().clone() for p in model.parameters()], [b.detach().clone() for b in model.buffers()], captured
+        finally:
+            engine.GRAPH_TRAIN, engine.LEVEL_STREAMS, engine.WGRAD_SIDE_STREAM = saved
+
+    base = run(False, False, False)
+    assert base[3] == 0
+    for cfg in ((False, True, True), (True, True, True), (True, False, True)):
+        got = run(*cfg)
+        assert got[3] == (1 if cfg[0] else 0), "the step was not captured"
+        for (lo, ls), (bo, bs) in zip(got[0], base[0]):
+            assert torch.equal(lo, bo) and torch.equal(ls, bs), cfg
+        for a, b in zip(got[1], base[1]):
+            assert torch.equal(a, b), cfg
+        for a, b in zip(got[2], base[2]):
+            assert torch.equal(a, b), cfg
