@@ -208,6 +208,26 @@ int nunet_input_to_nhwc32(const float* x, int32_t N, int32_t C, int32_t H, int32
 int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* plan);
 int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
 
+/* ---- fp32 check mode (forward only; csrc/check_fp32.cu) ------------------------------------------------------------
+ * The reference's fp32 arithmetic on CUDA cores: fp32 NHWC activations with a channel pitch, fp64 BatchNorm statistics.
+ * Used to hold the graph / BatchNorm / pooling / upsampling / head semantics to <= 1e-4 against the reference's logits. */
+int nunet_check_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+/* nn.Conv2d(Cin, Cout, 3, padding=1) incl. bias (finished/archs1.py:18,20); wt_scratch: 9*Cin*Cout floats */
+int nunet_check_conv3x3(const float* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t xpitch, const float* w_oihw,
+                        const float* bias, int32_t Cout, float* wt_scratch, float* y, void* stream);
+/* nn.BatchNorm2d (finished/archs1.py:19,21): train != 0: batch statistics (+ running-stat update), else running statistics;
+ * emits the per-channel scale/shift of a = relu(scale*y + shift) */
+int nunet_check_bn(const float* y, long long M, int32_t C, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, int32_t train, float* scale, float* shift, void* stream);
+int nunet_check_bn_relu(const float* y, long long M, int32_t C, const float* scale, const float* shift, float* dst, int32_t pitch,
+                        int32_t off, void* stream);
+/* mode 0 copy | 1 nn.MaxPool2d(2,2) | 2 nn.Upsample(2, bilinear, align_corners=True) of src [N,h,w,C] into the channel
+ * slice [off, off+C) of dst (torch.cat, finished/archs1.py:117-132) */
+int nunet_check_route(const float* src, int32_t N, int32_t h, int32_t w, int32_t C, int32_t mode, float* dst, int32_t pitch,
+                      int32_t off, void* stream);
+int nunet_check_head(const float* a, int32_t N, int32_t H, int32_t W, int32_t C, const float* wh, const float* bh, int32_t K,
+                     float* logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,12 @@ _SIGS = {
     "nunet_upsample2x": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_maxpool2x2": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_input_to_nhwc32": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_nchw_to_nhwc": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_conv3x3": ([C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_bn": ([C.c_void_p, C.c_longlong, C.c_int32] + [C.c_void_p] * 4 + [C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_bn_relu": ([C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p], C.c_int),
+    "nunet_check_route": ([C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p], C.c_int),
+    "nunet_check_head": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_fold_eval": ([C.c_int32] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 3, C.c_int),
 }
 

@@ -655,11 +655,89 @@ def _graphed_eval(model, x, params):
     return tuple(t.clone() for t in g.outs)
 
 
+# ------------------------------------------------------------------------------------------------ fp32 check mode
+# Forward-only evaluation of the same graph in CUDA-core fp32 (csrc/check_fp32.cu): the north_star's "<= 1e-4 in an fp32 check
+# mode" bound against the reference's logits.  Selected explicitly; never a fallback of the product path.
+CHECK_FP32 = _os.environ.get("NUNET_FP32_CHECK", "0") == "1"
+_ROUTE_MODE = {L.SRC_SAME: 0, L.SRC_POOL: 1, L.SRC_UP: 2}
+
+
+def _check_call(name, *args):
+    ops._call("check_fp32", 1, None, name, getattr(L.lib(), name), *args)
+
+
+def _forward_check(model, x, train):
+    st = _state(model)
+    specs = st.specs
+    ops.require_cuda(x, "input")
+    x = x.float().contiguous()
+    N, Cin, H, W = x.shape
+    if Cin != specs[0].cin_real or H % 16 or W % 16:
+        raise ValueError("expected %d input channels and height/width multiples of 16" % specs[0].cin_real)
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    P, S = ops._ptr, ops._stream
+    xin = torch.empty((N, H, W, Cin), **f32)
+    _check_call("nunet_check_nchw_to_nhwc", P(x), N, Cin, H, W, P(xin), S())
+    acts = {}
+    for s in specs:
+        h, w = H >> s.level, W >> s.level
+        if s.sources[0][0] < 0:
+            buf, cin = xin, Cin
+        elif s.which == 2:
+            buf, cin = acts[s.idx - 1], specs[s.idx - 1].cout
+        else:
+            cin = s.cin_real
+            buf = torch.empty((N, h, w, cin), **f32)
+            off = 0
+            for pi, kind, c in s.sources:      # torch.cat order: same-level nodes, then the upsampled one (archs1.py:117-132)
+                src = acts[pi]
+                _check_call("nunet_check_route", P(src), N, src.shape[1], src.shape[2], c, _ROUTE_MODE[kind], P(buf), cin, off, S())
+                off += c
+        wt = torch.empty(9 * cin * s.cout, **f32)
+        y = torch.empty((N, h, w, s.cout), **f32)
+        wgt = s.conv.weight.detach().float().contiguous()
+        bias = s.conv.bias.detach().float().contiguous() if s.conv.bias is not None else None
+        _check_call("nunet_check_conv3x3", P(buf), N, h, w, cin, cin, P(wgt), P(bias), s.cout, P(wt), P(y), S())
+        bn = s.bn
+        scale, shift = torch.empty(s.cout, **f32), torch.empty(s.cout, **f32)
+        track = bn.track_running_stats and bn.running_mean is not None
+        use_batch = train or not track
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+        _check_call("nunet_check_bn", P(y), N * h * w, s.cout, P(bn.weight), P(bn.bias), P(bn.running_mean if (track and (train or not use_batch)) else None),
+                    P(bn.running_var if (track and (train or not use_batch)) else None), float(momentum), float(bn.eps), 1 if use_batch else 0,
+                    P(scale), P(shift), S())
+        a = torch.empty((N, h, w, s.cout), **f32)
+        _check_call("nunet_check_bn_relu", P(y), N * h * w, s.cout, P(scale), P(shift), P(a), s.cout, 0, S())
+        acts[s.idx] = a
+    if train:
+        nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]
+        if nbt:
+            torch._foreach_add_(nbt, 1)
+    outs = []
+    for s in specs:
+        if s.head is not None:
+            K = s.head.out_channels
+            a = acts[s.idx]
+            logits = torch.empty((N, K, a.shape[1], a.shape[2]), **f32)
+            wh = s.head.weight.detach().float().reshape(K, -1).contiguous()
+            bh = s.head.bias.detach().float().contiguous() if s.head.bias is not None else None
+            _check_call("nunet_check_head", P(a), N, a.shape[1], a.shape[2], s.cout, P(wh), P(bh), K, P(logits), S())
+            outs.append(logits)
+    return tuple(outs)
+
+
 def run_model(model, x):
     """model(input) of the reference (trains.py:117-125, val.py:92-95)."""
     L.lib()  # fail loudly if the CUDA library is missing
     params = [p for p in model.parameters()]
     need_grad = model.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    if CHECK_FP32:
+        if need_grad:
+            raise L.NunetError("the fp32 check mode is forward-only: call the model under torch.no_grad()")
+        with torch.no_grad():
+            outs = _forward_check(model, x, model.training)
+        return list(outs) if model._returns_list else outs[0]
     if need_grad:
         outs = _NetFunction.apply(model, x, *params)
     elif (GRAPH_EVAL and not model.training and torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32

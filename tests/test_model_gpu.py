@@ -189,3 +189,47 @@ def test_captured_and_multistream_steps_are_bitwise_equal_to_the_single_stream_s
             assert torch.equal(a, b), cfg
         for a, b in zip(got[2], base[2]):
             assert torch.equal(a, b), cfg
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_check_mode_matches_reference_logits_to_1e_4(name):
+    """north_star: forward logits max|d|/max|ref| <= 1e-4 in the fp32 check mode (engine.CHECK_FP32: CUDA-core fp32 convs,
+    fp64 BatchNorm statistics).  Train-mode logits and the updated running statistics against the golden minted from the
+    unmodified reference; eval-mode logits (running statistics after that step) against the oracle restatement."""
+    import archs
+    import engine
+    from oracle import nunet_oracle as orc
+    g = _steps()[name]
+    torch.manual_seed(g["weight_seed"])
+    model = getattr(archs, g["arch"])(g["num_classes"], 3, g["deep_supervision"]).to(DEV)
+    x, _ = _synthetic(g)
+    saved = engine.CHECK_FP32
+    engine.CHECK_FP32 = True
+    try:
+        model.train()
+        with pytest.raises(Exception):
+            model(x.to(DEV))                      # forward-only: refuses to build a graph for backward
+        with torch.no_grad():
+            out = model(x.to(DEV))
+        outs = out if isinstance(out, list) else [out]
+        refs = g["logits"] if isinstance(g["logits"], list) else [g["logits"]]
+        for k, (o, r) in enumerate(zip(outs, refs)):
+            assert _relmax(o.cpu(), r) <= 1e-4, (k, _relmax(o.cpu(), r))
+        sd = model.state_dict()
+        for k, v in g["bn_after"].items():
+            assert torch.allclose(sd[k].cpu(), v, rtol=1e-4, atol=1e-6), (k, float((sd[k].cpu() - v).abs().max()))
+        assert int(sd["conv0_0.bn1.num_batches_tracked"]) == 1
+        model.eval()
+        with torch.no_grad():
+            oe = model(x.to(DEV))
+        oe = oe if isinstance(oe, list) else [oe]
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        if g["arch"] == "NestedUNet":
+            ref_e = orc.nested_unet_forward(sd_cpu, x, g["deep_supervision"], train=False)
+        else:
+            ref_e = orc.unet_forward(sd_cpu, x, train=False)
+        ref_e = ref_e if isinstance(ref_e, list) else [ref_e]
+        for o, r in zip(oe, ref_e):
+            assert _relmax(o.cpu(), r) <= 1e-4, _relmax(o.cpu(), r)
+    finally:
+        engine.CHECK_FP32 = saved

@@ -8,7 +8,7 @@ import archs, losses, metrics, ops
 dev = torch.device("cuda:0")
 
 
-def train_rate(arch, classes, ds, n, size, steps=5, warm=2):
+def train_rate(arch, classes, ds, n, size, steps=5, warm=3):   # warm >= 3: the second step captures the CUDA graphs
     torch.manual_seed(0)
     model = getattr(archs, arch)(classes, 3, ds).to(dev)
     crit = losses.BCEDiceLoss()
@@ -58,7 +58,7 @@ res = {}
 res["C1 NestedUNet woDS N=16 96x96 train"] = train_rate("NestedUNet", 1, False, 16, 96)
 res["C3 UNet N=64 256x256 train"] = train_rate("UNet", 1, False, 64, 256)
 res["C3 NestedUNet woDS N=64 256x256 train"] = train_rate("NestedUNet", 1, False, 64, 256)
-res["C4 NestedUNet 4-class DS N=8 512x512 train"] = train_rate("NestedUNet", 4, True, 8, 512, steps=3, warm=1)
+res["C4 NestedUNet 4-class DS N=8 512x512 train"] = train_rate("NestedUNet", 4, True, 8, 512, steps=3, warm=3)
 for n in (1, 4, 16, 64, 256, 1024):
     res["C5 NestedUNet eval+IoU N=%d 96x96" % n] = eval_rate("NestedUNet", n, 96)
 for n in (1, 4, 16, 64):
