@@ -191,53 +191,52 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* gz, cons
 // Bilinear 2x upsample (align_corners=True, ATen area_pixel_compute_scale) of an activated bf16 NHWC tensor:
 // out[N,2h,2w,C].  One 16-byte group per thread-iteration, fp32 blend, one rounding.  Used when the engine materialises
 // the upsampled skip operand once instead of re-blending it in every loader that reads it (forward + Cout/32 wgrad CTAs).
+constexpr int kUpRows = 8;   // output rows per CTA
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int N, int h, int w, int cgs,
                                                          __nv_bfloat16* __restrict__ out) {
+    // CTA = kUpRows consecutive output rows of one image; a thread owns (output column X, channel group) items and walks the
+    // rows, so the column indices / weights are computed once and no integer division is needed per item.
     const int H = 2 * h, W = 2 * w, C = cgs * 8;
     const int cg_shift = 31 - __clz(cgs);  // C/8 is a power of two
-    const unsigned items = (unsigned)N * H * W * cgs;   // < 2^31 (checked by the host)
+    const int rgroups = (H + kUpRows - 1) / kUpRows;
+    const int n = blockIdx.x / rgroups, Y0 = (blockIdx.x - n * rgroups) * kUpRows;
     const float ry = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
     const float rx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned it0 = blockIdx.x * blockDim.x + threadIdx.x; it0 < items; it0 += 2 * stride) {
-        uint4 r[2][4];
-        float wts[2][4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const unsigned it = it0 + u * stride;
-            if (it >= items) continue;
-            const int cg = it & (cgs - 1);
-            unsigned pix = it >> cg_shift;
-            const int X = pix % W; pix /= W;
-            const int Y = pix % H;
-            const int n = pix / H;
-            const float sy = ry * (float)Y, sx = rx * (float)X;
-            const int y0 = (int)sy, x0 = (int)sx;
-            const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
-            wts[u][1] = sy - (float)y0; wts[u][3] = sx - (float)x0; wts[u][0] = 1.f - wts[u][1]; wts[u][2] = 1.f - wts[u][3];
-            const __nv_bfloat16* base = in + (size_t)n * h * w * C + cg * 8;
-            r[u][0] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * C));
-            r[u][1] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * C));
-            r[u][2] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * C));
-            r[u][3] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * C));
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const unsigned it = it0 + u * stride;
-            if (it >= items) continue;
-            const float ly0 = wts[u][0], ly1 = wts[u][1], lx0 = wts[u][2], lx1 = wts[u][3];
-            const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&r[u][0]), *b = reinterpret_cast<const __nv_bfloat162*>(&r[u][1]),
-                                 *c = reinterpret_cast<const __nv_bfloat162*>(&r[u][2]), *d = reinterpret_cast<const __nv_bfloat162*>(&r[u][3]);
+    const __nv_bfloat16* img = in + (size_t)n * h * w * C;
+    __nv_bfloat16* oimg = out + (size_t)n * H * W * C;
+    const int row_items = W << cg_shift;
+    for (int i = threadIdx.x; i < row_items; i += 256) {
+        const int cg = i & (cgs - 1), X = i >> cg_shift;
+        const float sx = rx * (float)X;
+        const int x0 = (int)sx;
+        const int x1 = x0 + (x0 < w - 1);
+        const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+        const __nv_bfloat16* c0 = img + (size_t)x0 * C + cg * 8;
+        const __nv_bfloat16* c1 = img + (size_t)x1 * C + cg * 8;
+#pragma unroll 2
+        for (int r = 0; r < kUpRows; ++r) {
+            const int Y = Y0 + r;
+            if (Y >= H) break;
+            const float sy = ry * (float)Y;
+            const int y0 = (int)sy;
+            const int y1 = y0 + (y0 < h - 1);
+            const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+            const uint4 ra = __ldg(reinterpret_cast<const uint4*>(c0 + (size_t)y0 * w * C));
+            const uint4 rb = __ldg(reinterpret_cast<const uint4*>(c1 + (size_t)y0 * w * C));
+            const uint4 rc = __ldg(reinterpret_cast<const uint4*>(c0 + (size_t)y1 * w * C));
+            const uint4 rd = __ldg(reinterpret_cast<const uint4*>(c1 + (size_t)y1 * w * C));
+            const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&ra), *b = reinterpret_cast<const __nv_bfloat162*>(&rb),
+                                 *c = reinterpret_cast<const __nv_bfloat162*>(&rc), *d = reinterpret_cast<const __nv_bfloat162*>(&rd);
             uint32_t o[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 fa = __bfloat1622float2(a[i]), fb = __bfloat1622float2(b[i]), fc = __bfloat1622float2(c[i]), fd = __bfloat1622float2(d[i]);
+            for (int e = 0; e < 4; ++e) {
+                const float2 fa = __bfloat1622float2(a[e]), fb = __bfloat1622float2(b[e]), fc = __bfloat1622float2(c[e]), fd = __bfloat1622float2(d[e]);
                 const float v0 = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
                 const float v1 = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
                 __nv_bfloat162 q = __floats2bfloat162_rn(v0, v1);
-                o[i] = *reinterpret_cast<uint32_t*>(&q);
+                o[e] = *reinterpret_cast<uint32_t*>(&q);
             }
-            *reinterpret_cast<uint4*>(out + (size_t)it * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(oimg + ((size_t)Y * W + X) * C + cg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -379,9 +378,9 @@ extern "C" int nunet_upsample2x(const void* in, int32_t N, int32_t h, int32_t w,
     if (!in || !out || N < 1 || h < 1 || w < 1 || C < 8 || C % 8 != 0) return NUNET_E_BADARG;
     const long long items = (long long)N * 4 * h * w * (C / 8);
     if (items >= (1LL << 31) || ((C / 8) & (C / 8 - 1)) != 0) return NUNET_E_UNSUPPORTED;
-    long long blocks = (items + 511) / 512;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    upsample2x_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, h, w, C / 8, (__nv_bfloat16*)out);
+    const long long blocks = (long long)N * ((2 * h + kUpRows - 1) / kUpRows);
+    if (blocks >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
+    upsample2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, h, w, C / 8, (__nv_bfloat16*)out);
     return cuda_rc();
 }
 

@@ -11,6 +11,7 @@
 //      reductions of nn.BatchNorm2d's backward (yhat = (y-mean)*invstd).
 // The affine rest of BN backward (g_y = k1*g_z + k2*y + k3) is folded into the loaders of dgrad / wgrad.
 #include "conv_common.cuh"
+#include <cstdlib>
 
 namespace nunet {
 
@@ -200,6 +201,127 @@ __global__ void __launch_bounds__(256, 2) grad_router_kernel(const RouterParams 
     }
 }
 
+// Specialised router for what the engine launches (no UP consumer: those go through up_transpose.cu first).  Same arithmetic
+// for g_z; the second BatchNorm sum is accumulated as sum(g_z*y) and sum(g_z) and combined per thread at the end,
+//   sum(g_z*yhat) = invstd * (sum(g_z*y) - mean*sum(g_z)),
+// which keeps mean/invstd out of the loop: <= 64 registers, four CTAs per SM (twice the loads in flight of the generic kernel,
+// which ncu showed latency-bound at 25 % occupancy).  NS = number of same-resolution consumers (compile time).
+template <int NS, bool HAS_POOL, bool HAS_HEAD>
+__global__ void __launch_bounds__(256, HAS_POOL ? 3 : 4) grad_router_fast_kernel(const RouterParams p) {
+    const int cgs = p.C >> 3;
+    const int cg_shift = 31 - __clz(cgs);
+    const int cg = threadIdx.x & (cgs - 1);
+    const int ch = cg * 8;
+    const int HW = p.H * p.W;
+    const int items = p.N * HW * cgs;
+    float sc[8], sh[8], acc1[8], acc2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = p.scale[ch + i];
+        sh[i] = p.shift[ch + i];
+        acc1[i] = 0.f;
+        acc2[i] = 0.f;
+    }
+    constexpr int U = (NS <= 2 && !HAS_POOL) ? 2 : 1;
+    const int stride = gridDim.x * 256;
+    for (int it0 = blockIdx.x * 256 + threadIdx.x; it0 < items; it0 += stride * U) {
+        uint4 ry[U], rd[U][NS > 0 ? NS : 1];
+        int pix[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * stride;
+            pix[u] = (it < items) ? (it >> cg_shift) : -1;
+            if (pix[u] >= 0) {
+                ry[u] = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)pix[u] * p.C + ch));
+#pragma unroll
+                for (int ci = 0; ci < NS; ++ci)
+                    rd[u][ci] = __ldg(reinterpret_cast<const uint4*>(p.cons[ci].dx + (size_t)pix[u] * p.cons[ci].pitch + p.cons[ci].coff + ch));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (pix[u] < 0) continue;
+            float yv[8], g[8];
+            unpack8f(ry[u], yv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < NS; ++ci) add8(g, rd[u][ci], 1.f);
+            if constexpr (HAS_POOL || HAS_HEAD) {
+                const int n = pix[u] / HW, rem = pix[u] - n * HW;
+                if constexpr (HAS_POOL) {
+                    // consumer at (H/2, W/2): route to the first maximum of the 2x2 window of a = relu(scale*y+shift)
+                    const int yy = rem / p.W, xx = rem - yy * p.W;
+                    const GradCons& c = p.cons[NS];
+                    const int y0 = yy & ~1, x0 = xx & ~1;
+                    const int me = ((yy & 1) << 1) | (xx & 1);
+                    const size_t wbase = (size_t)n * HW + (size_t)y0 * p.W + x0;
+                    float am[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) am[i] = fmaxf(fmaf(yv[i], sc[i], sh[i]), 0.f);
+                    unsigned win = 0xFFu;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k == me) continue;
+                        float t[8];
+                        unpack8f(__ldg(reinterpret_cast<const uint4*>(p.y + (wbase + (size_t)(k >> 1) * p.W + (k & 1)) * p.C + ch)), t);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float ak = fmaxf(fmaf(t[i], sc[i], sh[i]), 0.f);
+                            const bool keep = (k < me) ? (am[i] > ak) : (am[i] >= ak);
+                            if (!keep) win &= ~(1u << i);
+                        }
+                    }
+                    const size_t cpix = ((size_t)n * (p.H >> 1) + (yy >> 1)) * (p.W >> 1) + (xx >> 1);
+                    float d[8];
+                    unpack8f(__ldg(reinterpret_cast<const uint4*>(c.dx + cpix * c.pitch + c.coff + ch)), d);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (win & (1u << i)) g[i] += d[i];
+                }
+                if constexpr (HAS_HEAD) {
+                    for (int k = 0; k < p.K; ++k) {
+                        const float dl = __ldg(p.dlogits + ((size_t)n * p.K + k) * HW + rem);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) g[i] = fmaf(dl, __ldg(p.wh + k * p.C + ch + i), g[i]);
+                    }
+                }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float z = fmaf(yv[i], sc[i], sh[i]);
+                const float gz = (z > 0.f) ? g[i] : 0.f;
+                g[i] = gz;
+                acc1[i] += gz;
+                acc2[i] = fmaf(gz, yv[i], acc2[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+                o[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(p.gz + (size_t)pix[u] * p.C + ch) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc2[i] = p.invstd[ch + i] * (acc2[i] - p.mean[ch + i] * acc1[i]);
+    // block reduction: threads with equal cg (tid % cgs) hold the same 8 channels
+    __shared__ float red[256][9];
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = pass == 0 ? acc1[i] : acc2[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < p.C; c += 256) {
+            const int g8 = c >> 3, e = c & 7;
+            float s = 0.f;
+            for (int t = g8; t < 256; t += cgs) s += red[t][e];
+            p.part[((size_t)blockIdx.x * 2 + pass) * p.C + c] = s;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -241,6 +363,16 @@ extern "C" int nunet_grad_router(const nunet_router_desc_t* d, void* stream) {
     const int rows = nunet_grad_router_rows(d->N, d->H, d->W, d->C);
     const bool hp = n_pool > 0, hu = n_up > 0, hh = d->dlogits != nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool no_fast = getenv("NUNET_ROUTER_GENERIC") != nullptr;
+    if (!hu && !no_fast) {
+#define NUNET_FAST_CASE(NS_, P_, H_) if (n_same == NS_ && hp == P_ && hh == H_) grad_router_fast_kernel<NS_, P_, H_><<<rows, 256, 0, st>>>(p)
+#define NUNET_FAST_NS(NS_) NUNET_FAST_CASE(NS_, false, false); NUNET_FAST_CASE(NS_, false, true); NUNET_FAST_CASE(NS_, true, false); NUNET_FAST_CASE(NS_, true, true)
+        NUNET_FAST_NS(0); NUNET_FAST_NS(1); NUNET_FAST_NS(2); NUNET_FAST_NS(3); NUNET_FAST_NS(4);
+#undef NUNET_FAST_NS
+#undef NUNET_FAST_CASE
+        cudaError_t e0 = cudaGetLastError();
+        return e0 == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e0;
+    }
 #define NUNET_ROUTER_CASE(P_, U_, H_) if (hp == P_ && hu == U_ && hh == H_) grad_router_kernel<P_, U_, H_><<<rows, 256, 0, st>>>(p)
     NUNET_ROUTER_CASE(false, false, false);
     NUNET_ROUTER_CASE(false, false, true);

@@ -2,7 +2,7 @@
 // align_corners=True), finished/archs1.py:42,83): routes a consumer's dgrad slice at (2h, 2w) back to the (h, w)
 // resolution of the node that was upsampled.  out[n,y,x,c] = sum_{Y,X} wy(Y,y) * wx(X,x) * dx[n,Y,X,coff+c].
 //
-// One CTA = an 8x8 tile of source pixels x 64 channels.  The (<= 22 x 22) window of contributing output pixels is
+// One CTA = an 8x8 tile of source pixels x 32 channels.  The (<= 22 x 22) window of contributing output pixels is
 // brought into shared memory once with cp.async; the gather is separable: x-reduction into an fp32 tile, then
 // y-reduction, so every dX element is read from HBM/L2 ~(22/16)^2 times instead of ~4 gathers per element from 16
 // scattered loads per thread.  The result is a dense bf16 NHWC tensor the gradient router reads as a SAME consumer.
@@ -12,7 +12,8 @@ namespace nunet {
 
 constexpr int kUT = 8;             // source tile edge
 constexpr int kUW = 2 * kUT + 6;   // output window edge (candidates [2s-3, 2s+4])
-constexpr int kUC = 64;            // channels per CTA
+constexpr int kUC = 32;            // channels per CTA (4 CTAs per SM)
+constexpr int kTaps = 5;           // contributing outputs of one source index are consecutive and at most 5 (2/r = 4.0x, r < 1/2)
 
 __device__ __forceinline__ float upw(int D, int s, int h, float r) {
     const float src = r * (float)D;
@@ -28,37 +29,53 @@ struct UpTParams {
     __nv_bfloat16* out;
 };
 
-__global__ void __launch_bounds__(256, 2) up_transpose_kernel(const UpTParams p) {
+__global__ void __launch_bounds__(256, 4) up_transpose_kernel(const UpTParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint4* s_in = reinterpret_cast<uint4*>(smem);                                  // [kUW][kUW][8 cg] x 16 B
-    float* s_tmp = reinterpret_cast<float*>(smem + (size_t)kUW * kUW * 8 * 16);     // [kUW][kUT][64] fp32
-    float* s_wy = s_tmp + kUW * kUT * kUC;                                          // [kUT][8]
-    float* s_wx = s_wy + kUT * 8;                                                   // [kUT][8]
+    constexpr int kCg = kUC / 8;
+    uint4* s_in = reinterpret_cast<uint4*>(smem);                                    // [kUW][kUW][kCg] x 16 B
+    float* s_tmp = reinterpret_cast<float*>(smem + (size_t)kUW * kUW * kCg * 16);     // [kUW][kUT][kUC] fp32
+    float* s_wy = s_tmp + kUW * kUT * kUC;                                            // [kUT][kTaps]
+    float* s_wx = s_wy + kUT * kTaps;                                                 // [kUT][kTaps]
+    int* s_k0 = reinterpret_cast<int*>(s_wx + kUT * kTaps);                           // [2][kUT] first contributing candidate (window coords 2s + k0)
     const int tiles_x = (p.w + kUT - 1) / kUT, tiles_y = (p.h + kUT - 1) / kUT;
     int t = blockIdx.x;
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y; t /= tiles_y;
     const int n = t;
     const int c0 = blockIdx.y * kUC;
-    const int ncg = min(8, (p.C - c0) >> 3);
+    const int ncg = min(kCg, (p.C - c0) >> 3);
     const int y0 = ty * kUT, x0 = tx * kUT;
     const int H2 = 2 * p.h, W2 = 2 * p.w;
     const int Ymin = 2 * y0 - 3, Xmin = 2 * x0 - 3;
     const float ry = (float)(p.h - 1) / (float)(H2 - 1), rx = (float)(p.w - 1) / (float)(W2 - 1);
-    // weights of candidate k (output index 2s-3+k) for each of the 8 tile rows / cols
-    if (threadIdx.x < 128) {
-        const int which = threadIdx.x >> 6, s = (threadIdx.x >> 3) & 7, k = threadIdx.x & 7;
-        if (which == 0) {
-            const int ys = y0 + s, Y = 2 * ys - 3 + k;
-            s_wy[s * 8 + k] = (ys < p.h && Y >= 0 && Y < H2) ? upw(Y, ys, p.h, ry) : 0.f;
-        } else {
-            const int xs = x0 + s, X = 2 * xs - 3 + k;
-            s_wx[s * 8 + k] = (xs < p.w && X >= 0 && X < W2) ? upw(X, xs, p.w, rx) : 0.f;
+    // per tile row / column s: first candidate k0 in [0,8) with a non-zero weight and the kTaps weights from there
+    if (threadIdx.x < 2 * kUT) {
+        const int which = threadIdx.x / kUT, s = threadIdx.x % kUT;
+        const int src = (which == 0 ? y0 : x0) + s, hh = which == 0 ? p.h : p.w, D2 = which == 0 ? H2 : W2;
+        const float r = which == 0 ? ry : rx;
+        float wk[8];
+        int k0 = 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int D = 2 * src - 3 + k;
+            wk[k] = (src < hh && D >= 0 && D < D2) ? upw(D, src, hh, r) : 0.f;
+            if (wk[k] != 0.f && k0 == 8) k0 = k;
         }
+        if (k0 > 8 - kTaps) k0 = 8 - kTaps;
+        float* dstw = (which == 0 ? s_wy : s_wx) + s * kTaps;
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k == k0 + j) v = wk[k];
+            dstw[j] = v;
+        }
+        s_k0[which * kUT + s] = k0;
     }
     // window load: kUW x kUW output pixels x ncg 16-byte groups (zero outside the image)
-    for (int i = threadIdx.x; i < kUW * kUW * 8; i += 256) {
-        const int cg = i & 7, px = (i >> 3) % kUW, py = (i >> 3) / kUW;
+    for (int i = threadIdx.x; i < kUW * kUW * kCg; i += 256) {
+        const int cg = i % kCg, px = (i / kCg) % kUW, py = i / (kCg * kUW);
         const int Y = Ymin + py, X = Xmin + px;
         const bool ok = cg < ncg && Y >= 0 && Y < H2 && X >= 0 && X < W2;
         const size_t pix = ((size_t)n * H2 + (ok ? Y : 0)) * W2 + (ok ? X : 0);
@@ -67,24 +84,23 @@ __global__ void __launch_bounds__(256, 2) up_transpose_kernel(const UpTParams p)
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    // x-reduction: tmp[py][xs][c] = sum_k wx[xs][k] * in[py][2*xs+k (window coords)][c]
-    for (int i = threadIdx.x; i < kUW * kUT * 8; i += 256) {
-        const int cg = i & 7, xs = (i >> 3) & 7, py = i >> 6;
+    // x-reduction: tmp[py][xs][c] = sum_j wx[xs][j] * in[py][2*xs + k0 + j (window coords)][c]
+    for (int i = threadIdx.x; i < kUW * kUT * kCg; i += 256) {
+        const int cg = i % kCg, xs = (i / kCg) % kUT, py = i / (kCg * kUT);
+        const int kb = 2 * xs + s_k0[kUT + xs];
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float wgt = s_wx[xs * 8 + k];
-            if (wgt != 0.f) {
-                const uint4 r = s_in[(py * kUW + 2 * xs + k) * 8 + cg];
-                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r);
+        for (int j = 0; j < kTaps; ++j) {
+            const float wgt = s_wx[xs * kTaps + j];
+            const uint4 r = s_in[(py * kUW + kb + j) * kCg + cg];
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(hh[e]);
-                    acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
-                    acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
-                }
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
+                acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
             }
         }
         float4* d = reinterpret_cast<float4*>(s_tmp + ((size_t)py * kUT + xs) * kUC + cg * 8);
@@ -93,22 +109,21 @@ __global__ void __launch_bounds__(256, 2) up_transpose_kernel(const UpTParams p)
     }
     __syncthreads();
     // y-reduction and store
-    for (int i = threadIdx.x; i < kUT * kUT * 8; i += 256) {
-        const int cg = i & 7, xs = (i >> 3) & 7, ys = i >> 6;
+    for (int i = threadIdx.x; i < kUT * kUT * kCg; i += 256) {
+        const int cg = i % kCg, xs = (i / kCg) % kUT, ys = i / (kCg * kUT);
         const int y = y0 + ys, x = x0 + xs;
         if (y >= p.h || x >= p.w || cg >= ncg) continue;
+        const int kb = 2 * ys + s_k0[ys];
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float wgt = s_wy[ys * 8 + k];
-            if (wgt != 0.f) {
-                const float4* s4 = reinterpret_cast<const float4*>(s_tmp + ((size_t)(2 * ys + k) * kUT + xs) * kUC + cg * 8);
-                const float4 a = s4[0], b = s4[1];
-                acc[0] = fmaf(wgt, a.x, acc[0]); acc[1] = fmaf(wgt, a.y, acc[1]); acc[2] = fmaf(wgt, a.z, acc[2]); acc[3] = fmaf(wgt, a.w, acc[3]);
-                acc[4] = fmaf(wgt, b.x, acc[4]); acc[5] = fmaf(wgt, b.y, acc[5]); acc[6] = fmaf(wgt, b.z, acc[6]); acc[7] = fmaf(wgt, b.w, acc[7]);
-            }
+        for (int j = 0; j < kTaps; ++j) {
+            const float wgt = s_wy[ys * kTaps + j];
+            const float4* s4 = reinterpret_cast<const float4*>(s_tmp + ((size_t)(kb + j) * kUT + xs) * kUC + cg * 8);
+            const float4 a = s4[0], b = s4[1];
+            acc[0] = fmaf(wgt, a.x, acc[0]); acc[1] = fmaf(wgt, a.y, acc[1]); acc[2] = fmaf(wgt, a.z, acc[2]); acc[3] = fmaf(wgt, a.w, acc[3]);
+            acc[4] = fmaf(wgt, b.x, acc[4]); acc[5] = fmaf(wgt, b.y, acc[5]); acc[6] = fmaf(wgt, b.z, acc[6]); acc[7] = fmaf(wgt, b.w, acc[7]);
         }
         uint32_t o[4];
 #pragma unroll
@@ -130,7 +145,7 @@ extern "C" int nunet_up_transpose(const void* dx, int32_t pitch, int32_t coff, i
     const long long tiles = (long long)N * ((h + kUT - 1) / kUT) * ((w + kUT - 1) / kUT);
     if (tiles >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
     UpTParams p{(const __nv_bfloat16*)dx, pitch, coff, N, h, w, C, (__nv_bfloat16*)out};
-    const size_t smem = (size_t)kUW * kUW * 8 * 16 + (size_t)kUW * kUT * kUC * 4 + 2 * kUT * 8 * 4;
+    const size_t smem = (size_t)kUW * kUW * (kUC / 8) * 16 + (size_t)kUW * kUT * kUC * 4 + 2 * kUT * kTaps * 4 + 2 * kUT * 4;
     cudaError_t e = cudaFuncSetAttribute(up_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
     up_transpose_kernel<<<dim3((unsigned)tiles, (C + kUC - 1) / kUC), 256, smem, (cudaStream_t)stream>>>(p);

@@ -493,6 +493,9 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
 # captured into a CUDA graph (same kernels, same per-stream order: bitwise identical results) and replayed: two graph
 # launches per step.  The optimizer stays outside (it updates the fp32 masters in place; the graph re-packs them).
 GRAPH_TRAIN = _os.environ.get("NUNET_GRAPH_TRAIN", "1") == "1"
+# Capturing the data-parallel step (NCCL all-reduces inside the graphs) is wired but OFF: with torch 2.11 / NCCL 2.28 the
+# capture of the bucketed async all-reduce + SyncBN exchanges deadlocked on 2 GPUs (gpurun, round 1); DP steps run eagerly.
+GRAPH_TRAIN_DP = _os.environ.get("NUNET_GRAPH_TRAIN_DP", "0") == "1"
 
 
 class _TrainGraph(object):
@@ -506,7 +509,9 @@ class _TrainGraph(object):
 
 def _train_graph(model, x, params):
     """The graph slot of this (shape, parameter set), or None when the step has to run eagerly."""
-    if not GRAPH_TRAIN or _world(model) is not None or ops.kernel_timing_enabled():
+    if not GRAPH_TRAIN or ops.kernel_timing_enabled():
+        return None
+    if _world(model) is not None and not GRAPH_TRAIN_DP:      # data parallel: the NCCL collectives are captured with the step
         return None
     if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous()):
         return None
@@ -599,7 +604,18 @@ class _NetFunction(torch.autograd.Function):
                 o, n, shape = offs[id(p)]
                 return tg.flat[o:o + n].view(shape)
             tg.views = offs
-            tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, lambda: _backward(ctx.model, tg.xs, tg.recs, tg.gl, grad_alloc=alloc))
+            if _world(ctx.model) is None:
+                tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, lambda: _backward(ctx.model, tg.xs, tg.recs, tg.gl, grad_alloc=alloc))
+            else:
+                # data parallel: backward writes into the bucket buffer it all-reduces in place (captured NCCL launches);
+                # the reduced gradients are then gathered into the slot's flat buffer inside the same graph
+                def bwd_dp():
+                    grads = _backward(ctx.model, tg.xs, tg.recs, tg.gl)
+                    for p in ctx.params:
+                        g = grads.get(id(p))
+                        if g is not None:
+                            alloc(p).copy_(g)
+                tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, bwd_dp)
         for i, g in zip(tg.head_layers, grad_logits):
             if g is None:
                 tg.gl[i].zero_()

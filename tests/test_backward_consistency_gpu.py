@@ -67,8 +67,8 @@ def test_backward_matches_autograd_with_forced_forward(arch, ds, K, n, h, w):
     keep = {}
     orig_forward = engine._forward
 
-    def _capturing_forward(m, xx, tr):
-        res = orig_forward(m, xx, tr)
+    def _capturing_forward(m, xx, tr, **kw):
+        res = orig_forward(m, xx, tr, **kw)
         keep["recs"] = res[1]
         return res
 
