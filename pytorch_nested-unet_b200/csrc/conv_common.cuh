@@ -22,6 +22,7 @@ struct ConvParams {
     int Wp, Hp1;  // W+2, H+1
     int Q;        // padded positions: (N*(H+1)+1)*(W+2)
     int T, NT, CK, S, P, nchunks, cin_pad, Cout, num_src, tmem_cols, ntg;
+    int res_b;          // 1: single K chunk, the weight block is fetched once per CTA and stays resident
     int a_stage_bytes;  // TMA mode: bytes of one A stage ((P + Wp) rows of 64 B, rounded to 1 KB)
     ConvSrc src[NUNET_MAX_SRC];
     const void* wpack;
