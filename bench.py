@@ -278,9 +278,14 @@ def run_native(args):
     side_saved, lvl_saved = engine.WGRAD_SIDE_STREAM, engine.LEVEL_STREAMS
     engine.WGRAD_SIDE_STREAM = False            # per-kernel CUDA events need every launch on the one (launching) stream
     engine.LEVEL_STREAMS = False
+    saved_graph = engine.GRAPH_TRAIN
+    engine.GRAPH_TRAIN = False
+    step(x_dev, t_dev)                          # untimed eager single-stream step: warms this schedule's allocator pool
+    torch.cuda.synchronize()
     ops.enable_kernel_timing(rank == 0)
     step(x_dev, t_dev)
     torch.cuda.synchronize()
+    engine.GRAPH_TRAIN = saved_graph
     timing = ops.collect_kernel_timing() if rank == 0 else None
     ops.enable_kernel_timing(False)
     engine.WGRAD_SIDE_STREAM, engine.LEVEL_STREAMS = side_saved, lvl_saved
