@@ -7,6 +7,7 @@
 // y-reduction, so every dX element is read from HBM/L2 ~(22/16)^2 times instead of ~4 gathers per element from 16
 // scattered loads per thread.  The result is a dense bf16 NHWC tensor the gradient router reads as a SAME consumer.
 #include "conv_common.cuh"
+#include <cstdlib>
 
 namespace nunet {
 
@@ -135,6 +136,124 @@ __global__ void __launch_bounds__(256, 4) up_transpose_kernel(const UpTParams p)
     }
 }
 
+// ---- streaming variant (default).  A thread owns one (source column x, 8-channel group) and walks the output rows Y that
+// touch its block of source rows.  Per output row it gathers the <= 5 contributing output columns (weights precomputed once),
+// and adds the x-reduced value to the two source rows Y blends (y0 with 1-ly, y1 with ly): y0 is non-decreasing in Y, so two
+// running row accumulators suffice and a row is written out the moment y0 moves past it.  10 16-byte loads per output item
+// (L1 serves the overlap between neighbouring threads), no shared memory, no barriers: HBM-bound instead of issue-bound.
+constexpr int kRB = 16;   // source rows per CTA (3 extra output rows are re-read per CTA)
+
+__global__ void __launch_bounds__(128) up_transpose_stream_kernel(const UpTParams p) {
+    const int cgs = p.C >> 3;
+    const int item = blockIdx.y * 128 + threadIdx.x;
+    if (item >= p.w * cgs) return;
+    const int cg = item % cgs, x = item / cgs;
+    const int rblocks = (p.h + kRB - 1) / kRB;
+    const int n = blockIdx.x / rblocks, ys = (blockIdx.x - n * rblocks) * kRB;
+    const int ye = min(p.h, ys + kRB);
+    const int H2 = 2 * p.h, W2 = 2 * p.w;
+    const float ry = (float)(p.h - 1) / (float)(H2 - 1), rx = (float)(p.w - 1) / (float)(W2 - 1);
+    // the <= kTaps consecutive output columns that read source column x
+    float wx[kTaps];
+    int X0 = 0;
+    {
+        float wk[8];
+        int k0 = 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int D = 2 * x - 3 + k;
+            wk[k] = (D >= 0 && D < W2) ? upw(D, x, p.w, rx) : 0.f;
+            if (wk[k] != 0.f && k0 == 8) k0 = k;
+        }
+        if (k0 > 8 - kTaps) k0 = 8 - kTaps;
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k == k0 + j) v = wk[k];
+            wx[j] = v;
+        }
+        X0 = 2 * x - 3 + k0;
+        // clamp the window into the image (weights of clamped-away columns are zero by construction)
+        if (X0 < 0) {
+#pragma unroll
+            for (int sft = 0; sft < 3; ++sft)
+                if (X0 < 0) {
+#pragma unroll
+                    for (int j = 0; j < kTaps - 1; ++j) wx[j] = wx[j + 1];
+                    wx[kTaps - 1] = 0.f;
+                    ++X0;
+                }
+        }
+    }
+    const __nv_bfloat16* src = p.dx + (size_t)n * H2 * W2 * p.pitch + p.coff + cg * 8;
+    __nv_bfloat16* dst = p.out + (size_t)n * p.h * p.w * p.C + (size_t)x * p.C + cg * 8;
+    float acc_a[8], acc_b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc_a[e] = 0.f; acc_b[e] = 0.f; }
+    const int Ystart = max(0, 2 * ys - 4);
+    int cur = (int)(ry * (float)Ystart);
+    for (int Y = Ystart; Y < H2; ++Y) {
+        const float sy = ry * (float)Y;
+        const int y0 = (int)sy;
+        if (y0 >= ye) break;
+        const int y1 = y0 + (y0 < p.h - 1);
+        const float ly = sy - (float)y0;
+        if (y0 > cur) {   // row `cur` is complete
+            if (cur >= ys) {
+                uint4 o;
+                __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) q[e] = __floats2bfloat162_rn(acc_a[2 * e], acc_a[2 * e + 1]);
+                *reinterpret_cast<uint4*>(dst + (size_t)cur * p.w * p.C) = o;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { acc_a[e] = acc_b[e]; acc_b[e] = 0.f; }
+            cur = y0;
+        }
+        const __nv_bfloat16* rowp = src + ((size_t)Y * W2 + X0) * p.pitch;
+        uint4 r[kTaps];
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) r[j] = (X0 + j < W2) ? __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)j * p.pitch)) : make_uint4(0, 0, 0, 0);
+        float xr[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xr[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r[j]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                xr[2 * e] = fmaf(wx[j], f.x, xr[2 * e]);
+                xr[2 * e + 1] = fmaf(wx[j], f.y, xr[2 * e + 1]);
+            }
+        }
+        const float w0 = 1.f - ly;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc_a[e] = fmaf(w0, xr[e], acc_a[e]);
+        if (y1 == y0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc_a[e] = fmaf(ly, xr[e], acc_a[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc_b[e] = fmaf(ly, xr[e], acc_b[e]);
+        }
+    }
+    // rows still held: `cur` (acc_a) and `cur + 1` (acc_b)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int row = cur + t;
+        if (row >= ys && row < ye) {
+            uint4 o;
+            __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q[e] = t == 0 ? __floats2bfloat162_rn(acc_a[2 * e], acc_a[2 * e + 1]) : __floats2bfloat162_rn(acc_b[2 * e], acc_b[2 * e + 1]);
+            *reinterpret_cast<uint4*>(dst + (size_t)row * p.w * p.C) = o;
+        }
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -145,6 +264,14 @@ extern "C" int nunet_up_transpose(const void* dx, int32_t pitch, int32_t coff, i
     const long long tiles = (long long)N * ((h + kUT - 1) / kUT) * ((w + kUT - 1) / kUT);
     if (tiles >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
     UpTParams p{(const __nv_bfloat16*)dx, pitch, coff, N, h, w, C, (__nv_bfloat16*)out};
+    static const bool tiled = getenv("NUNET_UPT_TILED") != nullptr;
+    if (!tiled) {
+        const long long bx = (long long)N * ((h + kRB - 1) / kRB);
+        if (bx >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
+        up_transpose_stream_kernel<<<dim3((unsigned)bx, (w * (C / 8) + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+        cudaError_t e0 = cudaGetLastError();
+        return e0 == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e0;
+    }
     const size_t smem = (size_t)kUW * kUW * (kUC / 8) * 16 + (size_t)kUW * kUT * kUC * 4 + 2 * kUT * kTaps * 4 + 2 * kUT * 4;
     cudaError_t e = cudaFuncSetAttribute(up_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
