@@ -7,6 +7,7 @@
 namespace nunet {
 
 constexpr int kRS = 32;  // row slices per channel group
+constexpr int kDirectRows = 1024;  // up to here one CTA per 32 channels reduces the partial rows directly
 
 struct BnFinalizeArgs {
     int mode;  // 0: forward statistics -> apply coefficients ; 1: backward sums -> dgamma/dbeta + loader coefficients
@@ -103,6 +104,30 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
         if (fin.gamma) bn_finalize_channel(fin, c, S, SS);
     }
     if (threadIdx.x == 0) counters[blockIdx.x] = 0;  // self-resetting for the next launch
+}
+
+// Single-pass variant for the row counts the conv / router kernels actually produce (<= a few hundred partial rows): one CTA
+// per 32 channels, 32 row lanes x 32 channels, fp64 accumulation per thread in a fixed order, no scratch / atomics / second
+// phase (the last-block-done kernel above costs ~12 us per BatchNorm layer, 60 times per step; this one ~3 us).
+__global__ void __launch_bounds__(1024) bn_reduce_direct_kernel(const float* __restrict__ part, int rows, int C, double* sums_out,
+                                                                 BnFinalizeArgs fin) {
+    __shared__ double sh[2][32][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double s = 0.0, ss = 0.0;
+    for (int r = rl; r < rows; r += 32) {
+        s += (double)part[(size_t)r * 2 * C + c];
+        ss += (double)part[(size_t)r * 2 * C + C + c];
+    }
+    sh[0][rl][cl] = s;
+    sh[1][rl][cl] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double S = 0.0, SS = 0.0;
+        for (int i = 0; i < 32; ++i) { S += sh[0][i][cl]; SS += sh[1][i][cl]; }
+        if (sums_out) { sums_out[c] = S; sums_out[C + c] = SS; }
+        if (fin.gamma) bn_finalize_channel(fin, c, S, SS);
+    }
 }
 
 __global__ void bn_finalize_from_sums_kernel(const double* __restrict__ sums, int C, BnFinalizeArgs fin) {
@@ -306,7 +331,10 @@ extern "C" int nunet_bn_finalize_train(const float* stat_part, int32_t rows, int
     if (!stat_part || rows <= 0 || C <= 0 || C % 32 != 0 || !scratch || !counters) return NUNET_E_BADARG;
     if (gamma && (!beta || !scale || !shift || count <= 0)) return NUNET_E_BADARG;
     BnFinalizeArgs f{0, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd};
-    bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(stat_part, rows, C, scratch, counters, sums_out, f);
+    if (rows <= kDirectRows)
+        bn_reduce_direct_kernel<<<C / 32, 1024, 0, (cudaStream_t)stream>>>(stat_part, rows, C, sums_out, f);
+    else
+        bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(stat_part, rows, C, scratch, counters, sums_out, f);
     return cuda_rc();
 }
 
@@ -338,7 +366,10 @@ extern "C" int nunet_bn_backward_reduce(const float* part, int32_t rows, int32_t
     f.mode = 1; f.count = count; f.gamma = gamma; f.save_mean = const_cast<float*>(save_mean);
     f.save_invstd = const_cast<float*>(save_invstd); f.dgamma = dgamma; f.dbeta = dbeta; f.k1 = k1; f.k2 = k2; f.k3 = k3;
     f.grad_scale = 1.f;
-    bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(part, rows, C, scratch, counters, sums_out, f);
+    if (rows <= kDirectRows)
+        bn_reduce_direct_kernel<<<C / 32, 1024, 0, (cudaStream_t)stream>>>(part, rows, C, sums_out, f);
+    else
+        bn_reduce_kernel<<<dim3(C / 32, kRS), 256, 0, (cudaStream_t)stream>>>(part, rows, C, scratch, counters, sums_out, f);
     return cuda_rc();
 }
 
