@@ -24,7 +24,7 @@ from torch.optim import lr_scheduler
 import archs
 import losses
 from metrics import iou_score
-from utils import AverageMeter, DevicePrefetcher, str2bool
+from utils import AverageMeter, str2bool
 
 ARCH_NAMES = archs.__all__
 LOSS_NAMES = losses.__all__ + ['BCEWithLogitsLoss']
@@ -92,7 +92,9 @@ def train(config, train_loader, model, criterion, optimizer):
     """trains.py:106-147."""
     avg_meters = {'loss': AverageMeter(), 'iou': AverageMeter()}
     model.train()
-    for input, target, _ in DevicePrefetcher(train_loader):
+    for input, target, _ in train_loader:
+        input = input.cuda(non_blocking=True)
+        target = target.cuda(non_blocking=True)
         loss, iou = _loss_and_iou(config, model, criterion, input, target)
         optimizer.zero_grad()
         loss.backward()
@@ -107,7 +109,9 @@ def validate(config, val_loader, model, criterion):
     avg_meters = {'loss': AverageMeter(), 'iou': AverageMeter()}
     model.eval()
     with torch.no_grad():
-        for input, target, _ in DevicePrefetcher(val_loader):
+        for input, target, _ in val_loader:
+            input = input.cuda(non_blocking=True)
+            target = target.cuda(non_blocking=True)
             loss, iou = _loss_and_iou(config, model, criterion, input, target)
             avg_meters['loss'].update(loss.item(), input.size(0))
             avg_meters['iou'].update(iou, input.size(0))
