@@ -566,11 +566,20 @@ class _NetFunction(torch.autograd.Function):
             ctx.head_layers = [i for i, _ in logits]
             return tuple(t for _, t in logits)
         if tg.fwd is None:
-            tg.pool = torch.cuda.graph_pool_handle()
-            tg.x = x.clone()
-            tg.fwd, (tg.xs, tg.recs, logits), tg.launches_f = _capture(tg, model, lambda: _forward(model, tg.x, True, want_dgrad=True))
-            tg.head_layers = [i for i, _ in logits]
-            tg.outs = tuple(t for _, t in logits)
+            try:
+                tg.pool = torch.cuda.graph_pool_handle()
+                tg.x = x.clone()
+                tg.fwd, (tg.xs, tg.recs, logits), tg.launches_f = _capture(tg, model, lambda: _forward(model, tg.x, True, want_dgrad=True))
+                tg.head_layers = [i for i, _ in logits]
+                tg.outs = tuple(t for _, t in logits)
+            except Exception as exc:      # capture is an optimisation: fall back to the eager step for this shape
+                import warnings
+                warnings.warn("nunet: CUDA-graph capture of the training forward failed (%s); running eagerly" % (exc,))
+                tg.failed, tg.fwd, ctx.tg = True, None, None
+                x, recs, logits = _forward(model, x, True, want_dgrad=True)
+                ctx.x, ctx.recs = x, recs
+                ctx.head_layers = [i for i, _ in logits]
+                return tuple(t for _, t in logits)
         tg.x.copy_(x)
         tg.fwd.replay()
         ops.add_launches(tg.launches_f)
@@ -604,8 +613,15 @@ class _NetFunction(torch.autograd.Function):
                 o, n, shape = offs[id(p)]
                 return tg.flat[o:o + n].view(shape)
             tg.views = offs
-            if _world(ctx.model) is None:
-                tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, lambda: _backward(ctx.model, tg.xs, tg.recs, tg.gl, grad_alloc=alloc))
+            if tg.failed:
+                pass
+            elif _world(ctx.model) is None:
+                try:
+                    tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, lambda: _backward(ctx.model, tg.xs, tg.recs, tg.gl, grad_alloc=alloc))
+                except Exception as exc:
+                    import warnings
+                    warnings.warn("nunet: CUDA-graph capture of the training backward failed (%s); running eagerly" % (exc,))
+                    tg.failed, tg.bwd = True, None
             else:
                 # data parallel: backward writes into the bucket buffer it all-reduces in place (captured NCCL launches);
                 # the reduced gradients are then gathered into the slot's flat buffer inside the same graph
@@ -621,9 +637,14 @@ class _NetFunction(torch.autograd.Function):
                 tg.gl[i].zero_()
             else:
                 tg.gl[i].copy_(g)
-        tg.bwd.replay()
-        ops.add_launches(tg.launches_b)
-        tg.bwd_gen = ctx.gen
+        if tg.bwd is not None:
+            tg.bwd.replay()
+            ops.add_launches(tg.launches_b)
+            tg.bwd_gen = ctx.gen
+        else:                         # backward capture failed earlier: eager backward on the captured forward's activations
+            grads = _backward(ctx.model, tg.xs, tg.recs, tg.gl)
+            tg.bwd_gen = ctx.gen
+            return (None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
         flat = tg.flat.clone()            # the caller owns its gradients; the graph's buffer is rewritten by the next replay
         out = []
         for p in ctx.params:
