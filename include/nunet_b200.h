@@ -61,6 +61,8 @@ typedef struct {
     const void* wpack; /* from nunet_pack_weights with the plan of this descriptor */
     void* out;         /* bf16 NHWC [N,H,W,Cout] */
     float* stat_part;  /* [plan.grid_m][2][Cout] fp32 or NULL */
+    int32_t wpack_layout; /* 0: standard pack (NUNET_PACK_FWD / _DGRAD); 1: stacked pack (NUNET_PACK_*_C32) for the Cout = 32 kernel,
+                           * only where nunet_conv3x3_c32_eligible() says so and every source is NUNET_SRC_ACT */
 } nunet_conv_desc_t;
 
 typedef struct {
@@ -75,8 +77,12 @@ int nunet_version(void);
 /* Tiling decision for a conv of this shape (pure host function, no CUDA calls). */
 int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* plan);
 int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream);
+/* 1 if a conv of this shape over NUNET_SRC_ACT sources can run on the stacked Cout = 32 kernel (csrc/conv_c32.cu): kernel columns
+ * stacked into N = 96 on the weight side, column shift applied to the accumulators.  Weights then use the *_C32 pack modes
+ * ([chunk][kernel row][k-group][kernel column * 32 + n][8]; same size as the standard pack). */
+int nunet_conv3x3_c32_eligible(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout);
 
-enum { NUNET_PACK_FWD = 0, NUNET_PACK_DGRAD = 1 };
+enum { NUNET_PACK_FWD = 0, NUNET_PACK_DGRAD = 1, NUNET_PACK_FWD_C32 = 2, NUNET_PACK_DGRAD_C32 = 3 };
 /* fp32 OIHW master weights [Cout,Cin,3,3] -> bf16 tile images consumed by cp.async.bulk (one contiguous block per
  * (N tile, K chunk)).  FWD: GEMM-N = Cout, GEMM-K = Cin (padded to cin_pad).  DGRAD: GEMM-N = Cin, GEMM-K = Cout,
  * taps flipped (transposed convolution).  `plan` is the plan of the conv that will consume the pack. */

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libnunet_b200.so")
 MAX_SRC = 5
 SRC_INPUT, SRC_SAME, SRC_POOL, SRC_UP, SRC_GRAD, SRC_ACT, SRC_POOL_ACT, SRC_UP_ACT = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_KIND = {SRC_SAME: SRC_ACT, SRC_POOL: SRC_POOL_ACT, SRC_UP: SRC_UP_ACT}
-PACK_FWD, PACK_DGRAD = 0, 1
+PACK_FWD, PACK_DGRAD, PACK_FWD_C32, PACK_DGRAD_C32 = 0, 1, 2, 3
 
 
 class Src(C.Structure):
@@ -20,7 +20,7 @@ class Src(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_src", C.c_int32), ("src", Src * MAX_SRC),
-                ("Cout", C.c_int32), ("wpack", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p)]
+                ("Cout", C.c_int32), ("wpack", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p), ("wpack_layout", C.c_int32)]
 
 
 class ConvPlan(C.Structure):
@@ -66,6 +66,7 @@ _SIGS = {
     "nunet_version": ([], C.c_int),
     "nunet_conv3x3_plan": ([C.c_int32] * 5 + [C.POINTER(ConvPlan)], C.c_int),
     "nunet_conv3x3_fwd": ([C.POINTER(ConvDesc), C.c_void_p], C.c_int),
+    "nunet_conv3x3_c32_eligible": ([C.c_int32] * 5, C.c_int),
     "nunet_pack_weights": ([C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ConvPlan), C.c_void_p, C.c_void_p], C.c_int),
     "nunet_pack_weights_batched": ([C.c_void_p, C.c_int32, C.c_void_p], C.c_int),
     "nunet_bn_workspace_bytes": ([C.c_int32], C.c_int),

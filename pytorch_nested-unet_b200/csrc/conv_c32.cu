@@ -1,0 +1,314 @@
+// 3x3 convolution with 32 OUTPUT channels over pre-activated bf16 NHWC sources (the level-0 layers of the network: forward
+// convs of the full-resolution nodes, and the dgrad of their second convs), TMA-fed, kernel columns stacked into N = 96.
+//
+// Why a second conv kernel.  With Cout = 32 the generic implicit GEMM (conv_igemm.cu) issues nine 128x32x16 MMAs per 16 input
+// channels and tile; each costs ~45 cycles because the 4 KB A operand is re-read from shared memory for every tap
+// (profiles/r01_umma_issue_rate.log): 36 % of the tensor peak at best, and those layers are the largest of the step.  Here the
+// three kernel COLUMNS share one A read:
+//     z_dc[q][co] = sum_{dr,ci} X[q + (dr-1)*PW][ci] * W[dr][dc][ci][co]          (3 MMAs 128x96x16 per 16 channels, ~56 cycles each)
+//     y[p][co]    = z_0[p-1][co] + z_1[p][co] + z_2[p+1][co]                      (epilogue: neighbour lanes)
+// i.e. N = 96 = (dc, co) on the weight side, and the column shift is applied to the accumulators instead of the operand.
+//
+// Geometry.  Rows are padded to PW >= W+2 positions; the tensor-load box starts at pixel -1, so position index u of a row
+// holds pixel u-1 (index 0 and indices > W are zero: the conv padding, filled by the TMA unit, like the rows above / below the
+// image).  A group is `ry` rows of one image = ry*PW consecutive positions, covered by tiles of 128 accumulator rows that
+// overlap by two (tile t = positions [126t, 126t+128) of the group; its lanes 1..126 produce outputs), so every output finds
+// both neighbours inside its tile.  The A stage of a 32-channel chunk is ONE tensor load: (32 ch, PW px, ry+3 rows), 64B
+// swizzle = the K-major SWIZZLE_64B operand with 64-byte rows; tap row dr and tile t are start-address offsets.
+// Weights: [chunk][dr][k-group][dc*32+co][8] (NUNET_PACK_*_C32), all chunks fetched once per CTA and kept resident (<= 110 KB).
+// Warps: 0-7 epilogue (TMEM quadrant x channel half), 8 MMA issuer + TMEM owner, 9 TMA / weight fetcher.  TMEM holds the up
+// to five tiles of a group (480 columns) with one full/empty barrier pair PER TILE: the issuer starts tile t of the next group as
+// soon as the epilogue has drained tile t of the current one, so the epilogue overlaps the following group's MMAs.
+// Epilogue: tcgen05.ld, neighbour exchange by warp shuffles (+ a 2 KB shared-memory hand-off between the four quadrant
+// warps), bf16 NHWC store, per-thread BatchNorm sums reduced once at the end (fixed order: deterministic).
+#include "conv_common.cuh"
+#include "loaders.cuh"
+#include "tma.cuh"
+#include <cstdlib>
+
+namespace nunet {
+
+struct C32Params {
+    CUtensorMap xmap[NUNET_MAX_SRC];
+    int N, H, W, PW;
+    int ry, gpi, groups_total;   // rows per group, groups per image
+    int box_rows, S, nch, num_src;
+    int srcC[NUNET_MAX_SRC];
+    int a_stage_bytes;
+    const void* wpack;
+    __nv_bfloat16* out;
+    float* stat_part;            // [gridDim.x][2][32] or null
+};
+
+constexpr int kC32Threads = 320;
+constexpr uint32_t kC32BBytes = 3u * 4u * 96u * 16u;   // one chunk of stacked weights
+constexpr int kC32MaxTiles = 5;
+
+__global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __grid_constant__ C32Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + (size_t)p.S * p.a_stage_bytes;                         // [nch] resident weight chunks
+    float* s_ex = reinterpret_cast<float*>(sB + (size_t)p.nch * kC32BBytes);   // [2 parity][4 lq][2 half][2 side][16]
+    float* s_red = s_ex + 2 * 4 * 2 * 2 * 16;                                  // [8 warps][2][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8 * 2 * 16);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.S;
+    uint64_t* acc_full = bars + 2 * p.S;      // [kC32MaxTiles] MMA -> epilogue, per tile
+    uint64_t* acc_empty = acc_full + kC32MaxTiles;
+    uint64_t* b_full = acc_empty + kC32MaxTiles;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < p.S; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int t = 0; t < kC32MaxTiles; ++t) {
+                mbar_init(&acc_full[t], 1);
+                mbar_init(&acc_empty[t], 8);
+            }
+            mbar_init(b_full, 1);
+            mbar_init_fence();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_ptr);
+    }
+    // the last tile of a group reads a few positions past the loaded rows: keep them finite
+    for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)p.S * (uint32_t)p.a_stage_bytes; i += kC32Threads * 16u) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 9) {
+        // =============================== tensor loads + weights
+        if (lane == 0) {
+            for (int si = 0; si < p.num_src; ++si) tma_prefetch_desc(&p.xmap[si]);
+            const uint32_t a_box_bytes = (uint32_t)p.box_rows * (uint32_t)p.PW * 64u;
+            mbar_arrive_expect_tx(b_full, (uint32_t)p.nch * kC32BBytes);
+            for (int c = 0; c < p.nch; ++c)
+                bulk_g2s(sB + (size_t)c * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, b_full);
+            int cc = 0;
+            for (int g = blockIdx.x; g < p.groups_total; g += gridDim.x) {
+                const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
+                int si = 0, c0 = 0;
+                for (int c = 0; c < p.nch; ++c, ++cc) {
+                    const int s = cc % p.S;
+                    const uint32_t ph = (uint32_t)(cc / p.S) & 1;
+                    const int cglob = c * 32;
+                    while (cglob >= c0 + p.srcC[si]) { c0 += p.srcC[si]; ++si; }
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], a_box_bytes);
+                    tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, -1, y0 - 1, n, &full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 8) {
+        // =============================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 96, kMajorK, kMajorK);
+            const uint32_t a_hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B (8 positions), version 1, SWIZZLE_64B
+            const uint32_t b_hi = umma_desc_hi(128u);                      // no swizzle: 8-row groups 128 B apart
+            const uint32_t pw4 = (uint32_t)p.PW * 4u;                      // one padded row in 16-byte units
+            int cc = 0, it = 0;
+            uint32_t tile_phase = 0;   // bit t: parity of tile t's barriers (groups may use fewer tiles than others)
+            for (int g = blockIdx.x; g < p.groups_total; g += gridDim.x, ++it) {
+                const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
+                const int rows = min(p.ry, p.H - y0);
+                const int ntile = (rows * p.PW + 125) / 126;
+                if (it == 0) mbar_wait(b_full, 0);
+                for (int c = 0; c < p.nch; ++c, ++cc) {
+                    const int s = cc % p.S;
+                    const uint32_t ph = (uint32_t)(cc / p.S) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_base = ((smem_u32(sA + (size_t)s * p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+                    const uint32_t b_base = umma_desc_lo(smem_u32(sB + (size_t)c * kC32BBytes), 96u * 16u);   // LBO = next 8 input channels
+                    for (int t = 0; t < ntile; ++t) {
+                        if (c == 0) {   // the epilogue has drained this tile's accumulator of the previous group
+                            mbar_wait(&acc_empty[t], ((tile_phase >> t) & 1u) ^ 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t d_addr = tmem_base + (uint32_t)(t * 96);
+                        const uint32_t a_t = a_base + (uint32_t)(t * 126) * 4u;    // 64 B per position
+#pragma unroll
+                        for (int dr = 0; dr < 3; ++dr) {
+                            const uint32_t a_lo = a_t + (uint32_t)dr * pw4;
+                            const uint32_t b_lo = b_base + (uint32_t)dr * 384u;     // 4 k-groups x 96 rows x 16 B
+                            umma_bf16_lohi(d_addr, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)((c | dr) != 0));
+                            umma_bf16_lohi(d_addr, a_lo + 2u, a_hi, b_lo + 192u, b_hi, idesc, 1u);   // channels 16..31: +32 B / +2 k-groups
+                        }
+                        if (c == p.nch - 1) {
+                            umma_commit(&acc_full[t]);
+                            tile_phase ^= 1u << t;
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue
+        const int lq = warp & 3, half = warp >> 2;
+        const int m = lq * 32 + lane;
+        const bool want_stats = p.stat_part != nullptr;
+        float ssum[16], ssq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        int par = 0;
+        uint32_t tile_phase = 0;
+        for (int g = blockIdx.x; g < p.groups_total; g += gridDim.x) {
+            const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
+            const int rows = min(p.ry, p.H - y0);
+            const int ntile = (rows * p.PW + 125) / 126;
+            for (int t = 0; t < ntile; ++t, par ^= 1) {
+                mbar_wait(&acc_full[t], (tile_phase >> t) & 1u);
+                tile_phase ^= 1u << t;
+                tc_fence_after();
+                uint32_t z0[16], z1[16], z2[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * 96 + half * 16);
+                tmem_ld16(taddr, z0);
+                tmem_ld16(taddr + 32u, z1);
+                tmem_ld16(taddr + 64u, z2);
+                tmem_ld_wait();
+                float* ex = s_ex + (size_t)par * (4 * 2 * 2 * 16);
+                if (lane == 31) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ex[((lq * 2 + half) * 2 + 0) * 16 + i] = __uint_as_float(z0[i]);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ex[((lq * 2 + half) * 2 + 1) * 16 + i] = __uint_as_float(z2[i]);
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                // this lane's output position inside the group (index u holds pixel u % PW - 1 of row u / PW)
+                const int u = t * 126 + m;
+                const int row = u / p.PW, px = u - row * p.PW - 1;
+                const bool valid = (m >= 1) && (m <= 126) && (row < rows) && (px >= 0) && (px < p.W);
+                float y[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float l = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[i]), 1);
+                    float r = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[i]), 1);
+                    if (lane == 0 && lq > 0) l = ex[(((lq - 1) * 2 + half) * 2 + 0) * 16 + i];
+                    if (lane == 31 && lq < 3) r = ex[(((lq + 1) * 2 + half) * 2 + 1) * 16 + i];
+                    y[i] = l + __uint_as_float(z1[i]) + r;
+                }
+                if (valid) {
+                    __nv_bfloat16* dst = p.out + (((size_t)n * p.H + (y0 + row)) * p.W + px) * 32 + half * 16;
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(y[0], y[1]); o0.y = pack_bf16x2(y[2], y[3]); o0.z = pack_bf16x2(y[4], y[5]); o0.w = pack_bf16x2(y[6], y[7]);
+                    o1.x = pack_bf16x2(y[8], y[9]); o1.y = pack_bf16x2(y[10], y[11]); o1.z = pack_bf16x2(y[12], y[13]); o1.w = pack_bf16x2(y[14], y[15]);
+                    reinterpret_cast<uint4*>(dst)[0] = o0;
+                    reinterpret_cast<uint4*>(dst)[1] = o1;
+                    if (want_stats) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { ssum[i] += y[i]; ssq[i] = fmaf(y[i], y[i], ssq[i]); }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[t]);
+            }
+        }
+        if (want_stats) {
+            // warp butterfly (fixed order), then the four quadrant warps of a channel half are summed in a fixed order
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], off);
+                    ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], off);
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { s_red[(warp * 2 + 0) * 16 + i] = ssum[i]; s_red[(warp * 2 + 1) * 16 + i] = ssq[i]; }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (threadIdx.x < 64) {
+                const int which = threadIdx.x >> 5, c = threadIdx.x & 31, h = c >> 4, i = c & 15;
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a += s_red[((h * 4 + q) * 2 + which) * 16 + i];
+                p.stat_part[((size_t)blockIdx.x * 2 + which) * 32 + c] = a;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace nunet
+
+using namespace nunet;
+
+struct C32Tiling {
+    int PW, ry, gpi, box_rows, S, a_stage_bytes, smem_bytes;
+};
+
+static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
+    const int PW = (W + 2 + 1) & ~1;
+    if (PW > 256) return false;
+    const int budget = 226 * 1024;
+    double best = 1e30;
+    for (int ry = 1; ry <= H && ry <= 64; ++ry) {
+        const int ntile = (ry * PW + 125) / 126;
+        if (ntile > 5) break;
+        // rows read: tap rows 0..2 above/below + the overhang of the last tile
+        const int box_rows = (2 * PW + 126 * (ntile - 1) + 128 + PW - 1) / PW;
+        if (box_rows > 256) break;
+        const int a = ((box_rows * PW * 64) + 1023) & ~1023;
+        const int fixed = nch * (int)kC32BBytes + 2048 + 1024 + 256;
+        int S = 4;
+        while (S >= 2 && S * a + fixed > budget) --S;
+        if (S < 2) continue;
+        const int gpi = (H + ry - 1) / ry;
+        const int last_rows = H - (gpi - 1) * ry;
+        const double tiles = (double)(gpi - 1) * ntile + (last_rows * PW + 125) / 126;
+        double cost = tiles + 0.15 * gpi;           // + the per-group epilogue hand-off (single-buffered accumulators)
+        if (S == 2) cost *= 1.08;
+        if (cost < best) {
+            best = cost;
+            t->PW = PW; t->ry = ry; t->gpi = gpi; t->box_rows = box_rows; t->S = S; t->a_stage_bytes = a;
+            t->smem_bytes = S * a + fixed;
+        }
+    }
+    return best < 1e30;
+}
+
+// 1 if nunet_conv3x3_fwd will route this conv (all sources NUNET_SRC_ACT) to the stacked kernel, i.e. expects weights packed
+// with NUNET_PACK_FWD_C32 / NUNET_PACK_DGRAD_C32.
+extern "C" int nunet_conv3x3_c32_eligible(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout) {
+    static const bool off = getenv("NUNET_NO_C32") != nullptr;
+    C32Tiling t;
+    // Cin = 32 (one chunk) measured slower than the generic kernel (0.128 vs 0.104 ms at 96x96, batch 256: the per-tile epilogue
+    // is not hidden behind six MMAs), Cin >= 96 faster (0.199 vs 0.254, 0.323 vs 0.479 ms): tools/dbg_c32.py
+    if (off || Cout != 32 || cin_total < 64 || cin_total % 32 != 0 || N < 1 || H < 1 || W < 1) return 0;
+    return c32_tiling(H, W, cin_total / 32, &t) ? 1 : 0;
+}
+
+int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStream_t stream) {
+    C32Tiling t;
+    if (!c32_tiling(d->H, d->W, cin / 32, &t)) return NUNET_E_UNSUPPORTED;
+    C32Params p{};
+    p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
+    p.box_rows = t.box_rows; p.S = t.S; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
+    p.wpack = d->wpack; p.out = (__nv_bfloat16*)d->out; p.stat_part = d->stat_part;
+    for (int i = 0; i < d->num_src; ++i) {
+        p.srcC[i] = d->src[i].C;
+        if (encode_nhwc_map(&p.xmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, t.PW, 64, t.box_rows, 1) != 0) return NUNET_E_UNSUPPORTED;
+    }
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem_bytes);
+    if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+    conv3x3_c32_kernel<<<grid, kC32Threads, t.smem_bytes, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
+}

@@ -445,6 +445,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
 // wpack[n_tile][chunk][tap][kg][NT][8]  (bf16);  FWD: n = co, k = ci ; DGRAD: n = ci, k = co, taps flipped.
 __device__ __forceinline__ void pack_group(const float* __restrict__ w, int Cout, int Cin, int mode, int NT, int CK, int nchunks,
                                            __nv_bfloat16* __restrict__ out, size_t g) {
+    if (mode >= NUNET_PACK_FWD_C32) {   // stacked layout of conv_c32.cu: [chunk][dr][kg 4][dc*32 + n][8], NT = 32, CK = 32
+        size_t r = g;
+        const int n96 = (int)(r % 96); r /= 96;
+        const int kg = (int)(r % 4); r /= 4;
+        const int dr = (int)(r % 3); r /= 3;
+        const int chunk = (int)r;
+        const int dc = n96 >> 5, n = n96 & 31, tap = dr * 3 + dc;
+        const int k0 = chunk * 32 + kg * 8;
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            float f = 0.f;
+            if (mode == NUNET_PACK_FWD_C32) {
+                if (n < Cout && k < Cin) f = w[((size_t)n * Cin + k) * 9 + tap];
+            } else {
+                if (n < Cin && k < Cout) f = w[((size_t)k * Cin + n) * 9 + (8 - tap)];
+            }
+            v[e] = __float2bfloat16_rn(f);
+        }
+        *reinterpret_cast<uint4*>(out + g * 8) = *reinterpret_cast<const uint4*>(v);
+        return;
+    }
     const int cgs = CK >> 3;
     size_t r = g;
     const int nl = (int)(r % NT); r /= NT;
@@ -584,6 +607,8 @@ static int launch_conv(const ConvParams& p, const nunet_conv_plan_t& pl, cudaStr
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
 }
 
+int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStream_t stream);
+
 extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->wpack || !d->out) return NUNET_E_BADARG;
     int cin = 0;
@@ -619,6 +644,7 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     int kinds[NUNET_MAX_SRC];
     for (int i = 0; i < d->num_src; ++i) kinds[i] = d->src[i].kind;
     const int mode = sources_mode(kinds, d->num_src);
+    if (d->wpack_layout != 0 && (d->wpack_layout != 1 || mode != MODE_ACT)) return NUNET_E_BADARG;
     switch (mode) {
         case MODE_INPUT: return launch_conv<MODE_INPUT>(p, pl, (cudaStream_t)stream);
         case MODE_SAME: return launch_conv<MODE_SAME>(p, pl, (cudaStream_t)stream);
@@ -626,6 +652,10 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
         case MODE_SAME_UP: return launch_conv<MODE_SAME_UP>(p, pl, (cudaStream_t)stream);
         case MODE_GRAD: return launch_conv<MODE_GRAD>(p, pl, (cudaStream_t)stream);
         case MODE_ACT: {
+            if (d->wpack_layout == 1) {
+                if (!nunet_conv3x3_c32_eligible(d->N, d->H, d->W, cin, d->Cout)) return NUNET_E_BADARG;
+                return nunet_conv_c32_launch(d, cin, pl.grid_m, (cudaStream_t)stream);
+            }
             // tensor-load path: box = (32 ch, W+2 px, 1, 1) per padded row, needs W+2 <= 256 and the CK=32 tiling
             static const bool no_tma = getenv("NUNET_NO_TMA") != nullptr;
             if (!no_tma && pl.CK == 32 && d->W + 2 <= 256 && pl.tma_smem_bytes > 0) {
@@ -661,7 +691,8 @@ extern "C" int nunet_debug_read_wait_prof(unsigned long long* out16, int reset) 
 
 extern "C" int nunet_pack_weights(const float* w, int32_t Cout, int32_t Cin, int32_t mode, const nunet_conv_plan_t* pl,
                                   void* wpack, void* stream) {
-    if (!w || !pl || !wpack || (mode != NUNET_PACK_FWD && mode != NUNET_PACK_DGRAD)) return NUNET_E_BADARG;
+    if (!w || !pl || !wpack || mode < NUNET_PACK_FWD || mode > NUNET_PACK_DGRAD_C32) return NUNET_E_BADARG;
+    if (mode >= NUNET_PACK_FWD_C32 && (pl->NT != 32 || pl->CK != 32 || pl->n_tiles != 1)) return NUNET_E_BADARG;
     const size_t groups = (size_t)pl->wpack_elems / 8;
     int blocks = (int)((groups + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -679,7 +710,7 @@ extern "C" int nunet_pack_weights_batched(const nunet_pack_job_t* jobs, int32_t 
         int blocks = 0;
         for (int j = 0; j < nj; ++j) {
             const nunet_pack_job_t& jb = jobs[j0 + j];
-            if (!jb.w || !jb.out || (jb.mode != NUNET_PACK_FWD && jb.mode != NUNET_PACK_DGRAD) || jb.NT < 1 || jb.CK < 8 || jb.nchunks < 1 || jb.n_tiles < 1)
+            if (!jb.w || !jb.out || jb.mode < NUNET_PACK_FWD || jb.mode > NUNET_PACK_DGRAD_C32 || jb.NT < 1 || jb.CK < 8 || jb.nchunks < 1 || jb.n_tiles < 1)
                 return NUNET_E_BADARG;
             b.jobs[j] = jb;
             b.start[j] = blocks;

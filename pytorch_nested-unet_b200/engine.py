@@ -152,6 +152,14 @@ def _tma_width(w):
     return w + 2 <= 256
 
 
+def _stacked(s, N, h, w, cin_pad):
+    """True if this layer's forward conv runs on the stacked Cout = 32 kernel (conv_c32.cu): all its sources are materialised
+    activations at this resolution (always the case where the TMA width limit holds) and the shape is eligible."""
+    if s.cout != 32 or not _tma_width(w) or not (MATERIALIZE_NODE_OUTPUTS and MATERIALIZE_UPSAMPLED and MATERIALIZE_ALL and MATERIALIZE_POOLED):
+        return False
+    return ops.c32_eligible(N, h, w, cin_pad, s.cout)
+
+
 def _cin_pad(s, packed_input):
     return 32 if (packed_input and s.sources[0][1] == L.SRC_INPUT) else s.cin_pad
 
@@ -203,7 +211,8 @@ class _State(object):
         items, keys = [], []
         for s in self.specs:
             h, w = H >> s.level, W >> s.level
-            modes = [(L.PACK_FWD, ops.conv_plan(N, h, w, _cin_pad(s, packed_input), s.cout))]
+            cinp = _cin_pad(s, packed_input)
+            modes = [(L.PACK_FWD_C32 if _stacked(s, N, h, w, cinp) else L.PACK_FWD, ops.conv_plan(N, h, w, cinp, s.cout))]
             if want_dgrad and s.sources[0][0] >= 0:
                 modes.append((L.PACK_DGRAD, ops.conv_plan(N, h, w, s.cout, s.cin_pad)))
             wt = s.conv.weight
@@ -266,9 +275,11 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
     """One conv + BatchNorm (+ the materialised operands its consumers read) on the current stream."""
     h, w = H >> s.level, W >> s.level
     srcs = _sources(s, recs, x, x32)
-    plan = ops.conv_plan(N, h, w, _cin_pad(s, x32 is not None), s.cout)
-    wp = st.pack(s, plan, L.PACK_FWD)
-    y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train)
+    cinp = _cin_pad(s, x32 is not None)
+    plan = ops.conv_plan(N, h, w, cinp, s.cout)
+    stacked = _stacked(s, N, h, w, cinp) and all(sr.kind == L.SRC_ACT for sr in srcs)
+    wp = st.pack(s, plan, L.PACK_FWD_C32 if stacked else L.PACK_FWD)
+    y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train, stacked=stacked)
     r = _Record()
     r.y, r.h, r.w, r.a, r.a_up, r.a_pool = y, h, w, None, None, None
     r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)

@@ -79,6 +79,12 @@ def require_cuda(t, what):
 
 
 @functools.lru_cache(maxsize=None)
+def c32_eligible(N, H, W, cin_total, Cout):
+    """True if a conv of this shape over pre-activated sources runs on the stacked Cout = 32 kernel (needs *_C32 weight packs)."""
+    return bool(L.lib().nunet_conv3x3_c32_eligible(N, H, W, cin_total, Cout))
+
+
+@functools.lru_cache(maxsize=None)
 def conv_plan(N, H, W, cin_total, Cout):
     pl = L.ConvPlan()
     L.check(L.lib().nunet_conv3x3_plan(N, H, W, cin_total, Cout, C.byref(pl)), "nunet_conv3x3_plan(%s)" % ((N, H, W, cin_total, Cout),))
@@ -121,7 +127,7 @@ def pack_weights_batched(items):
     _call("pack", (len(items) + 63) // 64, None, "nunet_pack_weights_batched", L.lib().nunet_pack_weights_batched, C.cast(jobs, C.c_void_p), len(items), _stream())
 
 
-def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False, cls=None):
+def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False, cls=None, stacked=False):
     """Launches the fused implicit-GEMM conv. Returns (out bf16 [N,H,W,Cout], stat_part [grid_m,2,Cout] or None)."""
     cin = sum(s.cpad for s in sources)
     plan = conv_plan(N, H, W, cin, Cout)
@@ -141,6 +147,7 @@ def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=
         d.src[i].C = s.C
         d.src[i].kind = s.kind
     d.wpack = wpack.data_ptr()
+    d.wpack_layout = 1 if stacked else 0
     d.out = out.data_ptr()
     d.stat_part = stat_part.data_ptr() if stat_part is not None else None
     if cls is None:

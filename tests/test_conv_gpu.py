@@ -157,3 +157,54 @@ def test_upsample2x_matches_torch():
         ref = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
         torch.cuda.synchronize()
         assert bool(((up.float() - ref).abs() <= 0.008 * ref.abs() + 1e-6).all())
+
+
+C32_CASES = [(2, 16, 16, [64]), (2, 32, 32, [32, 64]), (3, 48, 80, [32, 32, 64]), (4, 96, 96, [32] * 4 + [64]), (2, 6, 6, [64]), (5, 96, 96, [32, 32]),
+             (1, 16, 240, [32, 32, 32])]
+
+
+@pytest.mark.parametrize("case", C32_CASES, ids=lambda c: "N%d_%dx%d_cin%d" % (c[0], c[1], c[2], sum(c[3])))
+@pytest.mark.parametrize("mode", ["fwd", "dgrad"])
+def test_stacked_cout32_kernel_matches_torch_and_the_generic_kernel(case, mode):
+    """conv_c32.cu (kernel columns stacked into N = 96, column shift applied to the accumulators) against torch on identical
+    bf16 operands and against the generic implicit-GEMM kernel: outputs equal up to the bf16 rounding of slightly different fp32
+    accumulation orders, BatchNorm partial sums to 2e-5 of the sum of magnitudes."""
+    import torch.nn.functional as F
+    import _lib as L
+    import ops
+    dev = "cuda:0"
+    N, H, W, Cs = case
+    gen = torch.Generator(device=dev).manual_seed(7)
+    cin = sum(Cs)
+    srcs, xs = [], []
+    for c in Cs:
+        a = (torch.rand(N, H, W, c, generator=gen, device=dev) - 0.3).to(torch.bfloat16)
+        srcs.append(ops.Source(L.SRC_ACT, a, c))
+        xs.append(a.float().permute(0, 3, 1, 2))
+    assert ops.c32_eligible(N, H, W, cin, 32)
+    plan = ops.conv_plan(N, H, W, cin, 32)
+    if mode == "fwd":
+        w = torch.randn(32, cin, 3, 3, generator=gen, device=dev) * 0.1
+        wp, wp0 = ops.pack_weights(w, L.PACK_FWD_C32, plan), ops.pack_weights(w, L.PACK_FWD, plan)
+        ref = F.conv2d(torch.cat(xs, 1), w.to(torch.bfloat16).float(), padding=1)
+    else:
+        w = torch.randn(cin, 32, 3, 3, generator=gen, device=dev) * 0.1
+        wp, wp0 = ops.pack_weights(w, L.PACK_DGRAD_C32, plan), ops.pack_weights(w, L.PACK_DGRAD, plan)
+        ref = F.conv_transpose2d(torch.cat(xs, 1), w.to(torch.bfloat16).float(), padding=1)
+    y, part = ops.conv3x3(N, H, W, srcs, 32, wp, want_stats=True, stacked=True)
+    y0, _ = ops.conv3x3(N, H, W, srcs, 32, wp0, want_stats=True)
+    y_plain, none = ops.conv3x3(N, H, W, srcs, 32, wp, want_stats=False, stacked=True)
+    torch.cuda.synchronize()
+    refn = ref.permute(0, 2, 3, 1)
+    tol = 0.006 * float(refn.abs().max()) + 1e-3          # half a bf16 ulp of the largest output + accumulation-order noise
+    assert float((y.float() - refn).abs().max()) <= tol
+    assert float((y.float() - y0.float()).abs().max()) <= tol
+    assert torch.equal(y, y_plain) and none is None
+    flat = refn.reshape(-1, 32).double()
+    s_ref, q_ref = flat.sum(0), (flat ** 2).sum(0)
+    s, q = part[:, 0].double().sum(0), part[:, 1].double().sum(0)
+    # fp32 partial sums: the error scales with the sum of magnitudes (the per-channel sums themselves may cancel to ~0);
+    # the bf16-rounded outputs are what the reference sums, the kernel sums its fp32 accumulators (BatchNorm statistics)
+    l1 = flat.abs().sum(0)
+    assert float(((s - s_ref).abs() / l1).max()) <= 2e-5
+    assert float(((q - q_ref).abs() / (q_ref.abs() + 1.0)).max()) <= 1e-4
