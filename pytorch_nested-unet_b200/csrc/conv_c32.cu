@@ -15,7 +15,8 @@
 // overlap by two (tile t = positions [126t, 126t+128) of the group; its lanes 1..126 produce outputs), so every output finds
 // both neighbours inside its tile.  The A stage of a 32-channel chunk is ONE tensor load: (32 ch, PW px, ry+3 rows), 64B
 // swizzle = the K-major SWIZZLE_64B operand with 64-byte rows; tap row dr and tile t are start-address offsets.
-// Weights: [chunk][dr][k-group][dc*32+co][8] (NUNET_PACK_*_C32), all chunks fetched once per CTA and kept resident (<= 110 KB).
+// Weights: [chunk][dr][k-group][dc*32+co][8] (NUNET_PACK_*_C32): all chunks fetched once per CTA and kept resident when three
+// activation stages still fit beside them, else one 18 KB chunk travels with every stage.
 // Warps: 0-7 epilogue (TMEM quadrant x channel half), 8 MMA issuer + TMEM owner, 9 TMA / weight fetcher.  TMEM holds the up
 // to five tiles of a group (480 columns) with one full/empty barrier pair PER TILE: the issuer starts tile t of the next group as
 // soon as the epilogue has drained tile t of the current one, so the epilogue overlaps the following group's MMAs.
@@ -33,6 +34,7 @@ struct C32Params {
     int N, H, W, PW;
     int ry, gpi, groups_total;   // rows per group, groups per image
     int box_rows, S, nch, num_src;
+    int res_b;                   // 1: all weight chunks resident; 0: one chunk per pipeline stage (keeps >= 3 activation stages in flight)
     int srcC[NUNET_MAX_SRC];
     int a_stage_bytes;
     const void* wpack;
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)p.S * p.a_stage_bytes;                         // [nch] resident weight chunks
-    float* s_ex = reinterpret_cast<float*>(sB + (size_t)p.nch * kC32BBytes);   // [2 parity][4 lq][2 half][2 side][16]
+    float* s_ex = reinterpret_cast<float*>(sB + (size_t)(p.res_b ? p.nch : p.S) * kC32BBytes);   // [2 parity][4 lq][2 half][2 side][16]
     float* s_red = s_ex + 2 * 4 * 2 * 2 * 16;                                  // [8 warps][2][16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8 * 2 * 16);
     uint64_t* full = bars;
@@ -88,9 +90,13 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
         if (lane == 0) {
             for (int si = 0; si < p.num_src; ++si) tma_prefetch_desc(&p.xmap[si]);
             const uint32_t a_box_bytes = (uint32_t)p.box_rows * (uint32_t)p.PW * 64u;
-            mbar_arrive_expect_tx(b_full, (uint32_t)p.nch * kC32BBytes);
-            for (int c = 0; c < p.nch; ++c)
-                bulk_g2s(sB + (size_t)c * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, b_full);
+            if (p.res_b) {
+                mbar_arrive_expect_tx(b_full, (uint32_t)p.nch * kC32BBytes);
+                for (int c = 0; c < p.nch; ++c)
+                    bulk_g2s(sB + (size_t)c * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, b_full);
+            } else {
+                mbar_arrive(b_full);
+            }
             int cc = 0;
             for (int g = blockIdx.x; g < p.groups_total; g += gridDim.x) {
                 const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
@@ -101,8 +107,9 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                     const int cglob = c * 32;
                     while (cglob >= c0 + p.srcC[si]) { c0 += p.srcC[si]; ++si; }
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], a_box_bytes);
+                    mbar_arrive_expect_tx(&full[s], a_box_bytes + (p.res_b ? 0u : kC32BBytes));
                     tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, -1, y0 - 1, n, &full[s]);
+                    if (!p.res_b) bulk_g2s(sB + (size_t)s * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, &full[s]);
                 }
             }
         }
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_base = ((smem_u32(sA + (size_t)s * p.a_stage_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-                    const uint32_t b_base = umma_desc_lo(smem_u32(sB + (size_t)c * kC32BBytes), 96u * 16u);   // LBO = next 8 input channels
+                    const uint32_t b_base = umma_desc_lo(smem_u32(sB + (size_t)(p.res_b ? c : s) * kC32BBytes), 96u * 16u);   // LBO = next 8 input channels
                     for (int t = 0; t < ntile; ++t) {
                         if (c == 0) {   // the epilogue has drained this tile's accumulator of the previous group
                             mbar_wait(&acc_empty[t], ((tile_phase >> t) & 1u) ^ 1u);
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
 using namespace nunet;
 
 struct C32Tiling {
-    int PW, ry, gpi, box_rows, S, a_stage_bytes, smem_bytes;
+    int PW, ry, gpi, box_rows, S, res_b, a_stage_bytes, smem_bytes;
 };
 
 static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
@@ -266,10 +273,17 @@ static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
         const int box_rows = (2 * PW + 126 * (ntile - 1) + 128 + PW - 1) / PW;
         if (box_rows > 256) break;
         const int a = ((box_rows * PW * 64) + 1023) & ~1023;
-        const int fixed = nch * (int)kC32BBytes + 2048 + 1024 + 256;
-        int S = 4;
-        while (S >= 2 && S * a + fixed > budget) --S;
-        if (S < 2) continue;
+        // weights resident if that still leaves three activation stages in flight (the 56 KB tensor loads need ~2 stages of
+        // latency cover), otherwise one weight chunk travels with every stage
+        const int misc = 2048 + 1024 + 256;
+        int res_b = 1, S = 4;
+        while (S >= 3 && S * a + nch * (int)kC32BBytes + misc > budget) --S;
+        if (S < 3) {
+            res_b = 0; S = 4;
+            while (S >= 2 && S * (a + (int)kC32BBytes) + misc > budget) --S;
+            if (S < 2) continue;
+        }
+        const int fixed = (res_b ? nch : S) * (int)kC32BBytes + misc;
         const int gpi = (H + ry - 1) / ry;
         const int last_rows = H - (gpi - 1) * ry;
         const double tiles = (double)(gpi - 1) * ntile + (last_rows * PW + 125) / 126;
@@ -277,7 +291,7 @@ static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
         if (S == 2) cost *= 1.08;
         if (cost < best) {
             best = cost;
-            t->PW = PW; t->ry = ry; t->gpi = gpi; t->box_rows = box_rows; t->S = S; t->a_stage_bytes = a;
+            t->PW = PW; t->ry = ry; t->gpi = gpi; t->box_rows = box_rows; t->S = S; t->res_b = res_b; t->a_stage_bytes = a;
             t->smem_bytes = S * a + fixed;
         }
     }
@@ -300,7 +314,7 @@ int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStr
     if (!c32_tiling(d->H, d->W, cin / 32, &t)) return NUNET_E_UNSUPPORTED;
     C32Params p{};
     p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
-    p.box_rows = t.box_rows; p.S = t.S; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
+    p.box_rows = t.box_rows; p.S = t.S; p.res_b = t.res_b; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
     p.wpack = d->wpack; p.out = (__nv_bfloat16*)d->out; p.stat_part = d->stat_part;
     for (int i = 0; i < d->num_src; ++i) {
         p.srcC[i] = d->src[i].C;

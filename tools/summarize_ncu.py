@@ -32,14 +32,14 @@ for r in rows:
         d[m] = v * scale
 L = list(launches.values())
 starts = [k for k, d in enumerate(L) if "input_to_nhwc32" in d["name"]]
-if len(starts) < 4:
-    raise SystemExit("need at least 4 steps in the capture, found %d" % len(starts))
-a, b = starts[2], starts[3]          # third step of the run (after two warm-up steps)
+if len(starts) < 3:
+    raise SystemExit("need at least 3 steps in the capture, found %d" % len(starts))
+a, b = starts[-2], starts[-1]        # the last complete step of the run (steady state: after the warm-up steps)
 step = L[a - 1:b - 1]                 # the batched weight-pack launch precedes the input repack
 
 
 def cls(name):
-    for key, c in (("conv3x3_wgrad", "conv_wgrad"), ("wgrad_reduce", "conv_wgrad"), ("conv3x3_igemm", "conv_fwd+dgrad"), ("grad_router", "router"),
+    for key, c in (("conv3x3_wgrad", "conv_wgrad"), ("wgrad_reduce", "conv_wgrad"), ("conv3x3_igemm", "conv_fwd+dgrad"), ("conv3x3_c32", "conv_fwd+dgrad"), ("grad_router", "router"),
                    ("up_transpose", "up_transpose"), ("upsample2x", "upsample2x"), ("bn_bwd_apply", "bn_bwd_apply"), ("bn_apply", "bn_apply"),
                    ("bn_", "bn_small"), ("head_", "head"), ("loss_", "loss"), ("iou_", "loss"), ("pack_weights", "pack"), ("input_to", "input_pack"),
                    ("maxpool", "maxpool"), ("nccl", "nccl")):
@@ -71,5 +71,5 @@ conv = sum(g["dram_read"] + g["dram_write"] for c, g in agg.items() if c.startsw
 json.dump({"batch": 256, "size": 96, "steps_in_window": 1.0, "conv_dram_bytes_per_step": conv, "all_dram_bytes_per_step": tot_b,
            "kernel_time_us_per_step_serialized": tot_us, "launches_per_step": len(step),
            "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over bench.py --steps 1 --warmup 2; "
-                     "third step of the run (tools/summarize_ncu.py)"}, open(prefix + "_traffic.json", "w"), indent=1)
+                     "last complete step of the run (tools/summarize_ncu.py)"}, open(prefix + "_traffic.json", "w"), indent=1)
 print(open(prefix + "_ncu_launch_shares.csv").read())
