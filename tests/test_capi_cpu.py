@@ -74,3 +74,27 @@ def test_bad_arguments_are_refused_without_cuda():
     assert lib.nunet_conv3x3_fwd(C.byref(d), None) == 1
     assert lib.nunet_head_fwd(None, None, None, None, None, 1, 8, 8, 1, None, None) == 1
     assert lib.nunet_loss_iou_fwd(None, None, 1, 1, None, None, None, None, None, None) == 1
+
+
+@pytest.mark.parametrize("size,N", [(96, 256), (96, 16), (256, 64), (512, 8), (32, 2)])
+def test_tma_weight_gradient_and_stacked_conv_tilings(size, N):
+    """Host-only tiling decisions of the TMA-fed kernels: every eligible layer shape gets a tiling that fits shared memory,
+    covers all chunks, uses the kernel-row stacking only for Cin = 32, and rows wider than 254 pixels are left to the cp.async
+    kernels; the stacked Cout = 32 conv kernel is offered exactly for 32 output / >= 64 input channels."""
+    import _lib as L
+    lib = L.lib()
+    for (n, h, w, cin, cout) in _layers(size, N):
+        pw = L.WgradPlan()
+        assert lib.nunet_conv3x3_wgrad_plan(n, h, w, cin, cout, C.byref(pw)) == 0
+        want_tma = cin % 32 == 0 and w + 2 <= 256
+        assert bool(pw.tma) == want_tma, (n, h, w, cin, cout)
+        if pw.tma:
+            assert pw.tma_smem_bytes <= 227 * 1024 and 1 <= pw.tma_S <= 4
+            assert pw.tma_PW >= w + 2 and pw.tma_PW % 2 == 0
+            assert pw.tma_splits * pw.tma_cpc >= pw.tma_chunks and (pw.tma_splits - 1) * pw.tma_cpc < pw.tma_chunks
+            assert pw.tma_G == (1 if cin == 32 else 3) and pw.tma_Nt == 32
+            assert pw.part_elems >= pw.tma_splits * 9 * cin * cout
+            m_tiles = (cin + 127) // 128
+            assert pw.tma_splits * m_tiles * (cout // 32) <= 148 or pw.tma_splits == 1     # one wave of CTAs
+        want_c32 = cout == 32 and cin >= 64 and cin % 32 == 0 and w + 2 <= 256
+        assert bool(lib.nunet_conv3x3_c32_eligible(n, h, w, cin, cout)) == want_c32, (n, h, w, cin, cout)
