@@ -216,7 +216,9 @@ def run_native(args):
         torch.cuda.synchronize()
 
     model.train()
-    for _ in range(args.warmup):
+    # at least three untimed steps: the first runs eagerly, the second captures the CUDA graphs of the step, the third replays
+    warm_run = max(args.warmup, 3)
+    for _ in range(warm_run):
         step(x_dev, t_dev)
     barrier()
     sampler = ClockSampler(local)
@@ -322,7 +324,7 @@ def run_native(args):
                "sample": "oracle port of the reference train step, %s ds=%s batch 16 @%dx%d fp32, median of 3 steps (%.2f s/step)" % (args.arch, ds, S, S, med)}
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_run": warm_run,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": "%s(num_classes=1, input_channels=3, deep_supervision=%s) %dx%d, batch %d per GPU, full train step "
