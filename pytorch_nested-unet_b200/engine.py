@@ -9,6 +9,7 @@ working on the fp32 master parameters) runs, per conv in reverse order: gradient
 split-K wgrad, dgrad — all CUDA kernels behind the C ABI; nothing here calls an ATen compute op on activations.
 """
 import os as _os
+import weakref as _weakref
 
 import torch
 
@@ -511,11 +512,12 @@ GRAPH_TRAIN_DP = _os.environ.get("NUNET_GRAPH_TRAIN_DP", "0") == "1"
 
 class _TrainGraph(object):
     __slots__ = ("seen", "pool", "x", "fwd", "outs", "recs", "xs", "head_layers", "launches_f", "bwd", "gl", "flat", "views", "launches_b",
-                 "packs", "failed", "gen", "bwd_gen")
+                 "packs", "failed", "gen", "bwd_gen", "live")
 
     def __init__(self):
         self.seen, self.fwd, self.bwd, self.failed, self.packs = 0, None, None, False, {}
         self.gen = self.bwd_gen = 0   # forward replays / the last one whose backward ran
+        self.live = None              # weak reference to the autograd node of the last captured forward
 
 
 def _train_graph(model, x, params):
@@ -542,7 +544,10 @@ def _train_graph(model, x, params):
     if tg.seen <= 1 or tg.failed:
         return None
     if tg.gen != tg.bwd_gen:      # the previous captured forward still waits for its backward: its activations must survive
-        return None
+        if tg.live is not None and tg.live() is None:
+            tg.bwd_gen = tg.gen   # ... unless its outputs were dropped without a backward (the autograd node is gone)
+        else:
+            return None
     return tg
 
 
@@ -596,6 +601,10 @@ class _NetFunction(torch.autograd.Function):
         ops.add_launches(tg.launches_f)
         tg.gen += 1
         ctx.gen = tg.gen
+        try:
+            tg.live = _weakref.ref(ctx)
+        except TypeError:
+            tg.live = None
         ctx.head_layers = tg.head_layers
         return tuple(t.clone() for t in tg.outs)
 

@@ -233,3 +233,48 @@ def test_fp32_check_mode_matches_reference_logits_to_1e_4(name):
             assert _relmax(o.cpu(), r) <= 1e-4, _relmax(o.cpu(), r)
     finally:
         engine.CHECK_FP32 = saved
+
+
+def test_captured_step_survives_forwards_without_backward():
+    """A captured forward whose outputs are dropped without a backward must not disable the captured path, and a second forward
+    issued BEFORE the first one's backward must leave the first one's activations intact (it runs eagerly)."""
+    import gc
+    import archs
+    import engine
+    import losses
+    if not engine.GRAPH_TRAIN:
+        pytest.skip("training-step graphs disabled")
+    torch.manual_seed(0)
+    model = archs.NestedUNet(1, 3, False).to(DEV).train()
+    crit = losses.BCEDiceLoss()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(2, 3, 32, 32, generator=g, device=DEV)
+    x2 = torch.randn(2, 3, 32, 32, generator=g, device=DEV)
+    t = (torch.rand(2, 1, 32, 32, generator=g, device=DEV) > 0.5).float()
+
+    def grads_of(out):
+        model.zero_grad()
+        crit(out, t).backward()
+        return [p.grad.detach().clone() for p in model.parameters()]
+
+    for _ in range(2):                       # eager step, then the capturing step
+        grads_of(model(x))
+    tg = next(iter(engine._state(model).__dict__["train_graphs"].values()))
+    assert tg.fwd is not None and tg.bwd is not None
+    ref = grads_of(model(x))                 # captured forward + backward
+    gen0 = tg.gen
+    out = model(x)                           # captured forward, outputs dropped without backward
+    assert tg.gen == gen0 + 1
+    del out
+    gc.collect()
+    got = grads_of(model(x))                 # must be captured again (the dropped node is gone) and give the same gradients
+    assert tg.gen == gen0 + 2
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    o1 = model(x)                            # captured
+    o2 = model(x2)                           # issued before o1's backward: eager, must not overwrite o1's activations
+    assert tg.gen == gen0 + 3
+    g1 = grads_of(o1)
+    for a, b in zip(g1, ref):
+        assert torch.equal(a, b)
+    del o2
