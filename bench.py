@@ -146,7 +146,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-        "data": "synthetic", "config": {"workload": "NestedUNet-DS 96x96 train step (BASELINE config 2 shape), CPU sample batch %d" % n},
+        "data": "synthetic",
+        "config": {"workload": "%s(num_classes=1, input_channels=3, deep_supervision=%s) %dx%d, batch %d per GPU, full train step "
+                               "(fwd + BCEDice + IoU + bwd + SGD)" % (args.arch, ds, args.size, args.size, args.batch),
+                   "global_batch": args.batch * args.gpus, "parallelism": "cpu (reference step on the host cores)",
+                   "sample": "each step is a batch-%d sample of the workload (a batch-%d CPU step takes ~10 s)" % (n, args.batch)},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
