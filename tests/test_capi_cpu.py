@@ -94,6 +94,12 @@ def test_tma_weight_gradient_and_stacked_conv_tilings(size, N):
             assert pw.tma_splits * pw.tma_cpc >= pw.tma_chunks and (pw.tma_splits - 1) * pw.tma_cpc < pw.tma_chunks
             assert pw.tma_G == (1 if cin == 32 else 3) and pw.tma_Nt == 32
             assert pw.part_elems >= pw.tma_splits * 9 * cin * cout
+            # chunk enumeration covers every padded row exactly once: ry rows of one image, or kimg whole images
+            if pw.tma_r > 0:
+                assert pw.tma_chunks == n * ((h + 1 + pw.tma_r - 1) // pw.tma_r)
+                assert -(-(pw.tma_r * pw.tma_PW) // 16) * 16 <= 1024
+            else:
+                assert pw.tma_chunks == (n + (-pw.tma_r) - 1) // (-pw.tma_r) and (-pw.tma_r) * (h + 1) <= 256
             m_tiles = (cin + 127) // 128
             assert pw.tma_splits * m_tiles * (cout // 32) <= 148 or pw.tma_splits == 1     # one wave of CTAs
         want_c32 = cout == 32 and cin >= 64 and cin % 32 == 0 and w + 2 <= 256
