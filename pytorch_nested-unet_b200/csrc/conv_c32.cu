@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
         if (lane == 0) {
             for (int si = 0; si < p.num_src; ++si) tma_prefetch_desc(&p.xmap[si]);
             const uint32_t a_box_bytes = (uint32_t)p.box_rows * (uint32_t)p.PW * 64u;
-            if (p.res_b) {
+            if ((int)blockIdx.x >= p.groups_total) {
+                // a CTA without work (tiny problems: the grid is the generic plan's) must not leave bulk copies in flight at exit
+            } else if (p.res_b) {
                 mbar_arrive_expect_tx(b_full, (uint32_t)p.nch * kC32BBytes);
                 for (int c = 0; c < p.nch; ++c)
                     bulk_g2s(sB + (size_t)c * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, b_full);
