@@ -128,3 +128,23 @@ def test_grad_buckets_and_syncbn_exchange_gloo_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert res[0][2] >= 2  # more than one bucket was exercised
+
+
+def test_kernel_selection_policy_for_materialised_operands():
+    """Pure host logic: which layers run on the stacked Cout = 32 kernel, and where the TMA width limit switches the engine back
+    to the fused loaders."""
+    import archs
+    import engine
+    m = archs.NestedUNet(1, 3, True)
+    specs = engine._state(m).specs
+    stacked = sorted((s.node, s.which, s.cin_pad) for s in specs
+                     if engine._stacked(s, 4, 96 >> s.level, 96 >> s.level, engine._cin_pad(s, True)))
+    assert stacked == [("0_1", 1, 96), ("0_2", 1, 128), ("0_3", 1, 160), ("0_4", 1, 192)]
+    # 256-pixel rows exceed the 254-pixel TMA box: nothing at level 0 is stacked / repacked there, level 1 (128 px) still is eligible
+    assert not any(engine._stacked(s, 4, 256, 256, engine._cin_pad(s, False)) for s in specs if s.level == 0)
+    assert engine._tma_width(254) and not engine._tma_width(255)
+    stem = specs[0]
+    assert engine._cin_pad(stem, True) == 32 and engine._cin_pad(stem, False) == 16
+    u = archs.UNet(1, 3)
+    us = engine._state(u).specs
+    assert [(s.node, s.cin_pad) for s in us if engine._stacked(s, 2, 64 >> s.level, 64 >> s.level, engine._cin_pad(s, True))] == [("0_4", 96)]
