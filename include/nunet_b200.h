@@ -192,7 +192,10 @@ int nunet_bn_bwd_apply(const void* gz, const void* y, const float* k1, const flo
  * as the forward conv (src[]).  part: plan.part_elems fp32 of scratch. */
 typedef struct {
     int32_t KP, S, Pg, cpc, nchunks_total, splits, m_tiles, n_tiles, cin_pad, smem_bytes, triple;
-    /* TMA variant (all sources pre-activated, same resolution): r padded rows of PW pixels per K chunk */
+    /* TMA variant (all sources NUNET_SRC_ACT, rows <= 254 px; csrc/conv_wgrad_tma.cu).  tma = 1: applies.  tma_PW: padded row
+     * length; tma_r > 0: padded rows of one image per K chunk, tma_r < 0: -(whole images per chunk); tma_S: pipeline stages;
+     * tma_G: MMAs per 16-position K step (3: kernel columns stacked into N = 96; 1: Cin = 32, kernel rows stacked on A too);
+     * tma_Nt: output channels per CTA (32); tma_splits x tma_cpc >= tma_chunks: split-K partition (one wave of CTAs). */
     int32_t tma, tma_PW, tma_r, tma_S, tma_G, tma_Nt, tma_splits, tma_cpc, tma_chunks, tma_smem_bytes;
     int64_t part_elems;
 } nunet_wgrad_plan_t;
