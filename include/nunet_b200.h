@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define NUNET_ABI_VERSION 1
+#define NUNET_ABI_VERSION 2
 #define NUNET_MAX_SRC 5
 
 enum { NUNET_OK = 0, NUNET_E_BADARG = 1, NUNET_E_UNSUPPORTED = 2, NUNET_E_SMEM = 3, NUNET_E_CUDA = 1000 };
@@ -217,9 +217,10 @@ int nunet_input_to_nhwc32(const float* x, int32_t N, int32_t C, int32_t H, int32
 int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* plan);
 int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
 
-/* ---- fp32 check mode (forward only; csrc/check_fp32.cu) ------------------------------------------------------------
+/* ---- fp32 check mode (forward and backward; csrc/check_fp32.cu) -----------------------------------------------------
  * The reference's fp32 arithmetic on CUDA cores: fp32 NHWC activations with a channel pitch, fp64 BatchNorm statistics.
- * Used to hold the graph / BatchNorm / pooling / upsampling / head semantics to <= 1e-4 against the reference's logits. */
+ * Used to hold the graph / BatchNorm / pooling / upsampling / head semantics to <= 1e-4 against the reference's logits and
+ * <= 1e-3 (rel-L2) against the reference's gradients. */
 int nunet_check_nchw_to_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
 /* nn.Conv2d(Cin, Cout, 3, padding=1) incl. bias (finished/archs1.py:18,20); wt_scratch: 9*Cin*Cout floats */
 int nunet_check_conv3x3(const float* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t xpitch, const float* w_oihw,
@@ -227,7 +228,8 @@ int nunet_check_conv3x3(const float* x, int32_t N, int32_t H, int32_t W, int32_t
 /* nn.BatchNorm2d (finished/archs1.py:19,21): train != 0: batch statistics (+ running-stat update), else running statistics;
  * emits the per-channel scale/shift of a = relu(scale*y + shift) */
 int nunet_check_bn(const float* y, long long M, int32_t C, const float* gamma, const float* beta, float* running_mean,
-                   float* running_var, float momentum, float eps, int32_t train, float* scale, float* shift, void* stream);
+                   float* running_var, float momentum, float eps, int32_t train, float* scale, float* shift, float* save_mean,
+                   float* save_invstd, void* stream);
 int nunet_check_bn_relu(const float* y, long long M, int32_t C, const float* scale, const float* shift, float* dst, int32_t pitch,
                         int32_t off, void* stream);
 /* mode 0 copy | 1 nn.MaxPool2d(2,2) | 2 nn.Upsample(2, bilinear, align_corners=True) of src [N,h,w,C] into the channel
@@ -236,6 +238,23 @@ int nunet_check_route(const float* src, int32_t N, int32_t h, int32_t w, int32_t
                       int32_t off, void* stream);
 int nunet_check_head(const float* a, int32_t N, int32_t H, int32_t W, int32_t C, const float* wh, const float* bh, int32_t K,
                      float* logits, void* stream);
+/* Backward of the check-mode graph (autograd of finished/archs1.py:23-32,82-83,117-142 in fp32 with fp64 reductions).
+ * relu_bn_bwd: g_z = g_a*[scale*y+shift > 0]; dbeta = sum g_z; dgamma = sum g_z*yhat; g_y = gamma*invstd*(g_z - dbeta/M - yhat*dgamma/M).
+ * conv3x3_dgrad: dx [N,H,W,Cin] dense (overwritten); conv3x3_wgrad: dw OIHW (overwritten), dbias [Cout] optional (sum of g_y).
+ * route_bwd: ga [N,h,w,C] (dense, ACCUMULATED) += transpose of nunet_check_route applied to the slice [off, off+C) of dx; a_src is the
+ * routed activation (needed for mode 1: gradient goes to the first maximum of each 2x2 window in scan order, as ATen).
+ * head_bwd: ga += dlogits * wh (ACCUMULATED); dwh [K][C], dbh [K] (optional) overwritten. */
+int nunet_check_relu_bn_bwd(const float* ga, const float* y, long long M, int32_t C, const float* scale, const float* shift,
+                            const float* gamma, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* gy,
+                            void* stream);
+int nunet_check_conv3x3_dgrad(const float* gy, int32_t N, int32_t H, int32_t W, int32_t Cout, const float* w_oihw, int32_t Cin,
+                              float* wt_scratch, float* dx, void* stream);
+int nunet_check_conv3x3_wgrad(const float* x, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t xpitch, const float* gy, int32_t Cout,
+                              float* dw_oihw, float* dbias, void* stream);
+int nunet_check_route_bwd(const float* dx, int32_t N, int32_t h, int32_t w, int32_t C, int32_t mode, int32_t pitch, int32_t off,
+                          const float* a_src, float* ga, void* stream);
+int nunet_check_head_bwd(const float* dlogits, const float* a, int32_t N, int32_t H, int32_t W, int32_t C, const float* wh, int32_t K,
+                         float* ga, float* dwh, float* dbh, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnunet_b200.so")
 
 MAX_SRC = 5
+ABI_VERSION = 2   # NUNET_ABI_VERSION of include/nunet_b200.h these structures mirror
 SRC_INPUT, SRC_SAME, SRC_POOL, SRC_UP, SRC_GRAD, SRC_ACT, SRC_POOL_ACT, SRC_UP_ACT = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_KIND = {SRC_SAME: SRC_ACT, SRC_POOL: SRC_POOL_ACT, SRC_UP: SRC_UP_ACT}
 PACK_FWD, PACK_DGRAD, PACK_FWD_C32, PACK_DGRAD_C32 = 0, 1, 2, 3
@@ -95,7 +96,12 @@ _SIGS = {
     "nunet_input_to_nhwc32": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_check_nchw_to_nhwc": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),
     "nunet_check_conv3x3": ([C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
-    "nunet_check_bn": ([C.c_void_p, C.c_longlong, C.c_int32] + [C.c_void_p] * 4 + [C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_bn": ([C.c_void_p, C.c_longlong, C.c_int32] + [C.c_void_p] * 4 + [C.c_float, C.c_float, C.c_int32] + [C.c_void_p] * 5, C.c_int),
+    "nunet_check_relu_bn_bwd": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32] + [C.c_void_p] * 9, C.c_int),
+    "nunet_check_conv3x3_dgrad": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_conv3x3_wgrad": ([C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_route_bwd": ([C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_check_head_bwd": ([C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_int32] + [C.c_void_p] * 4, C.c_int),
     "nunet_check_bn_relu": ([C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p], C.c_int),
     "nunet_check_route": ([C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p], C.c_int),
     "nunet_check_head": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
@@ -115,6 +121,8 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = res
+        if l.nunet_version() != ABI_VERSION:
+            raise NunetError("libnunet_b200.so has ABI version %d, this binding expects %d: rebuild the library" % (l.nunet_version(), ABI_VERSION))
         _lib = l
     return _lib
 

@@ -530,6 +530,9 @@ static int pick_nt(int C) {
 // cycles through the stage ring), slower for narrower tiles (tools/time_conv.py) -> only used for NT >= 128.
 static bool resident_weights(int NT) {
     static const bool on = getenv("NUNET_NO_RESIDENT_B") == nullptr;
+#ifdef NUNET_EXPERIMENT
+    if (const char* e = getenv("NUNET_RESB_MIN_NT")) return on && NT >= atoi(e);
+#endif
     return on && NT >= 128;
 }
 
@@ -563,13 +566,26 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
             if (cin_pad % CK != 0) continue;
             const int nch = cin_pad / CK;
             const int P = 128 * T + 2 * (W + 2) + 2;
-            for (int S = ((nch == 1 && resident_weights(NT)) ? 4 : 3); S >= minS; --S) {  // the stage ring runs across tile groups, so S may exceed the chunks per group
+            // the stage ring runs across tile groups, so S may exceed the chunks per group; with a resident weight block (level-0 dgrads)
+            // deeper rings measured 35-50 % SLOWER (32->192 at 96x96: S=2 0.264 ms, S=3 0.399 ms; profiles/r02_conv_tiling_sweep.log)
+            for (int S = ((nch == 1 && resident_weights(NT)) ? 2 : 3); S >= minS; --S) {
                 if ((size_t)P * 16 >= (1u << 18)) continue;
                 if (conv_smem_bytes(T, NT, CK, S, P, cin_pad) <= budget) { bestT = T; bestCK = CK; bestS = S; break; }
             }
         }
     }
     if (!bestT) return NUNET_E_SMEM;
+#ifdef NUNET_EXPERIMENT
+    // tiling overrides for sweeps (tools/sweep_conv.sh); never compiled into the shipped library
+    if (const char* e = getenv("NUNET_CONV_T")) {
+        const int T = atoi(e), P = 128 * T + 2 * (W + 2) + 2;
+        int S = getenv("NUNET_CONV_S") ? atoi(getenv("NUNET_CONV_S")) : bestS;
+        if (T >= 1 && 2 * T * NT <= 512 && cin_pad % 32 == 0) {
+            while (S > 1 && conv_smem_bytes(T, NT, 32, S, P, cin_pad) > budget) --S;
+            if (conv_smem_bytes(T, NT, 32, S, P, cin_pad) <= budget) { bestT = T; bestCK = 32; bestS = S; }
+        }
+    }
+#endif
     pl->T = bestT; pl->NT = NT; pl->CK = bestCK; pl->S = bestS;
     pl->P = 128 * bestT + 2 * (W + 2) + 2;
     pl->nchunks = cin_pad / bestCK;

@@ -713,8 +713,9 @@ def _graphed_eval(model, x, params):
 
 
 # ------------------------------------------------------------------------------------------------ fp32 check mode
-# Forward-only evaluation of the same graph in CUDA-core fp32 (csrc/check_fp32.cu): the north_star's "<= 1e-4 in an fp32 check
-# mode" bound against the reference's logits.  Selected explicitly; never a fallback of the product path.
+# Evaluation of the same graph, forward AND backward, in CUDA-core fp32 with fp64 reductions (csrc/check_fp32.cu): the
+# north_star's "<= 1e-4 in an fp32 check mode" bound against the reference's logits, and the reference's gradients to <= 1e-3
+# rel-L2 (tests/test_model_gpu.py).  Selected explicitly; never a fallback of the product path.
 CHECK_FP32 = _os.environ.get("NUNET_FP32_CHECK", "0") == "1"
 _ROUTE_MODE = {L.SRC_SAME: 0, L.SRC_POOL: 1, L.SRC_UP: 2}
 
@@ -723,7 +724,12 @@ def _check_call(name, *args):
     ops._call("check_fp32", 1, None, name, getattr(L.lib(), name), *args)
 
 
-def _forward_check(model, x, train):
+class _CheckRecord(object):
+    __slots__ = ("buf", "cin", "y", "a", "scale", "shift", "mean", "invstd", "h", "w")
+
+
+def _forward_check(model, x, train, keep=False):
+    """Returns (logits tuple, per-layer records or None).  keep=True retains what the backward pass needs."""
     st = _state(model)
     specs = st.specs
     ops.require_cuda(x, "input")
@@ -736,7 +742,7 @@ def _forward_check(model, x, train):
     P, S = ops._ptr, ops._stream
     xin = torch.empty((N, H, W, Cin), **f32)
     _check_call("nunet_check_nchw_to_nhwc", P(x), N, Cin, H, W, P(xin), S())
-    acts = {}
+    acts, recs = {}, []
     for s in specs:
         h, w = H >> s.level, W >> s.level
         if s.sources[0][0] < 0:
@@ -758,15 +764,20 @@ def _forward_check(model, x, train):
         _check_call("nunet_check_conv3x3", P(buf), N, h, w, cin, cin, P(wgt), P(bias), s.cout, P(wt), P(y), S())
         bn = s.bn
         scale, shift = torch.empty(s.cout, **f32), torch.empty(s.cout, **f32)
+        mean, invstd = (torch.empty(s.cout, **f32), torch.empty(s.cout, **f32)) if keep else (None, None)
         track = bn.track_running_stats and bn.running_mean is not None
         use_batch = train or not track
         momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
         _check_call("nunet_check_bn", P(y), N * h * w, s.cout, P(bn.weight), P(bn.bias), P(bn.running_mean if (track and (train or not use_batch)) else None),
                     P(bn.running_var if (track and (train or not use_batch)) else None), float(momentum), float(bn.eps), 1 if use_batch else 0,
-                    P(scale), P(shift), S())
+                    P(scale), P(shift), P(mean), P(invstd), S())
         a = torch.empty((N, h, w, s.cout), **f32)
         _check_call("nunet_check_bn_relu", P(y), N * h * w, s.cout, P(scale), P(shift), P(a), s.cout, 0, S())
         acts[s.idx] = a
+        if keep:
+            r = _CheckRecord()
+            r.buf, r.cin, r.y, r.a, r.scale, r.shift, r.mean, r.invstd, r.h, r.w = buf, cin, y, a, scale, shift, mean, invstd, h, w
+            recs.append(r)
     if train:
         nbt = [s.bn.num_batches_tracked for s in specs if s.bn.num_batches_tracked is not None]
         if nbt:
@@ -781,7 +792,72 @@ def _forward_check(model, x, train):
             bh = s.head.bias.detach().float().contiguous() if s.head.bias is not None else None
             _check_call("nunet_check_head", P(a), N, a.shape[1], a.shape[2], s.cout, P(wh), P(bh), K, P(logits), S())
             outs.append(logits)
-    return tuple(outs)
+    return tuple(outs), (recs if keep else None)
+
+
+def _backward_check(model, N, recs, grad_logits):
+    """Autograd of _forward_check in fp32 (fp64 reductions).  grad_logits: {layer idx: dlogits fp32 NCHW}.  Returns {id(param): grad}."""
+    specs = _state(model).specs
+    dev = recs[0].y.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    P, S = ops._ptr, ops._stream
+    grads, ga = {}, {}
+    for s in reversed(specs):
+        r = recs[s.idx]
+        h, w = r.h, r.w
+        g = ga.pop(s.idx, None)
+        if g is None:
+            g = torch.zeros((N, h, w, s.cout), **f32)
+        if s.head is not None and grad_logits.get(s.idx) is not None:
+            K = s.head.out_channels
+            dl = grad_logits[s.idx].float().contiguous()
+            wh = s.head.weight.detach().float().reshape(K, -1).contiguous()
+            dwh, dbh = torch.empty((K, s.cout), **f32), torch.empty((K,), **f32)
+            _check_call("nunet_check_head_bwd", P(dl), P(r.a), N, h, w, s.cout, P(wh), K, P(g), P(dwh), P(dbh), S())
+            grads[id(s.head.weight)] = dwh.view_as(s.head.weight)
+            if s.head.bias is not None:
+                grads[id(s.head.bias)] = dbh
+        dgamma, dbeta = torch.empty(s.cout, **f32), torch.empty(s.cout, **f32)
+        gy = torch.empty((N, h, w, s.cout), **f32)
+        _check_call("nunet_check_relu_bn_bwd", P(g), P(r.y), N * h * w, s.cout, P(r.scale), P(r.shift), P(s.bn.weight), P(r.mean), P(r.invstd),
+                    P(dgamma), P(dbeta), P(gy), S())
+        grads[id(s.bn.weight)], grads[id(s.bn.bias)] = dgamma, dbeta
+        dw = torch.empty_like(s.conv.weight, dtype=torch.float32)
+        db = torch.empty(s.cout, **f32) if s.conv.bias is not None else None
+        _check_call("nunet_check_conv3x3_wgrad", P(r.buf), N, h, w, r.cin, r.cin, P(gy), s.cout, P(dw), P(db), S())
+        grads[id(s.conv.weight)] = dw
+        if db is not None:
+            grads[id(s.conv.bias)] = db
+        if s.sources[0][0] < 0:
+            continue
+        wgt = s.conv.weight.detach().float().contiguous()
+        wt = torch.empty(9 * r.cin * s.cout, **f32)
+        dx = torch.empty((N, h, w, r.cin), **f32)
+        _check_call("nunet_check_conv3x3_dgrad", P(gy), N, h, w, s.cout, P(wgt), r.cin, P(wt), P(dx), S())
+        off = 0
+        for pi, kind, c in s.sources:
+            rp = recs[pi]
+            if pi not in ga:
+                ga[pi] = torch.zeros((N, rp.h, rp.w, c), **f32)
+            _check_call("nunet_check_route_bwd", P(dx), N, rp.h, rp.w, c, _ROUTE_MODE[kind], r.cin, off, P(rp.a), P(ga[pi]), S())
+            off += c
+    return grads
+
+
+class _CheckFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        outs, recs = _forward_check(model, x, True, keep=True)
+        ctx.model, ctx.params, ctx.recs, ctx.N = model, params, recs, x.shape[0]
+        ctx.head_layers = [s.idx for s in _state(model).specs if s.head is not None]
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grad_logits):
+        gl = {i: g for i, g in zip(ctx.head_layers, grad_logits) if g is not None}
+        grads = _backward_check(ctx.model, ctx.N, ctx.recs, gl)
+        ctx.recs = None
+        return (None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
 
 
 def run_model(model, x):
@@ -791,9 +867,10 @@ def run_model(model, x):
     need_grad = model.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
     if CHECK_FP32:
         if need_grad:
-            raise L.NunetError("the fp32 check mode is forward-only: call the model under torch.no_grad()")
-        with torch.no_grad():
-            outs = _forward_check(model, x, model.training)
+            outs = _CheckFunction.apply(model, x, *params)
+        else:
+            with torch.no_grad():
+                outs, _ = _forward_check(model, x, model.training)
         return list(outs) if model._returns_list else outs[0]
     if need_grad:
         outs = _NetFunction.apply(model, x, *params)

@@ -44,6 +44,13 @@ def train_case(archs, losses, metrics, arch, num_classes, ds, n, h, w, dist, wei
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
     x, t = O.synthetic_batch(n, h, w, num_classes, 3, data_seed, dist)
     model.train()
+    for i in range(warm):               # `warm` full SGD steps of the reference loop body (trains.py:113-136) on other batches first
+        xw, tw = O.synthetic_batch(n, h, w, num_classes, 3, data_seed + 1000 + i, dist)
+        ow = model(xw)
+        lw = sum(crit(o, tw) for o in ow) / len(ow) if isinstance(ow, list) else crit(ow, tw)
+        opt.zero_grad()
+        lw.backward()
+        opt.step()
     out = model(x)
     if isinstance(out, list):
         loss = 0
@@ -64,7 +71,7 @@ def train_case(archs, losses, metrics, arch, num_classes, ds, n, h, w, dist, wei
     t_ = t.numpy() > 0.5
     rec = {
         "arch": arch, "num_classes": num_classes, "deep_supervision": ds, "n": n, "h": h, "w": w, "dist": dist,
-        "weight_seed": weight_seed, "data_seed": data_seed,
+        "weight_seed": weight_seed, "data_seed": data_seed, "warm": warm,
         "logits": [o.detach().clone() for o in out] if isinstance(out, list) else out.detach().clone(),
         "loss": float(loss.detach()), "iou": float(iou),
         "I": int((o_ & t_).sum()), "U": int((o_ | t_).sum()),

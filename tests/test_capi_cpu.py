@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export: " + n
     assert set(L.exported_symbols()) == set(names)
-    assert lib.nunet_version() == 1
+    assert lib.nunet_version() == L.ABI_VERSION
 
 
 def _layers(size, N):

@@ -3,17 +3,20 @@ reference (tests/golden/make_golden.py): one trains.py-style step (forward, BCED
 SGD step) and one val.py-style eval forward.
 
 Tolerances (bf16 tensor-core operands, fp32 accumulation, fp32 statistics) — see DESIGN.md "Numerics":
-  train-mode logits : max|d|/max|ref| <= 8e-2 per head at random init (SURVEY.md 8c finding 2: an ideal bf16-operand
-                      pipeline gives 1e-2..4e-2 from head 1 to head 4; the reference under bf16 autocast 1.3e-2..5.7e-2);
-                      rel-L2 <= 8e-2
+  train-mode logits : per head, max|d|/max|ref| <= max(2e-2, 1.25 x what the UNMODIFIED reference itself shows under
+                      torch.autocast(bfloat16) on the same case) — the north_star's 2e-2 where bf16 operands can meet it at all
+                      (SURVEY.md 8c finding 2: an ideal bf16-operand pipeline gives 1e-2..4e-2 from head 1 to head 4 in train mode
+                      at random init; the per-case autocast numbers are minted into tests/golden/steps_r02.pt)
   eval-mode logits  : max|d|/max|ref| <= 2e-2 (north_star bound)
   loss              : |d| <= 1e-3 (north_star bound)
-  gradients         : bf16-vs-fp32 FORWARD differences flip ReLU gates / max-pool winners at a few % of pixels per layer
-                      (each an O(1) change of that pixel's gradient), so the end-to-end gradient comparison with the
-                      fp32 reference is only a sanity bound: per-parameter L2 norm within 20 %, cosine >= 0.6 on the
-                      checked tensors.  The backward kernels themselves are held to <= 6e-2 rel-L2 against autograd on
-                      the SAME forward in tests/test_backward_consistency_gpu.py, and to ~1e-5 per kernel in
-                      tests/test_backward_gpu.py.
+  gradients (bf16)  : bf16-vs-fp32 FORWARD differences flip ReLU gates / max-pool winners at a few % of pixels per layer
+                      (each an O(1) change of that pixel's gradient), so the bf16 gradients are only sanity-bounded against the
+                      fp32 reference here (norm within 20 %, cosine >= 0.6).  The TIGHT gradient check is
+                      test_fp32_check_mode_forward_and_backward_match_reference below: the same graph in CUDA-core fp32 must
+                      reproduce every gradient norm and the 15 stored gradient tensors of the reference to <= 1e-3 (rel-L2), or 4x
+                      the reference's own sensitivity to a 1e-7 input perturbation where that is larger (goldens.grad_tolerances).
+                      The bf16 backward kernels are held to <= 6e-2 rel-L2 against autograd on the SAME forward in
+                      tests/test_backward_consistency_gpu.py, and to ~1e-5 per kernel in tests/test_backward_gpu.py.
 """
 import os
 
@@ -25,14 +28,15 @@ DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+import goldens
+
+
 def _steps():
-    return torch.load(os.path.join(GOLD, "steps.pt"))
+    return goldens.load("steps.pt")
 
 
 def _synthetic(g):
-    # identical generator recipe to oracle.nunet_oracle.synthetic_batch (kept here so the product modules never import oracle)
-    from oracle.nunet_oracle import synthetic_batch
-    return synthetic_batch(g["n"], g["h"], g["w"], g["num_classes"], 3, g["data_seed"], g["dist"])
+    return goldens.synthetic(g)
 
 
 def _relmax(a, b):
@@ -43,19 +47,35 @@ def _rell2(a, b):
     return float((a - b).norm() / b.norm())
 
 
-CASES = ["nested_ds_n2_32", "nested_wods_n2_32_dsb", "unet_n4_64", "nested_ds_c4_n2_32", "nested_wods_n4_96", "nested_ds_n3_48x80"]
+def _build(g):
+    """Model on the device in the state the golden's recorded step starts from, its SGD optimizer (momentum buffers restored for a
+    warm case) and the loss."""
+    import archs
+    import losses
+    sd, bufs = goldens.start_state(g)
+    model = getattr(archs, g["arch"])(g["num_classes"], 3, g["deep_supervision"])
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    named = dict(model.named_parameters())
+    for k, b in bufs.items():
+        opt.state[named[k]]["momentum_buffer"] = b.to(DEV).clone()
+    return model, opt, losses.BCEDiceLoss().to(DEV)
+
+
+R1_CASES = ["nested_ds_n2_32", "nested_wods_n2_32_dsb", "unet_n4_64", "nested_ds_c4_n2_32", "nested_wods_n4_96", "nested_ds_n3_48x80"]
+# round 2: BASELINE config 1 exactly; 256x256 (rows wider than the 254-px TMA box: the mixed materialised / fused-loader engine branch);
+# W = 272 with 4 classes + deep supervision and through UNet; a case that starts after 20 reference SGD steps
+R2_CASES = ["c1_nested_wods_n16_96_dsb", "c3_nested_wods_n2_256", "nested_ds_c4_n2_32x272", "unet_n2_32x272", "warm_nested_ds_n4_32"]
+CASES = R1_CASES + R2_CASES
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_train_step_and_eval_against_reference_golden(name):
-    import archs
-    import losses
     import metrics
-    g = _steps()[name]
-    torch.manual_seed(g["weight_seed"])
-    model = getattr(archs, g["arch"])(g["num_classes"], 3, g["deep_supervision"]).to(DEV)
-    crit = losses.BCEDiceLoss().to(DEV)
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    g = goldens.case(name)
+    warm = g.get("warm", 0)
+    model, opt, crit = _build(g)
     x, t = _synthetic(g)
     x, t = x.to(DEV), t.to(DEV)
     model.train()
@@ -75,10 +95,13 @@ def test_train_step_and_eval_against_reference_golden(name):
     opt.zero_grad()
     loss.backward()
     report = []
+    ctx = goldens.autocast_context(name)
     for k, (o, r) in enumerate(zip(outs, refs)):
         rm, rl = _relmax(o.detach().cpu(), r), _rell2(o.detach().cpu(), r)
-        report.append("head%d relmax %.3e rell2 %.3e" % (k + 1, rm, rl))
-        assert rm <= 8e-2 and rl <= 8e-2, report
+        # what the reference itself loses under bf16 autocast on this case and head (None for the warm case: same net as nested_ds_n2_32)
+        ac_m, ac_l = (ctx["relmax"][k], ctx["rell2"][k]) if ctx and ctx["relmax"] else (4.9e-2, 5e-2)
+        report.append("head%d relmax %.3e (ref autocast %.3e) rell2 %.3e (%.3e)" % (k + 1, rm, ac_m, rl, ac_l))
+        assert rm <= max(2e-2, 1.25 * ac_m) and rl <= max(2e-2, 1.25 * ac_l), report
     assert abs(float(loss) - g["loss"]) <= 1e-3, (float(loss), g["loss"])
     # IoU: identical-logit exactness is covered in test_head_loss_gpu; end to end bf16 flips a few near-zero logits
     I, U = metrics.iou_counts(last, t)
@@ -109,7 +132,7 @@ def test_train_step_and_eval_against_reference_golden(name):
     sd = model.state_dict()
     for k, v in g["bn_after"].items():
         assert torch.allclose(sd[k].cpu(), v, rtol=3e-2, atol=3e-3), (k, float((sd[k].cpu() - v).abs().max()))
-    assert int(sd["conv0_0.bn1.num_batches_tracked"]) == 1
+    assert int(sd["conv0_0.bn1.num_batches_tracked"]) == warm + 1
     opt.step()
     for k, n_ref in g["param_after_norms"].items():
         if sd[k].is_floating_point() and "running" not in k:
@@ -192,45 +215,65 @@ def test_captured_and_multistream_steps_are_bitwise_equal_to_the_single_stream_s
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_fp32_check_mode_matches_reference_logits_to_1e_4(name):
-    """north_star: forward logits max|d|/max|ref| <= 1e-4 in the fp32 check mode (engine.CHECK_FP32: CUDA-core fp32 convs,
-    fp64 BatchNorm statistics).  Train-mode logits and the updated running statistics against the golden minted from the
-    unmodified reference; eval-mode logits (running statistics after that step) against the oracle restatement."""
-    import archs
+def test_fp32_check_mode_forward_and_backward_match_reference(name):
+    """north_star: forward logits max|d|/max|ref| <= 1e-4 in the fp32 check mode (engine.CHECK_FP32: CUDA-core fp32 convs, fp64
+    BatchNorm statistics), and — VERDICT r01 item 1a — the reference's GRADIENTS: every per-parameter gradient norm and all stored
+    gradient tensors of the golden to <= 1e-3 (rel-L2), or 4x the reference's own sensitivity to a 1e-7 input perturbation where that
+    is larger (goldens.grad_tolerances; ReLU gates and max-pool winners are discontinuous).  Train-mode logits, gradients, the
+    parameters after the SGD step and the updated running statistics against the golden minted from the unmodified reference;
+    eval-mode logits (running statistics after that step) against the golden's eval forward."""
     import engine
-    from oracle import nunet_oracle as orc
-    g = _steps()[name]
-    torch.manual_seed(g["weight_seed"])
-    model = getattr(archs, g["arch"])(g["num_classes"], 3, g["deep_supervision"]).to(DEV)
-    x, _ = _synthetic(g)
+    g = goldens.case(name)
+    warm = g.get("warm", 0)
+    model, opt, crit = _build(g)
+    x, t = _synthetic(g)
+    x, t = x.to(DEV), t.to(DEV)
     saved = engine.CHECK_FP32
     engine.CHECK_FP32 = True
     try:
         model.train()
-        with pytest.raises(Exception):
-            model(x.to(DEV))                      # forward-only: refuses to build a graph for backward
-        with torch.no_grad():
-            out = model(x.to(DEV))
+        out = model(x)
         outs = out if isinstance(out, list) else [out]
         refs = g["logits"] if isinstance(g["logits"], list) else [g["logits"]]
+        ltol = 5e-4 if warm else 1e-4        # warm: the start state itself is rebuilt by 20 oracle steps (tests/goldens.py)
         for k, (o, r) in enumerate(zip(outs, refs)):
-            assert _relmax(o.cpu(), r) <= 1e-4, (k, _relmax(o.cpu(), r))
+            assert _relmax(o.detach().cpu(), r) <= ltol, (k, _relmax(o.detach().cpu(), r))
+        loss = sum(crit(o, t) for o in outs) / len(outs)
+        assert abs(float(loss) - g["loss"]) <= (2e-5 if warm else 5e-6), (float(loss), g["loss"])
+        opt.zero_grad()
+        loss.backward()
+        ntol, gtol = goldens.grad_tolerances(name, floor=8e-2 if warm else 1e-3)
+        named = dict(model.named_parameters())
+        worst_n = worst_g = 0.0
+        for k, n_ref in g["grad_norms"].items():
+            gr = named[k].grad
+            assert gr is not None, k
+            if k.endswith(("conv1.bias", "conv2.bias")):      # analytically zero under train-mode BatchNorm: round-off only, on both sides
+                assert n_ref < 1e-4 and float(gr.norm()) < 1e-4, (k, n_ref, float(gr.norm()))
+                continue
+            rel = abs(float(gr.norm()) - n_ref) / max(n_ref, 1e-12)
+            worst_n = max(worst_n, rel)
+            assert rel <= ntol, (k, float(gr.norm()), n_ref, ntol)
+        for k, g_ref in g["grads"].items():
+            if k.endswith(("conv1.bias", "conv2.bias")):
+                continue
+            rel = _rell2(named[k].grad.cpu(), g_ref)
+            worst_g = max(worst_g, rel)
+            assert rel <= gtol, (k, rel, gtol)
+        print(name, "fp32 check: worst grad-norm rel %.2e (tol %.1e), worst gradient rel-L2 %.2e (tol %.1e)" % (worst_n, ntol, worst_g, gtol))
         sd = model.state_dict()
         for k, v in g["bn_after"].items():
-            assert torch.allclose(sd[k].cpu(), v, rtol=1e-4, atol=1e-6), (k, float((sd[k].cpu() - v).abs().max()))
-        assert int(sd["conv0_0.bn1.num_batches_tracked"]) == 1
+            assert torch.allclose(sd[k].cpu(), v, rtol=1e-3 if warm else 1e-4, atol=1e-4 if warm else 1e-6), (k, float((sd[k].cpu() - v).abs().max()))
+        assert int(sd["conv0_0.bn1.num_batches_tracked"]) == warm + 1
+        opt.step()
+        for k, n_ref in g["param_after_norms"].items():
+            if "running" not in k and sd[k].is_floating_point():
+                assert abs(float(model.state_dict()[k].float().norm()) - n_ref) <= (1e-4 if warm else 1e-5) * max(n_ref, 1.0), k
         model.eval()
         with torch.no_grad():
-            oe = model(x.to(DEV))
-        oe = oe if isinstance(oe, list) else [oe]
-        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        if g["arch"] == "NestedUNet":
-            ref_e = orc.nested_unet_forward(sd_cpu, x, g["deep_supervision"], train=False)
-        else:
-            ref_e = orc.unet_forward(sd_cpu, x, train=False)
-        ref_e = ref_e if isinstance(ref_e, list) else [ref_e]
-        for o, r in zip(oe, ref_e):
-            assert _relmax(o.cpu(), r) <= 1e-4, _relmax(o.cpu(), r)
+            oe = model(x)
+        oe_last = oe[-1] if isinstance(oe, list) else oe
+        assert _relmax(oe_last.cpu(), g["eval_logits_last"]) <= ltol, _relmax(oe_last.cpu(), g["eval_logits_last"])
     finally:
         engine.CHECK_FP32 = saved
 

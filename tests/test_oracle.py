@@ -10,44 +10,46 @@ from oracle import nunet_oracle as O
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(scope="module")
-def steps():
-    return torch.load(os.path.join(GOLD, "steps.pt"))
-
-
-def _model_sd(g):
-    import archs
-    torch.manual_seed(g["weight_seed"])
-    m = getattr(archs, g["arch"])(g["num_classes"], 3, g["deep_supervision"])  # parameter container; same init order as the reference
-    return {k: v.clone() for k, v in m.state_dict().items()}
-
-
-@pytest.mark.parametrize("name", ["nested_ds_n2_32", "nested_wods_n2_32_dsb", "unet_n4_64", "nested_ds_c4_n2_32", "nested_ds_n3_48x80"])
-def test_oracle_train_step_matches_reference(steps, name):
-    g = steps[name]
-    sd = _model_sd(g)
+# steps.pt: round-1 cases; steps_r02.pt: BASELINE config 1 exactly, the 256x256 ISIC shape, rows wider than 254 px, and a case
+# that starts from 20 SGD steps of the reference (weights, momentum buffers and running statistics away from their initial values)
+@pytest.mark.parametrize("name", ["nested_ds_n2_32", "nested_wods_n2_32_dsb", "unet_n4_64", "nested_ds_c4_n2_32", "nested_ds_n3_48x80",
+                                  "c1_nested_wods_n16_96_dsb", "c3_nested_wods_n2_256", "nested_ds_c4_n2_32x272", "unet_n2_32x272",
+                                  "warm_nested_ds_n4_32"])
+def test_oracle_train_step_matches_reference(name):
+    import goldens
+    g = goldens.case(name)
+    sd, bufs = goldens.start_state(g)
     x, t = O.synthetic_batch(g["n"], g["h"], g["w"], g["num_classes"], 3, g["data_seed"], g["dist"])
-    new_sd, loss, iou, grads, outs = O.train_step(sd, x, t, g["arch"], g["deep_supervision"])
+    new_sd, loss, iou, grads, outs = O.train_step(sd, x, t, g["arch"], g["deep_supervision"], bufs=bufs)
     refs = g["logits"] if isinstance(g["logits"], list) else [g["logits"]]
     outs = outs if isinstance(outs, list) else [outs]
+    warm = g.get("warm", 0)      # the start state of a warm case is rebuilt with `warm` oracle steps: their fp32 round-off differences accumulate
     for o, r in zip(outs, refs):
-        assert torch.allclose(o, r, rtol=1e-4, atol=2e-5 * float(r.abs().max())), float((o - r).abs().max())
-    assert abs(loss - g["loss"]) < 2e-6
-    assert (O.iou_counts(outs[-1], t)) == (g["I"], g["U"])
-    assert iou == g["iou"]
+        assert torch.allclose(o, r, rtol=1e-4, atol=(5e-4 if warm else 2e-5) * float(r.abs().max())), float((o - r).abs().max())
+    assert abs(loss - g["loss"]) < (2e-5 if warm else 2e-6)
+    I, U = O.iou_counts(outs[-1], t)
+    if warm:
+        flips = int(((torch.sigmoid(outs[-1]) > 0.5) != (torch.sigmoid(refs[-1]) > 0.5)).sum())
+        assert abs(I - g["I"]) <= flips and abs(U - g["U"]) <= flips and flips <= 4
+    else:
+        assert (I, U) == (g["I"], g["U"])
+        assert iou == g["iou"]
+    # ReLU gates / max-pool winners are discontinuous: the reference's OWN gradients move by `sens` (rel-L2) under a 1e-7 input
+    # perturbation (tests/golden/make_golden_r02.py, grad_sensitivity) — two fp32 implementations cannot agree better than that
+    ntol, gtol = goldens.grad_tolerances(name, floor=8e-2 if warm else 2e-3)   # warm: logits already differ by ~1e-4, gate flips amplify that to a few % in the gradients
     for k, n_ref in g["grad_norms"].items():
         if k.endswith(("conv1.bias", "conv2.bias")):
             assert n_ref < 1e-4 and float(grads[k].norm()) < 1e-4   # analytically zero under train-mode BN: fp32 noise only
             continue
-        assert abs(float(grads[k].norm()) - n_ref) <= 2e-3 * n_ref + 1e-7, k
+        assert abs(float(grads[k].norm()) - n_ref) <= ntol * n_ref + 1e-7, k
     for k, g_ref in g["grads"].items():
         if k.endswith(("conv1.bias", "conv2.bias")):
             continue
-        assert torch.allclose(grads[k], g_ref, rtol=1e-3, atol=2e-3 * float(g_ref.abs().max()) + 1e-9), k
+        assert float((grads[k] - g_ref).norm()) <= gtol * float(g_ref.norm()) + 1e-9, k
     for k, v in g["bn_after"].items():
-        assert torch.allclose(new_sd[k], v, rtol=1e-4, atol=1e-6), k
+        assert torch.allclose(new_sd[k], v, rtol=1e-3 if warm else 1e-4, atol=1e-4 if warm else 1e-6), k
     for k, n_ref in g["param_after_norms"].items():
-        assert abs(float(new_sd[k].float().norm()) - n_ref) <= 1e-5 * max(n_ref, 1.0), k
+        assert abs(float(new_sd[k].float().norm()) - n_ref) <= (1e-4 if warm else 1e-5) * max(n_ref, 1.0), k
     # eval path with the post-step state
     le, ie, oe = O.eval_step(new_sd, x, t, g["arch"], g["deep_supervision"])
     oe_last = oe[-1] if isinstance(oe, list) else oe

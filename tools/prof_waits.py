@@ -10,11 +10,10 @@ rd.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_ulonglong * 16)()
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
-CASES = [("fwd", 256, 96, 96, [("same", 32)], 32), ("fwd", 256, 96, 96, [("act", 32)] * 4 + [("act", 64)], 32),
-         ("fwd", 256, 48, 48, [("act", 64)] * 3 + [("act", 128)], 64), ("fwd", 256, 24, 24, [("act", 128)] * 2 + [("act", 256)], 128),
-         ("fwd", 256, 12, 12, [("act", 256), ("act", 512)], 256), ("fwd", 256, 6, 6, [("same", 512)], 512),
-         ("dgrad", 256, 96, 96, [("act", 32)], 192), ("dgrad", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 48, 48, [("act", 64)], 320),
-         ("dgrad", 256, 24, 24, [("act", 128)], 512)]
+CASES = [("fwd", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 96, 96, [("act", 32)], 192),
+         ("dgrad", 256, 96, 96, [("act", 32)], 128), ("fwd", 256, 48, 48, [("act", 64)], 64), ("fwd", 256, 48, 48, [("act", 64)] * 3 + [("act", 128)], 64),
+         ("dgrad", 256, 48, 48, [("act", 64)], 320), ("fwd", 256, 24, 24, [("act", 128)] * 2 + [("act", 256)], 128), ("dgrad", 256, 24, 24, [("act", 128)], 512),
+         ("fwd", 256, 12, 12, [("act", 256), ("act", 512)], 256), ("fwd", 256, 6, 6, [("act", 512)], 512)]
 for kind, N, H, W, srcs, Cout in CASES:
     sources = []
     for k, Cc in srcs:
