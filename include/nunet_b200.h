@@ -46,6 +46,32 @@ typedef struct {
     int32_t kind;
 } nunet_src_t;
 
+/* BatchNorm finalisation run as the TAIL of the kernel that produced the per-CTA partial sums (csrc/bn_tail.cuh): the last CTA to
+ * finish reduces the partial rows in a fixed order (fp64, deterministic) and writes the per-channel coefficients, so no separate
+ * launch sits between a convolution and its consumer.  counter == NULL disables the tail (the caller then launches
+ * nunet_bn_finalize_train / nunet_bn_backward_reduce on the partials itself).
+ * counter: ONE zero-initialised uint32 owned by this layer (self-resetting; launches that may overlap need distinct counters).
+ * Forward (nn.BatchNorm2d train-mode statistics, finished/archs1.py:19,21): fields as nunet_bn_finalize_train.
+ * gamma == NULL: only sums_out ([2][C] fp64) is written — the SyncBN exchange point. */
+typedef struct {
+    uint32_t* counter;
+    double count;
+    const float *gamma, *beta, *conv_bias;
+    float *running_mean, *running_var;
+    float momentum, eps;
+    float *scale, *shift, *save_mean, *save_invstd;
+    double* sums_out;
+} nunet_bn_tail_t;
+/* Backward (sums of nunet_grad_router): fields as nunet_bn_backward_reduce / nunet_bn_backward_from_sums. */
+typedef struct {
+    uint32_t* counter;
+    double count;
+    const float *gamma, *save_mean, *save_invstd;
+    float *dgamma, *dbeta, *k1, *k2, *k3;
+    float grad_scale;
+    double* sums_out;
+} nunet_bn_bwd_tail_t;
+
 /* One fused 3x3 convolution:  out[n,y,x,co] = sum_{src, ci, r, s} T_src(a_src)[n,y+r-1,x+s-1,ci] * W[co,ci,r,s]
  * (zero padding applied AFTER the per-source transform, as torch.cat + nn.Conv2d(padding=1) does).
  * Replaces, for one VGGBlock conv: nn.Conv2d (finished/archs1.py:18,20,24,28) and — via the source kinds — the
@@ -63,6 +89,21 @@ typedef struct {
     float* stat_part;  /* [plan.grid_m][2][Cout] fp32 or NULL */
     int32_t wpack_layout; /* 0: standard pack (NUNET_PACK_FWD / _DGRAD); 1: stacked pack (NUNET_PACK_*_C32) for the Cout = 32 kernel,
                            * only where nunet_conv3x3_c32_eligible() says so and every source is NUNET_SRC_ACT */
+    nunet_bn_tail_t bn;   /* bn.counter != NULL (needs stat_part): BatchNorm finalisation in the kernel's tail */
+    /* dgrad only.  num_out_seg > 0: the Cout output channels (= the forward conv's concatenated input channels) are written to one
+     * DENSE bf16 NHWC tensor per segment (out_seg[i]: [N,H,W,out_seg_c[i]], channel counts multiples of 32 summing to Cout) instead
+     * of `out`: the gradient router / nunet_up_transpose then read whole cache lines instead of 64-byte slices of a wide row
+     * (measured: 1.77x DRAM over-read on the interleaved layout, profiles/r02_ncu_kernels.csv). */
+    int32_t num_out_seg;
+    void* out_seg[NUNET_MAX_SRC];
+    int32_t out_seg_c[NUNET_MAX_SRC];
+    /* dgrad of a VGGBlock's SECOND conv only: fuses the block-internal gradient router (autograd of finished/archs1.py:25-26, the
+     * first conv's BatchNorm + ReLU) into the epilogue.  mask_y: the first conv's raw output y1 (bf16 NHWC, Cout channels);
+     * out = dX * [mask_scale*y1 + mask_shift > 0] (= g_z of the first conv); stat_part rows receive [sum g_z, sum g_z*yhat] with
+     * yhat = (y1 - mask_mean)*mask_invstd; bn_bwd.counter != NULL: BatchNorm-backward coefficients in the kernel's tail. */
+    const void* mask_y;
+    const float *mask_scale, *mask_shift, *mask_mean, *mask_invstd;
+    nunet_bn_bwd_tail_t bn_bwd;
 } nunet_conv_desc_t;
 
 typedef struct {
@@ -70,6 +111,7 @@ typedef struct {
     int32_t nchunks, n_tiles, grid_m, cin_pad; /* grid_m = CTAs along x = rows of stat_part (persistent kernel) */
     int32_t smem_bytes, tmem_cols, ntg;       /* ntg = tile groups of 128*T positions */
     int32_t tma_a_stage_bytes, tma_smem_bytes; /* > 0: the TMA tensor-load variant of this tiling fits (copy-mode sources) */
+    int32_t tma_epi_warps, pad_;               /* warps draining TMEM in the TMA variant (16 or 8) */
     int64_t wpack_elems; /* bf16 elements the packed weights occupy */
 } nunet_conv_plan_t;
 
@@ -165,6 +207,7 @@ typedef struct {
     int32_t K;
     void* gz;    /* out: g_z = g_a * [a>0], bf16 NHWC */
     float* part; /* out: [nunet_grad_router_rows()][2][C]: sum g_z, sum g_z*yhat */
+    nunet_bn_bwd_tail_t bn; /* bn.counter != NULL: BatchNorm-backward coefficients in the kernel's tail */
 } nunet_router_desc_t;
 int nunet_grad_router_rows(int32_t N, int32_t H, int32_t W, int32_t C);
 int nunet_grad_router(const nunet_router_desc_t* d, void* stream);

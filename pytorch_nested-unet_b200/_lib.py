@@ -19,16 +19,31 @@ class Src(C.Structure):
                 ("k2", C.c_void_p), ("C", C.c_int32), ("kind", C.c_int32)]
 
 
+class BnTail(C.Structure):      # nunet_bn_tail_t
+    _fields_ = [("counter", C.c_void_p), ("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("conv_bias", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p), ("sums_out", C.c_void_p)]
+
+
+class BnBwdTail(C.Structure):   # nunet_bn_bwd_tail_t
+    _fields_ = [("counter", C.c_void_p), ("count", C.c_double), ("gamma", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p), ("k3", C.c_void_p),
+                ("grad_scale", C.c_float), ("sums_out", C.c_void_p)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_src", C.c_int32), ("src", Src * MAX_SRC),
-                ("Cout", C.c_int32), ("wpack", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p), ("wpack_layout", C.c_int32)]
+                ("Cout", C.c_int32), ("wpack", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p), ("wpack_layout", C.c_int32),
+                ("bn", BnTail), ("num_out_seg", C.c_int32), ("out_seg", C.c_void_p * MAX_SRC), ("out_seg_c", C.c_int32 * MAX_SRC),
+                ("mask_y", C.c_void_p), ("mask_scale", C.c_void_p), ("mask_shift", C.c_void_p), ("mask_mean", C.c_void_p),
+                ("mask_invstd", C.c_void_p), ("bn_bwd", BnBwdTail)]
 
 
 class ConvPlan(C.Structure):
     _fields_ = [("T", C.c_int32), ("NT", C.c_int32), ("CK", C.c_int32), ("S", C.c_int32), ("P", C.c_int32),
                 ("nchunks", C.c_int32), ("n_tiles", C.c_int32), ("grid_m", C.c_int32), ("cin_pad", C.c_int32),
                 ("smem_bytes", C.c_int32), ("tmem_cols", C.c_int32), ("ntg", C.c_int32), ("tma_a_stage_bytes", C.c_int32),
-                ("tma_smem_bytes", C.c_int32), ("wpack_elems", C.c_int64)]
+                ("tma_smem_bytes", C.c_int32), ("tma_epi_warps", C.c_int32), ("pad_", C.c_int32), ("wpack_elems", C.c_int64)]
 
 
 class GradCons(C.Structure):
@@ -39,7 +54,7 @@ class RouterDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("y", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("num_cons", C.c_int32), ("cons", GradCons * 6), ("dlogits", C.c_void_p), ("wh", C.c_void_p),
-                ("K", C.c_int32), ("gz", C.c_void_p), ("part", C.c_void_p)]
+                ("K", C.c_int32), ("gz", C.c_void_p), ("part", C.c_void_p), ("bn", BnBwdTail)]
 
 
 class WgradPlan(C.Structure):

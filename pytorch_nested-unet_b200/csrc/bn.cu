@@ -3,63 +3,12 @@
 // coefficient kernel.  All HBM-trivial (C <= 512 channels); latency matters, so one launch does reduce + finalize via
 // the last-block-done pattern (deterministic: the last block sums the fixed RS slices in a fixed order, in fp64).
 #include "conv_common.cuh"
+#include "bn_tail.cuh"
 
 namespace nunet {
 
 constexpr int kRS = 32;  // row slices per channel group
 constexpr int kDirectRows = 1024;  // up to here one CTA per 32 channels reduces the partial rows directly
-
-struct BnFinalizeArgs {
-    int mode;  // 0: forward statistics -> apply coefficients ; 1: backward sums -> dgamma/dbeta + loader coefficients
-    double count;
-    const float* gamma;
-    const float* beta;
-    const float* conv_bias;
-    float* running_mean;
-    float* running_var;
-    float momentum, eps;
-    float* scale;
-    float* shift;
-    float* save_mean;
-    float* save_invstd;
-    // mode 1 (inputs: gamma, save_mean, save_invstd ; sums S1 = sum g_z, S2 = sum g_z*yhat)
-    float* dgamma;
-    float* dbeta;
-    float* k1;
-    float* k2;
-    float* k3;
-    float grad_scale;  // mode 1: multiplies dgamma / dbeta (1/world_size under SyncBN, see dist.py)
-};
-
-// BatchNorm backward (nn.BatchNorm2d, train): dbeta = S1, dgamma = S2,
-//   g_y = gamma*r*(g_z - S1/M - yhat*S2/M),  yhat = (y-mean)*r   =>   g_y = k1*g_z + k2*y + k3.
-__device__ __forceinline__ void bn_backward_channel(const BnFinalizeArgs& a, int c, double S1, double S2) {
-    const double g = a.gamma[c], r = a.save_invstd[c], mu = a.save_mean[c], M = a.count;
-    a.dbeta[c] = (float)(S1 * a.grad_scale);
-    a.dgamma[c] = (float)(S2 * a.grad_scale);
-    a.k1[c] = (float)(g * r);
-    a.k2[c] = (float)(-g * r * r * S2 / M);
-    a.k3[c] = (float)(-g * r * S1 / M + g * r * r * mu * S2 / M);
-}
-
-__device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS) {
-    if (a.mode == 1) { bn_backward_channel(a, c, S, SS); return; }
-    const double mean = S / a.count;
-    double var = SS / a.count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    const float sc = a.gamma[c] * invstd;
-    a.scale[c] = sc;
-    a.shift[c] = a.beta[c] - (float)mean * sc;
-    if (a.save_mean) a.save_mean[c] = (float)mean;
-    if (a.save_invstd) a.save_invstd[c] = invstd;
-    if (a.running_mean) {
-        const double b = a.conv_bias ? (double)a.conv_bias[c] : 0.0;  // the dropped conv bias only shifts the mean
-        a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * (mean + b));
-        const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
-        a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
-    }
-}
 
 // grid (C/32, kRS), block 256 = 32 channels x 8 row lanes.  part: [rows][2][C].
 // sums_out (optional): [2][C] fp64 — the cross-rank SyncBN exchange buffer.  fin.gamma == nullptr -> reduce only.

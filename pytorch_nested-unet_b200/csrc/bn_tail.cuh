@@ -1,0 +1,114 @@
+// BatchNorm finalisation as the TAIL of the kernel that produced the per-CTA partial sums (conv epilogue statistics in forward,
+// gradient-router sums in backward): the last CTA to finish (device-wide atomic counter, self-resetting) reduces the partial rows
+// in a fixed order in fp64 — bitwise deterministic whichever CTA happens to be last — and emits the per-channel coefficients the
+// next kernel consumes.  No separate finalize launch sits between a conv and its consumer any more (60 launches per step in round 1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nunet {
+
+struct BnFinalizeArgs {
+    int mode;  // 0: forward statistics -> apply coefficients ; 1: backward sums -> dgamma/dbeta + g_y coefficients
+    double count;
+    const float* gamma;
+    const float* beta;
+    const float* conv_bias;
+    float* running_mean;
+    float* running_var;
+    float momentum, eps;
+    float* scale;
+    float* shift;
+    float* save_mean;
+    float* save_invstd;
+    // mode 1 (inputs: gamma, save_mean, save_invstd ; sums S1 = sum g_z, S2 = sum g_z*yhat)
+    float* dgamma;
+    float* dbeta;
+    float* k1;
+    float* k2;
+    float* k3;
+    float grad_scale;  // mode 1: multiplies dgamma / dbeta (1/world_size under SyncBN, see dist.py)
+};
+
+struct BnTail {
+    unsigned* counter;   // nullptr: no tail (the caller launches nunet_bn_finalize_train / nunet_bn_backward_reduce itself)
+    double* sums_out;    // optional [2][C] fp64 (SyncBN exchange buffer)
+    BnFinalizeArgs fin;  // fin.gamma == nullptr: only sums_out is produced
+};
+
+// BatchNorm backward (nn.BatchNorm2d, train): dbeta = S1, dgamma = S2,
+//   g_y = gamma*r*(g_z - S1/M - yhat*S2/M),  yhat = (y-mean)*r   =>   g_y = k1*g_z + k2*y + k3.
+__device__ __forceinline__ void bn_backward_channel(const BnFinalizeArgs& a, int c, double S1, double S2) {
+    const double g = a.gamma[c], r = a.save_invstd[c], mu = a.save_mean[c], M = a.count;
+    a.dbeta[c] = (float)(S1 * a.grad_scale);
+    a.dgamma[c] = (float)(S2 * a.grad_scale);
+    a.k1[c] = (float)(g * r);
+    a.k2[c] = (float)(-g * r * r * S2 / M);
+    a.k3[c] = (float)(-g * r * S1 / M + g * r * r * mu * S2 / M);
+}
+
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS) {
+    if (a.mode == 1) { bn_backward_channel(a, c, S, SS); return; }
+    const double mean = S / a.count;
+    double var = SS / a.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    const float sc = a.gamma[c] * invstd;
+    a.scale[c] = sc;
+    a.shift[c] = a.beta[c] - (float)mean * sc;
+    if (a.save_mean) a.save_mean[c] = (float)mean;
+    if (a.save_invstd) a.save_invstd[c] = invstd;
+    if (a.running_mean) {
+        const double b = a.conv_bias ? (double)a.conv_bias[c] : 0.0;  // the dropped conv bias only shifts the mean
+        a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * (mean + b));
+        const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+        a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
+    }
+}
+
+// Executed by the 256 threads `tid` = 0..255 of a CTA that share named barrier `bar_id`, AFTER they have written the CTA's own
+// row(s) of part[rows][2][C] (C a multiple of 32, <= 512).  `scratch`: >= 8 KB + 16 B of shared memory that is free at this point.
+// total_ctas = CTAs of the grid (every one of them must come through here exactly once).
+// The reduction is latency-bound (one CTA, L2 loads): a thread owns four adjacent columns of the 2C-wide rows (one 16-byte load per
+// row) and every L-th row, and keeps eight loads in flight; the L row lanes are then combined in a fixed order.
+__device__ __forceinline__ void bn_tail_run(const BnTail& t, const float* part, int rows, int C, unsigned total_ctas, int tid, int bar_id,
+                                            void* scratch) {
+    double* sh = reinterpret_cast<double*>(scratch);                      // [L][2C] partial sums (<= 1024 doubles)
+    volatile int* flag = reinterpret_cast<volatile int*>(sh + 1024);
+    __threadfence();                                                      // this CTA's partial row is visible device-wide ...
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    if (tid == 0) *flag = (atomicAdd(t.counter, 1u) == total_ctas - 1) ? 1 : 0;   // ... before it is counted
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    if (!*flag) return;
+    __threadfence();
+    const int groups = C >> 1;              // 16-byte column groups per row (2C floats)
+    const int L = 256 / groups;             // row lanes: 16 (C = 32) ... 1 (C = 512)
+    const int g = tid % groups, lane = tid / groups;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < L) {
+        const float4* base = reinterpret_cast<const float4*>(part) + g;
+        constexpr int U = 8;
+        for (int r0 = lane; r0 < rows; r0 += L * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + u * L;
+                v[u] = (r < rows) ? __ldcg(base + (size_t)r * groups) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { acc[0] += (double)v[u].x; acc[1] += (double)v[u].y; acc[2] += (double)v[u].z; acc[3] += (double)v[u].w; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sh[(size_t)lane * 2 * C + g * 4 + e] = acc[e];
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    for (int c = tid; c < C; c += 256) {
+        double S = 0.0, SS = 0.0;
+        for (int l = 0; l < L; ++l) { S += sh[(size_t)l * 2 * C + c]; SS += sh[(size_t)l * 2 * C + C + c]; }
+        if (t.sums_out) { t.sums_out[c] = S; t.sums_out[C + c] = SS; }
+        if (t.fin.gamma) bn_finalize_channel(t.fin, c, S, SS);
+    }
+    if (tid == 0) *t.counter = 0;   // self-resetting for the next launch
+}
+
+}  // namespace nunet

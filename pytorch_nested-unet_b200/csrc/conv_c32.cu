@@ -41,6 +41,7 @@ struct C32Params {
     const void* wpack;
     __nv_bfloat16* out;
     float* stat_part;            // [gridDim.x][2][32] or null
+    BnTail tail;                 // BatchNorm finalisation by the last CTA
 };
 
 constexpr int kC32Threads = 320;
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                 for (int q = 0; q < 4; ++q) a += s_red[((h * 4 + q) * 2 + which) * 16 + i];
                 p.stat_part[((size_t)blockIdx.x * 2 + which) * 32 + c] = a;
             }
+            if (p.tail.counter) bn_tail_run(p.tail, p.stat_part, (int)gridDim.x, 32, gridDim.x, threadIdx.x, 2, sA);   // operand stages are idle: free scratch
         }
     }
 
@@ -320,6 +322,7 @@ int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStr
     p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
     p.box_rows = t.box_rows; p.S = t.S; p.res_b = t.res_b; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
     p.wpack = d->wpack; p.out = (__nv_bfloat16*)d->out; p.stat_part = d->stat_part;
+    p.tail = make_bn_tail(d->bn);
     for (int i = 0; i < d->num_src; ++i) {
         p.srcC[i] = d->src[i].C;
         if (encode_nhwc_map(&p.xmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, t.PW, 64, t.box_rows, 1) != 0) return NUNET_E_UNSUPPORTED;

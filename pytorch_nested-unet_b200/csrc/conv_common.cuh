@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
+#include "bn_tail.cuh"
 #include "../../include/nunet_b200.h"
 
 namespace nunet {
@@ -24,10 +25,36 @@ struct ConvParams {
     int T, NT, CK, S, P, nchunks, cin_pad, Cout, num_src, tmem_cols, ntg;
     int res_b;          // 1: single K chunk, the weight block is fetched once per CTA and stays resident
     int a_stage_bytes;  // TMA mode: bytes of one A stage ((P + Wp) rows of 64 B, rounded to 1 KB)
+    int epi_warps;      // TMA mode: warps that drain TMEM (16, or 8 where the transpose scratch of 16 does not fit)
     ConvSrc src[NUNET_MAX_SRC];
     const void* wpack;
     void* out;
     float* stat_part;
+    BnTail tail;        // BatchNorm finalisation by the last CTA (tail.counter != nullptr)
+    // fused block-internal gradient router (dgrad of a block's second conv): out = dX * [mask_scale*mask_y + mask_shift > 0]
+    const void* mask_y;
+    const float *mask_scale, *mask_shift, *mask_mean, *mask_invstd;
+    // plain epilogue: output channels scattered to one dense tensor per concatenated source of the forward conv
+    void* out_seg[NUNET_MAX_SRC];
+    int out_seg_c[NUNET_MAX_SRC];
+    int num_out_seg;
 };
+
+// host: C-ABI descriptor -> kernel parameter block
+static inline BnTail make_bn_tail(const nunet_bn_tail_t& b) {
+    BnTail t{};
+    t.counter = b.counter;
+    t.sums_out = b.sums_out;
+    t.fin.mode = 0; t.fin.count = b.count; t.fin.gamma = b.gamma; t.fin.beta = b.beta; t.fin.conv_bias = b.conv_bias;
+    t.fin.running_mean = b.running_mean; t.fin.running_var = b.running_var; t.fin.momentum = b.momentum; t.fin.eps = b.eps;
+    t.fin.scale = b.scale; t.fin.shift = b.shift; t.fin.save_mean = b.save_mean; t.fin.save_invstd = b.save_invstd;
+    return t;
+}
+static inline bool bn_tail_ok(const nunet_bn_tail_t& b, const float* stat_part) {
+    if (!b.counter) return true;
+    if (!stat_part || b.count <= 0) return false;
+    if (b.gamma) return b.beta && b.scale && b.shift;
+    return b.sums_out != nullptr;
+}
 
 }  // namespace nunet

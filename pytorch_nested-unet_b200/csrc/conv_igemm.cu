@@ -25,12 +25,46 @@
 namespace nunet {
 
 // ------------------------------------------------------------------------------------------------ kernel
-constexpr int kProducerWarps = 8;                 // warps 0-7 : stage the transformed input halo
-constexpr int kEpilogueWarp0 = 8;                 // warps 8-15: TMEM -> bf16 NHWC + BN statistics (warp % 4 = TMEM lane quadrant,
-constexpr int kEpilogueWarps = 8;                 //             two warps per quadrant split the column slabs)
 constexpr int kMmaWarp = 16;                      // warp 16   : tcgen05.mma issuer (one lane) + TMEM owner
-constexpr int kFetchWarp = 17;                    // warp 17   : weight fetcher (cp.async.bulk, one lane)
+constexpr int kFetchWarp = 17;                    // warp 17   : weight fetcher (cp.async.bulk, one lane; TMA mode: the activation tensor loads too)
 constexpr int kThreads = 18 * 32;
+// Warps 0-15.  Loader modes: warps 0-7 stage the transformed input halo, warps 8-15 drain TMEM (warp % 4 = TMEM lane quadrant, two
+// warps per quadrant).  TMA mode (MODE_ACT_TMA): nothing is staged by threads, so ALL SIXTEEN warps drain TMEM (four per quadrant) —
+// the epilogue of the level-0 layers is a latency chain (tcgen05.ld -> convert -> store) and eight warps could not hide it
+// (profiles/r02_ncu_stalls.md: 23 % of the dgrad 32->192 samples sat on the store waiting for its shared-memory transposition).
+constexpr int kProducerWarps = 8;
+#ifndef NUNET_DBG_SKIP
+#define NUNET_DBG_SKIP 0      // experiment builds only (tools/ab_epilogue.sh): 1 no epilogue stores, 2 no MMAs, 4 no activation tensor loads
+#endif
+constexpr int kEpiSlot = 32 * 80;                 // bytes of transpose scratch per epilogue warp
+
+// Shared-memory carve-up, identical on host (sizing) and device.
+struct SmemLayout {
+    uint32_t a_bytes, b_bytes, off_b, off_tab, off_coef, off_mask, off_stat, off_seg, off_epi, off_bar, total;
+};
+__host__ __device__ inline SmemLayout conv_smem_layout(bool tma, int T, int NT, int CK, int S, int P, int cin_pad, int a_stage_bytes, bool res_b, int epi_warps) {
+    SmemLayout L;
+    L.a_bytes = tma ? (uint32_t)a_stage_bytes : (uint32_t)(CK / 8) * P * 16u;
+    L.b_bytes = 9u * CK * NT * 2u;
+    uint32_t o = (uint32_t)S * L.a_bytes;
+    L.off_b = o;       o += (res_b ? 1u : (uint32_t)S) * L.b_bytes;
+    L.off_tab = o;     o += tma ? 0u : 2u * P * 8u;                    // position tables (loader modes only)
+    L.off_coef = o;    o += tma ? 0u : (uint32_t)cin_pad * 12u;        // per-input-channel loader coefficients
+    L.off_mask = o;    o += 2u * NT * 4u;                              // ReLU-mask coefficients of the fused-router epilogue
+    L.off_seg = o;     o += 24u * 16u;                                 // output segment of each 32-channel slab {pointer, pitch}
+    // a launch runs either the plain epilogue (transpose scratch) or a statistics epilogue (per-thread-owned slots [<= 8 rows][2][NT])
+    const uint32_t stat_b = 8u * 2u * NT * 4u, epi_b = (uint32_t)epi_warps * kEpiSlot;
+    L.off_stat = o;
+    L.off_epi = o;     o += stat_b > epi_b ? stat_b : epi_b;
+    L.off_bar = o;     o += (2u * S + 6u) * 8u + 16u;
+    L.total = o + 128u;
+    return L;
+}
+
+struct OutSeg {
+    __nv_bfloat16* base;   // already offset to the slab's first channel inside its segment
+    int pitch, pad_;
+};
 
 // Optional wait/work cycle accounting per warp role (build with -DNUNET_PROFILE_WAITS; tools/prof_waits.py reads it).
 #ifdef NUNET_PROFILE_WAITS
@@ -44,36 +78,40 @@ __device__ unsigned long long g_wait_prof[16];
 #define PROF_FLUSH(base) {}
 #endif
 
-// Persistent: CTA (x, n_tile) processes tile groups x, x+gridDim.x, ... of 128*T positions each.  Accumulators and the
-// position table are double-buffered so the producers / tensor core work on group i+1 while the epilogue drains group i.
+// Persistent: CTA (x, n_tile) processes tile groups x, x+gridDim.x, ... of 128*T positions each.  Accumulators (and, in the loader
+// modes, the position table) are double-buffered so the operand pipeline and the tensor core work on group i+1 while the epilogue
+// drains group i.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cgs = p.CK >> 3;
     constexpr bool kTma = (MODE == MODE_ACT_TMA);
-    // TMA mode: an A stage is (P + Wp) whole padded rows of 32 channels (64-byte rows, 64B hardware swizzle) written by
-    // tensor loads; otherwise the no-swizzle [channel group][position][8] layout written by the producer warps.
-    const uint32_t a_bytes = kTma ? (uint32_t)p.a_stage_bytes : (uint32_t)cgs * p.P * 16u;
-    const uint32_t b_bytes = 9u * p.CK * p.NT * 2u;
-
-    uint8_t* sA = smem;
+    const int kEpi = kTma ? p.epi_warps : 8;       // epilogue warps (TMA mode: 16 where their transpose scratch fits, else 8)
+    const int kParts = kEpi >> 2;                  // warps per TMEM lane quadrant
     // A single K chunk (Cin <= 32: the level-0 second convs and every level-0 dgrad): the weight block is the same for every tile
     // group, so it is fetched ONCE per CTA and stays resident; only the activation stages cycle.
     const bool res_b = p.res_b != 0;
+    const SmemLayout L = conv_smem_layout(kTma, p.T, p.NT, p.CK, p.S, p.P, p.cin_pad, p.a_stage_bytes, res_b, kEpi);
+    // TMA mode: an A stage is (P + Wp) whole padded rows of 32 channels (64-byte rows, 64B hardware swizzle) written by
+    // tensor loads; otherwise the no-swizzle [channel group][position][8] layout written by the producer warps.
+    const uint32_t a_bytes = L.a_bytes, b_bytes = L.b_bytes;
     const uint32_t b_stride = res_b ? 0u : b_bytes;
-    uint8_t* sB = sA + (size_t)p.S * a_bytes;
-    PixInfo* pixtab = reinterpret_cast<PixInfo*>(sB + (size_t)(res_b ? 1 : p.S) * b_bytes);  // [2][P]
-    float* s_scale = reinterpret_cast<float*>(pixtab + 2 * p.P);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + L.off_b;
+    PixInfo* pixtab = reinterpret_cast<PixInfo*>(smem + L.off_tab);  // [2][P]
+    float* s_scale = reinterpret_cast<float*>(smem + L.off_coef);
     float* s_shift = s_scale + p.cin_pad;
     float* s_k2 = s_shift + p.cin_pad;
-    float* s_stat = s_k2 + p.cin_pad;  // [8 epilogue warps][2][NT], each slot owned by one thread (deterministic)
-    uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_stat + 16 * p.NT);  // [8 epilogue warps][32 rows][80 B] transpose scratch
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + kEpilogueWarps * 32 * 80);
+    float* s_mask = reinterpret_cast<float*>(smem + L.off_mask);     // [2][NT]: scale, shift of the masking BatchNorm
+    float* s_stat = reinterpret_cast<float*>(smem + L.off_stat);
+    OutSeg* s_seg = reinterpret_cast<OutSeg*>(smem + L.off_seg);
+    uint8_t* s_epi = smem + L.off_epi;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* full = bars;                 // [S]  producers + fetcher -> MMA
     uint64_t* empty = bars + p.S;          // [S]  MMA -> producers + fetcher
     uint64_t* acc_full = bars + 2 * p.S;   // [2]  MMA -> epilogue
-    uint64_t* acc_empty = acc_full + 2;    // [2]  epilogue -> MMA + producers (accumulator AND table buffer are free)
+    uint64_t* acc_empty = acc_full + 2;    // [2]  epilogue -> MMA (+ producers: accumulator AND table buffer are free)
     uint64_t* tab_full = acc_empty + 2;    // [2]  producers -> epilogue (position table of the group is written)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tab_full + 2);
 
@@ -89,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&acc_full[b], 1);
-                mbar_init(&acc_empty[b], kEpilogueWarps);
+                mbar_init(&acc_empty[b], kEpi);
                 mbar_init(&tab_full[b], kProducerWarps);
             }
             mbar_init_fence();
@@ -104,27 +142,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
         }
     }
     {
-        int cbase = 0;
-        for (int si = 0; si < p.num_src; ++si) {
-            const ConvSrc& s = p.src[si];
-            const int cpad = (s.kind == NUNET_SRC_INPUT) ? 16 : s.C;
-            for (int c = threadIdx.x; c < cpad; c += kThreads) {
-                const bool has = (s.kind != NUNET_SRC_INPUT) && s.scale != nullptr;
-                s_scale[cbase + c] = has ? s.scale[c] : 1.f;
-                s_shift[cbase + c] = has ? s.shift[c] : 0.f;
-                s_k2[cbase + c] = (s.kind == NUNET_SRC_GRAD) ? s.k2[c] : 0.f;
+        if constexpr (!kTma) {
+            int cbase = 0;
+            for (int si = 0; si < p.num_src; ++si) {
+                const ConvSrc& s = p.src[si];
+                const int cpad = (s.kind == NUNET_SRC_INPUT) ? 16 : s.C;
+                for (int c = threadIdx.x; c < cpad; c += kThreads) {
+                    const bool has = (s.kind != NUNET_SRC_INPUT) && s.scale != nullptr;
+                    s_scale[cbase + c] = has ? s.scale[c] : 1.f;
+                    s_shift[cbase + c] = has ? s.shift[c] : 0.f;
+                    s_k2[cbase + c] = (s.kind == NUNET_SRC_GRAD) ? s.k2[c] : 0.f;
+                }
+                cbase += cpad;
             }
-            cbase += cpad;
         }
         for (int i = threadIdx.x; i < 16 * p.NT; i += kThreads) s_stat[i] = 0.f;
+        if (p.mask_y)
+            for (int c = threadIdx.x; c < p.NT; c += kThreads) {
+                s_mask[c] = p.mask_scale[n_tile * p.NT + c];
+                s_mask[p.NT + c] = p.mask_shift[n_tile * p.NT + c];
+            }
+        // where each 32-channel slab of this N tile goes: the dense output, or the per-source segment that owns those channels
+        for (int sl = threadIdx.x; sl < (p.NT >> 5); sl += kThreads) {
+            int gc = n_tile * p.NT + sl * 32;
+            OutSeg o;
+            o.base = reinterpret_cast<__nv_bfloat16*>(p.out) + gc;
+            o.pitch = p.Cout;
+            o.pad_ = 0;
+            for (int k = 0; k < p.num_out_seg; ++k) {
+                if (gc < p.out_seg_c[k]) { o.base = reinterpret_cast<__nv_bfloat16*>(p.out_seg[k]) + gc; o.pitch = p.out_seg_c[k]; break; }
+                gc -= p.out_seg_c[k];
+            }
+            s_seg[sl] = o;
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const bool is_epi = kTma ? (warp < kEpi) : (warp >= kProducerWarps && warp < 16);
 
-    if (warp < kProducerWarps) {
-        // =============================== producers
+    if (!kTma && warp < kProducerWarps) {
+        // =============================== producers (loader modes)
         const int nblk = (p.P + 7) >> 3;
         const int pl = lane & 7, r = lane >> 3;
         // CK=32: the four lane groups of a warp take the four channel groups of one 8-position block;
@@ -146,7 +205,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (lane == 0) mbar_arrive(&tab_full[b]);
             PROF_MARK(1)
-            if constexpr (kTma) continue;  // operands are staged by the fetch warp's tensor loads
             int si = 0, src_c0 = 0;  // current source and its first concatenated channel
             for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                 const int s = cc % p.S;
@@ -175,21 +233,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             }
         }
         if (threadIdx.x == 0) PROF_FLUSH(0)
-    } else if (warp < kMmaWarp) {
-        // =============================== epilogue (4 warps, one TMEM lane quadrant each)
-        const int lq = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
-        const int nslab = p.NT >> 4;  // 16-channel slabs
+    } else if (is_epi) {
+        // =============================== epilogue: kEpi warps, kParts per TMEM lane quadrant
+        const int eidx = kTma ? warp : warp - kProducerWarps;
+        const int lq = eidx & 3, part = eidx >> 2;      // lq == warp % 4 in both numberings
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
         const bool want_stats = p.stat_part != nullptr;
-        float* my_stat = s_stat + (size_t)(warp - kEpilogueWarp0) * 2 * p.NT;
+        const bool masked = p.mask_y != nullptr;         // fused block-internal gradient router (dgrad of a block's second conv)
+        const __nv_bfloat16* mask_y = reinterpret_cast<const __nv_bfloat16*>(p.mask_y);
+        // statistic paths: 16-column slabs; a warp owns slab group sg (of G) and tile group tsel (of TG)
+        const int nslab = p.NT >> 4;
+        const int G = nslab < kParts ? nslab : kParts, TG = kParts / G;
+        const int sg = part % G, tsel = part / G;
+        float* my_stat = s_stat + (size_t)((lq * TG + tsel) * 2) * p.NT;   // slots written by this warp only (deterministic)
         int it = 0;
         PROF_DECL
         for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
             const int b = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
             const PixInfo* tab = pixtab + (size_t)b * p.P;
-            mbar_wait(&tab_full[b], k & 1);
+            const int q0 = tg * group_positions + lq * 32 + lane;   // this lane's output position in tile 0 of the group
+#ifdef NUNET_POLL1
+            if (lane == 0) { if constexpr (!kTma) mbar_wait(&tab_full[b], k & 1); mbar_wait(&acc_full[b], k & 1); }
+            __syncwarp();
+#else
+            if constexpr (!kTma) mbar_wait(&tab_full[b], k & 1);
             mbar_wait(&acc_full[b], k & 1);
+#endif
             PROF_MARK(0)
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);
@@ -198,107 +268,137 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                 // store would touch 32 different 128-byte lines per instruction; the 32x64 B tile is transposed through a padded
                 // per-warp smem scratch so that four lanes write one row's 64 contiguous bytes (8 lines per store instruction).
                 const int nslab32 = p.NT >> 5;
-                uint8_t* scratch = s_epi + (size_t)(warp - kEpilogueWarp0) * (32 * 80);
-                for (int t = 0; t < p.T; ++t) {
-                    const PixInfo pi = tab[t * 128 + lq * 32 + lane + p.Wp + 1];
-                    for (int cs = half; cs < nslab32; cs += 2) {
-                        uint32_t v[32];
-                        tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
-                        tmem_ld_wait();
+                uint8_t* scratch = s_epi + (size_t)eidx * kEpiSlot;
+                for (int wi = part; wi < p.T * nslab32; wi += kParts) {
+                    const int t = wi / nslab32, cs = wi - t * nslab32;
+                    int pix;
+                    if constexpr (kTma) pix = decode_position(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q).pix;
+                    else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
+                    uint32_t v[32];
+                    tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 o;
-                            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                            *reinterpret_cast<uint4*>(scratch + lane * 80 + j * 16) = o;
-                        }
-                        __syncwarp();
-                        __nv_bfloat16* obase = out + n_tile * p.NT + cs * 32 + (lane & 3) * 8;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int row = i * 8 + (lane >> 2);
-                            const int rpix = __shfl_sync(0xffffffffu, pi.pix, row);
-                            const uint4 o = *reinterpret_cast<const uint4*>(scratch + row * 80 + (lane & 3) * 16);
-                            if (rpix >= 0) *reinterpret_cast<uint4*>(obase + (size_t)rpix * p.Cout) = o;
-                        }
-                        __syncwarp();
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                        *reinterpret_cast<uint4*>(scratch + lane * 80 + j * 16) = o;
                     }
+                    __syncwarp();
+                    const OutSeg seg = s_seg[cs];
+                    __nv_bfloat16* obase = seg.base + (lane & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + (lane >> 2);
+                        const int rpix = __shfl_sync(0xffffffffu, pix, row);
+                        const uint4 o = *reinterpret_cast<const uint4*>(scratch + row * 80 + (lane & 3) * 16);
+                        if (rpix >= 0 && !(NUNET_DBG_SKIP & 1)) *reinterpret_cast<uint4*>(obase + (size_t)rpix * seg.pitch) = o;
+                    }
+                    __syncwarp();
                 }
             } else {
-            for (int cs = half; cs < nslab; cs += 2) {
-                float ssum[16], ssq[16];
+                for (int cs = sg; cs < nslab; cs += G) {
+                    float ssum[16], ssq[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
-                for (int t = 0; t < p.T; ++t) {
-                    const PixInfo pi = tab[t * 128 + lq * 32 + lane + p.Wp + 1];
-                    uint32_t v[16];
-                    tmem_ld16(acc + (uint32_t)(t * p.NT + cs * 16), v);
-                    tmem_ld_wait();
-                    if (pi.pix >= 0) {
-                        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pi.pix * p.Cout + n_tile * p.NT + cs * 16);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint4 o;
-                            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                            dst[j] = o;
+                    for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+                    const int gc = n_tile * p.NT + cs * 16;
+                    for (int t = tsel; t < p.T; t += TG) {
+                        int pix;
+                        if constexpr (kTma) pix = decode_position(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q).pix;
+                        else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
+                        uint32_t v[16];
+                        tmem_ld16(acc + (uint32_t)(t * p.NT + cs * 16), v);
+                        uint4 ym[2];
+                        if (masked && pix >= 0) {
+                            const uint4* ysrc = reinterpret_cast<const uint4*>(mask_y + (size_t)pix * p.Cout + gc);
+                            ym[0] = __ldg(ysrc);
+                            ym[1] = __ldg(ysrc + 1);
                         }
+                        tmem_ld_wait();
+                        if (pix >= 0) {
+                            float f[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float f = __uint_as_float(v[i]);
-                            ssum[i] += f;
-                            ssq[i] = fmaf(f, f, ssq[i]);
+                            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                            if (masked) {
+                                // g_z = dX * [scale*y + shift > 0]; sums: S1 = sum g_z, S2' = sum g_z*y (combined with mean / invstd at the end)
+                                float yv[16];
+                                unpack8(ym[0], *reinterpret_cast<float(*)[8]>(&yv[0]));
+                                unpack8(ym[1], *reinterpret_cast<float(*)[8]>(&yv[8]));
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float z = fmaf(yv[i], s_mask[cs * 16 + i], s_mask[p.NT + cs * 16 + i]);
+                                    f[i] = (z > 0.f) ? f[i] : 0.f;
+                                    ssum[i] += f[i];
+                                    ssq[i] = fmaf(f[i], yv[i], ssq[i]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    ssum[i] += f[i];
+                                    ssq[i] = fmaf(f[i], f[i], ssq[i]);
+                                }
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pix * p.Cout + gc);
+#pragma unroll
+                            for (int j = 0; j < ((NUNET_DBG_SKIP & 1) ? 0 : 2); ++j) {
+                                uint4 o;
+                                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                                dst[j] = o;
+                            }
                         }
                     }
-                }
-                // fold the two half-warps, then a transposing butterfly: lane L ends with the total of channel L & 15
+                    // fold the two half-warps, then a transposing butterfly: lane L ends with the total of channel L & 15
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
-                    ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
-                }
+                    for (int i = 0; i < 16; ++i) {
+                        ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
+                        ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
+                    }
 #pragma unroll
-                for (int off = 8; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
+                    for (int off = 8; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
 #pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float sa = up ? ssum[i] : ssum[i + off];
-                        const float ka = up ? ssum[i + off] : ssum[i];
-                        ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-                        const float sb = up ? ssq[i] : ssq[i + off];
-                        const float kb = up ? ssq[i + off] : ssq[i];
-                        ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+                        for (int i = 0; i < off; ++i) {
+                            const float sa = up ? ssum[i] : ssum[i + off];
+                            const float ka = up ? ssum[i + off] : ssum[i];
+                            ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+                            const float sb = up ? ssq[i] : ssq[i + off];
+                            const float kb = up ? ssq[i + off] : ssq[i];
+                            ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+                        }
+                    }
+                    if (lane < 16) {  // this thread is the only writer of these two slots, groups are visited in a fixed order
+                        my_stat[cs * 16 + lane] += ssum[0];
+                        my_stat[p.NT + cs * 16 + lane] += ssq[0];
                     }
                 }
-                if (lane < 16) {  // this thread is the only writer of these two slots, groups are visited in a fixed order
-                    my_stat[cs * 16 + lane] += ssum[0];
-                    my_stat[p.NT + cs * 16 + lane] += ssq[0];
-                }
-            }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[b]);
             PROF_MARK(1)
         }
-        if (warp == kEpilogueWarp0 && lane == 0) PROF_FLUSH(4)
+        if (eidx == 0 && lane == 0) PROF_FLUSH(4)
         if (want_stats) {
-            asm volatile("bar.sync 2, 256;" ::: "memory");  // the 8 epilogue warps only
+            asm volatile("bar.sync 2, %0;" ::"r"(kEpi * 32) : "memory");  // the epilogue warps only
+            const int tid_e = eidx * 32 + lane;
             float* dst = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n_tile * p.NT;
-            for (int c = threadIdx.x - kEpilogueWarp0 * 32; c < p.NT; c += 256) {
+            for (int c = tid_e; c < p.NT; c += kEpi * 32) {
                 float a = 0.f, bb = 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4 * TG; ++q) {       // fixed order over the rows of slots
                     a += s_stat[(q * 2 + 0) * p.NT + c];
                     bb += s_stat[(q * 2 + 1) * p.NT + c];
                 }
+                if (masked) bb = p.mask_invstd[n_tile * p.NT + c] * (bb - p.mask_mean[n_tile * p.NT + c] * a);   // sum g_z*yhat
                 dst[c] = a;
                 dst[p.Cout + c] = bb;
             }
+            // BatchNorm finalisation by the last CTA of the grid (all operand stages are idle by now: sA is free scratch)
+            if (p.tail.counter && tid_e < 256) bn_tail_run(p.tail, p.stat_part, (int)gridDim.x, p.Cout, gridDim.x * gridDim.y, tid_e, 3, sA);
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer
@@ -339,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                             const uint32_t d_addr = acc + (uint32_t)(t * p.NT);
                             uint32_t b_lo = b_lo0;
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
+                            for (int tap = 0; tap < ((NUNET_DBG_SKIP & 2) ? 1 : 9); ++tap) {
                                 const uint32_t a_lo = a_base + (woff + (uint32_t)(t * 128) + tapoff[tap]) * 4u;   // 64 B per position
                                 umma_bf16_lohi(d_addr, a_lo, a_hi_sw, b_lo, hi, idesc, (uint32_t)((chunk | tap) != 0));
                                 umma_bf16_lohi(d_addr, a_lo + 2u, a_hi_sw, b_lo + b_step, hi, idesc, 1u);         // next 16 channels: +32 B
@@ -377,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             PROF_FLUSH(8)
         }
         __syncwarp();
-    } else {
+    } else if (warp == kFetchWarp) {
         // =============================== weight fetcher (bulk async copy engine)
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)n_tile * p.nchunks * b_bytes;
@@ -402,10 +502,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                         const int cglob = chunk * 32;
                         while (cglob >= src_c0 + p.src[si].C) { src_c0 += p.src[si].C; ++si; }
                         const bool fetch_b = !res_b || cc == 0;
-                        mbar_arrive_expect_tx(&full[s], (fetch_b ? b_bytes : 0u) + (uint32_t)nrows * row_bytes);
+                        mbar_arrive_expect_tx(&full[s], (fetch_b ? b_bytes : 0u) + ((NUNET_DBG_SKIP & 4) ? 0u : (uint32_t)nrows * row_bytes));
                         if (fetch_b) bulk_g2s(sB + (size_t)s * b_stride, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
                         uint8_t* dstA = sA + (size_t)s * a_bytes;
-                        for (int r = 0; r < nrows; ++r) {
+                        for (int r = 0; r < ((NUNET_DBG_SKIP & 4) ? 0 : nrows); ++r) {
                             const int R = R_lo + r;
                             // padded row R = n*(H+1) + 1 + y ; separator rows (y = -1) and rows outside the batch are out of bounds -> zeros
                             const int n = (R >= 0) ? R / p.Hp1 : -1;
@@ -526,20 +626,26 @@ static int pick_nt(int C) {
     return 0;
 }
 
-// Resident weight block for single-chunk layers: measured 6-13 % faster for N tiles >= 128 (the 55-110 KB block no longer
-// cycles through the stage ring), slower for narrower tiles (tools/time_conv.py) -> only used for NT >= 128.
+// Resident weight block for single-chunk layers: measured 3-13 % faster for N tiles >= 96 (the 55-110 KB block no longer
+// cycles through the stage ring; it also frees a stage's worth of shared memory for the sixteen-warp epilogue scratch), no gain for
+// narrower tiles (profiles/r02_conv_tiling_sweep.log) -> used for NT >= 96.
 static bool resident_weights(int NT) {
     static const bool on = getenv("NUNET_NO_RESIDENT_B") == nullptr;
 #ifdef NUNET_EXPERIMENT
     if (const char* e = getenv("NUNET_RESB_MIN_NT")) return on && NT >= atoi(e);
 #endif
-    return on && NT >= 128;
+    return on && NT >= 96;
 }
 
 static size_t conv_smem_bytes(int T, int NT, int CK, int S, int P, int cin_pad) {
-    size_t a = (size_t)(CK / 8) * P * 16, b = (size_t)9 * CK * NT * 2;
-    const size_t stages = (cin_pad == CK && resident_weights(NT)) ? S * a + b : S * (a + b);   // one K chunk: resident weight block
-    return stages + (size_t)2 * P * 8 + (size_t)cin_pad * 12 + (size_t)16 * NT * 4 + 8 * 32 * 80 + (2 * S + 6) * 8 + 16 + 128;
+    return conv_smem_layout(false, T, NT, CK, S, P, cin_pad, 0, cin_pad == CK && resident_weights(NT), 8).total;
+}
+
+static size_t conv_tma_a_stage(int P, int W) {
+    return (((size_t)(P + 2 * (W + 2)) * 64) + 1023) & ~(size_t)1023;  // whole padded rows: up to 2 Wp - 2 extra positions
+}
+static size_t conv_tma_smem_bytes(int T, int NT, int S, int P, int W, int cin_pad, int epi_warps) {
+    return (size_t)conv_smem_layout(true, T, NT, 32, S, P, cin_pad, (int)conv_tma_a_stage(P, W), cin_pad == 32 && resident_weights(NT), epi_warps).total + 1024;
 }
 
 extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_conv_plan_t* pl) {
@@ -570,7 +676,12 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
             // deeper rings measured 35-50 % SLOWER (32->192 at 96x96: S=2 0.264 ms, S=3 0.399 ms; profiles/r02_conv_tiling_sweep.log)
             for (int S = ((nch == 1 && resident_weights(NT)) ? 2 : 3); S >= minS; --S) {
                 if ((size_t)P * 16 >= (1u << 18)) continue;
-                if (conv_smem_bytes(T, NT, CK, S, P, cin_pad) <= budget) { bestT = T; bestCK = CK; bestS = S; break; }
+                if (conv_smem_bytes(T, NT, CK, S, P, cin_pad) > budget) continue;
+                // rows that fit a tensor-load box: the same (T, S) must also fit the TMA variant's larger stages (copy-mode sources
+                // then run on tensor loads with sixteen epilogue warps; a deeper ring that only fits the cp.async layout is slower)
+                if (CK == 32 && W + 2 <= 256 && conv_tma_smem_bytes(T, NT, S, P, W, cin_pad, 8) > 227 * 1024) continue;
+                bestT = T; bestCK = CK; bestS = S;
+                break;
             }
         }
     }
@@ -601,11 +712,13 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     // TMA variant of the same tiling: A stage = (P + Wp) rows of 64 B rounded to 1 KB (first in shared memory: 1 KB aligned)
     pl->tma_a_stage_bytes = 0;
     pl->tma_smem_bytes = 0;
+    pl->tma_epi_warps = 0;
     if (bestCK == 32) {
-        const size_t a_tma = (((size_t)(pl->P + 2 * (W + 2)) * 64) + 1023) & ~(size_t)1023;  // whole rows: up to 2 Wp - 2 extra positions
-        const size_t a_old = (size_t)4 * pl->P * 16;
-        const size_t total = (size_t)pl->smem_bytes + bestS * (a_tma - a_old) + 1024;
-        if (total <= 227 * 1024) { pl->tma_a_stage_bytes = (int)a_tma; pl->tma_smem_bytes = (int)total; }
+        const size_t a_tma = conv_tma_a_stage(pl->P, W);
+        for (int ew = 16; ew >= 8 && !pl->tma_smem_bytes; ew -= 8) {
+            const size_t total = conv_tma_smem_bytes(bestT, NT, bestS, pl->P, W, cin_pad, ew);
+            if (total <= 227 * 1024) { pl->tma_a_stage_bytes = (int)a_tma; pl->tma_smem_bytes = (int)total; pl->tma_epi_warps = ew; }
+        }
     }
     int cols = 2 * bestT * NT, tc = 32;
     while (tc < cols) tc <<= 1;
@@ -626,7 +739,7 @@ static int launch_conv(const ConvParams& p, const nunet_conv_plan_t& pl, cudaStr
 int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStream_t stream);
 
 extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
-    if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->wpack || !d->out) return NUNET_E_BADARG;
+    if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->wpack || (!d->out && d->num_out_seg <= 0)) return NUNET_E_BADARG;
     int cin = 0;
     for (int i = 0; i < d->num_src; ++i) {
         const nunet_src_t& s = d->src[i];
@@ -656,6 +769,32 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
         p.src[i].C = d->src[i].C; p.src[i].kind = d->src[i].kind;
     }
     p.wpack = d->wpack; p.out = d->out; p.stat_part = d->stat_part;
+    if (!bn_tail_ok(d->bn, d->stat_part)) return NUNET_E_BADARG;
+    p.tail = make_bn_tail(d->bn);
+    if (d->num_out_seg < 0 || d->num_out_seg > NUNET_MAX_SRC) return NUNET_E_BADARG;
+    if (d->num_out_seg > 0) {   // output channels scattered to one dense tensor per segment (plain epilogue only)
+        int tot = 0;
+        for (int i = 0; i < d->num_out_seg; ++i) {
+            if (!d->out_seg[i] || d->out_seg_c[i] < 32 || d->out_seg_c[i] % 32 != 0) return NUNET_E_BADARG;
+            p.out_seg[i] = d->out_seg[i]; p.out_seg_c[i] = d->out_seg_c[i];
+            tot += d->out_seg_c[i];
+        }
+        if (tot != d->Cout || d->stat_part || d->mask_y) return NUNET_E_BADARG;
+        p.num_out_seg = d->num_out_seg;
+    }
+    if (d->mask_y) {            // fused block-internal gradient router: ReLU mask of the producer + BatchNorm-backward sums
+        if (!d->stat_part || !d->mask_scale || !d->mask_shift || !d->mask_mean || !d->mask_invstd || d->bn.counter) return NUNET_E_BADARG;
+        p.mask_y = d->mask_y; p.mask_scale = d->mask_scale; p.mask_shift = d->mask_shift; p.mask_mean = d->mask_mean; p.mask_invstd = d->mask_invstd;
+        const nunet_bn_bwd_tail_t& b = d->bn_bwd;
+        if (b.counter) {
+            if (b.count <= 0 || (b.gamma ? (!b.save_mean || !b.save_invstd || !b.dgamma || !b.dbeta || !b.k1 || !b.k2 || !b.k3) : !b.sums_out)) return NUNET_E_BADARG;
+            p.tail.counter = b.counter; p.tail.sums_out = b.sums_out;
+            p.tail.fin.mode = 1; p.tail.fin.count = b.count; p.tail.fin.gamma = b.gamma;
+            p.tail.fin.save_mean = const_cast<float*>(b.save_mean); p.tail.fin.save_invstd = const_cast<float*>(b.save_invstd);
+            p.tail.fin.dgamma = b.dgamma; p.tail.fin.dbeta = b.dbeta; p.tail.fin.k1 = b.k1; p.tail.fin.k2 = b.k2; p.tail.fin.k3 = b.k3;
+            p.tail.fin.grad_scale = b.grad_scale;
+        }
+    }
     p.res_b = (pl.nchunks == 1 && resident_weights(pl.NT)) ? 1 : 0;
     int kinds[NUNET_MAX_SRC];
     for (int i = 0; i < d->num_src; ++i) kinds[i] = d->src[i].kind;
@@ -669,7 +808,7 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
         case MODE_GRAD: return launch_conv<MODE_GRAD>(p, pl, (cudaStream_t)stream);
         case MODE_ACT: {
             if (d->wpack_layout == 1) {
-                if (!nunet_conv3x3_c32_eligible(d->N, d->H, d->W, cin, d->Cout)) return NUNET_E_BADARG;
+                if (!nunet_conv3x3_c32_eligible(d->N, d->H, d->W, cin, d->Cout) || d->mask_y || d->num_out_seg) return NUNET_E_BADARG;
                 return nunet_conv_c32_launch(d, cin, pl.grid_m, (cudaStream_t)stream);
             }
             // tensor-load path: box = (32 ch, W+2 px, 1, 1) per padded row, needs W+2 <= 256 and the CK=32 tiling
@@ -682,6 +821,7 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
                     nunet_conv_plan_t pt = pl;
                     pt.smem_bytes = pl.tma_smem_bytes;
                     p.a_stage_bytes = pl.tma_a_stage_bytes;
+                    p.epi_warps = pl.tma_epi_warps;
                     return launch_conv<MODE_ACT_TMA>(p, pt, (cudaStream_t)stream);
                 }
             }

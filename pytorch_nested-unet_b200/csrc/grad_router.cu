@@ -30,6 +30,7 @@ struct RouterParams {
     int K;
     __nv_bfloat16* gz;
     float* part;  // [gridDim.x][2][C]
+    BnTail tail;  // BatchNorm-backward coefficients by the last CTA
 };
 
 __device__ __forceinline__ void add8(float (&g)[8], const uint4& r, float w) {
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256, 2) grad_router_kernel(const RouterParams 
         }
         __syncthreads();
     }
+    if (p.tail.counter) bn_tail_run(p.tail, p.part, (int)gridDim.x, p.C, gridDim.x, threadIdx.x, 0, &red[0][0]);
 }
 
 // Specialised router for what the engine launches (no UP consumer: those go through up_transpose.cu first).  Same arithmetic
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(256, HAS_POOL ? 3 : 4) grad_router_fast_kernel
         }
         __syncthreads();
     }
+    if (p.tail.counter) bn_tail_run(p.tail, p.part, (int)gridDim.x, p.C, gridDim.x, threadIdx.x, 0, &red[0][0]);
 }
 
 }  // namespace nunet
@@ -329,7 +332,9 @@ using namespace nunet;
 extern "C" int nunet_grad_router_rows(int32_t N, int32_t H, int32_t W, int32_t C) {
     long long items = (long long)N * H * W * (C / 8);
     long long b = (items + 255) / 256;
-    if (b > 148 * 4) b = 148 * 4;
+    // the last CTA reduces rows x 2C partial sums in its tail: fewer rows for the wide (and small) deep layers
+    const long long cap = C <= 64 ? 148 * 4 : (C <= 128 ? 148 * 2 : 148);
+    if (b > cap) b = cap;
     return (int)(b < 1 ? 1 : b);
 }
 
@@ -360,6 +365,15 @@ extern "C" int nunet_grad_router(const nunet_router_desc_t* d, void* stream) {
     if ((long long)d->N * d->H * d->W * (d->C / 8) >= (1LL << 31) - (1LL << 22)) return NUNET_E_UNSUPPORTED;
     p.dlogits = d->dlogits; p.wh = d->wh; p.K = d->K;
     p.gz = (__nv_bfloat16*)d->gz; p.part = d->part;
+    if (d->bn.counter) {
+        const nunet_bn_bwd_tail_t& b = d->bn;
+        if (b.count <= 0 || (b.gamma ? (!b.save_mean || !b.save_invstd || !b.dgamma || !b.dbeta || !b.k1 || !b.k2 || !b.k3) : !b.sums_out)) return NUNET_E_BADARG;
+        p.tail.counter = b.counter; p.tail.sums_out = b.sums_out;
+        p.tail.fin.mode = 1; p.tail.fin.count = b.count; p.tail.fin.gamma = b.gamma;
+        p.tail.fin.save_mean = const_cast<float*>(b.save_mean); p.tail.fin.save_invstd = const_cast<float*>(b.save_invstd);
+        p.tail.fin.dgamma = b.dgamma; p.tail.fin.dbeta = b.dbeta; p.tail.fin.k1 = b.k1; p.tail.fin.k2 = b.k2; p.tail.fin.k3 = b.k3;
+        p.tail.fin.grad_scale = b.grad_scale;
+    }
     const int rows = nunet_grad_router_rows(d->N, d->H, d->W, d->C);
     const bool hp = n_pool > 0, hu = n_up > 0, hh = d->dlogits != nullptr;
     cudaStream_t st = (cudaStream_t)stream;

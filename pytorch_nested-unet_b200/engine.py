@@ -32,6 +32,8 @@ PACK_INPUT = _os.environ.get("NUNET_PACK_INPUT", "1") == "1"
 # loader costs 4-8x the arithmetic of writing it once (measured: tools/prof_wgrad.py). False = fused NUNET_SRC_UP* loaders.
 MATERIALIZE_UPSAMPLED = True
 WGRAD_SIDE_STREAM = _os.environ.get("NUNET_WGRAD_SIDE_STREAM", "1") == "1"
+# The gradient router of a block's first conv (one consumer: the block's second conv) runs in the epilogue of that conv's dgrad.
+FUSE_BLOCK_ROUTER = _os.environ.get("NUNET_FUSE_BLOCK_ROUTER", "1") == "1"
 # Training steps run every resolution level of the nested graph on its own CUDA stream (+ one weight-gradient stream per
 # level): nodes of one anti-diagonal are independent, so the HBM-bound kernels of one level (BN apply, upsample, gradient
 # router) execute while another level's convolution holds the tensor pipes.  Cross-level edges (pool / upsample in forward,
@@ -73,7 +75,7 @@ class LayerSpec(object):
 
     def __init__(self):
         self.sources = []    # [(producer layer idx | -1, kind, C)]
-        self.consumers = []  # [(consumer layer idx, channel offset in its concatenated input, kind)]
+        self.consumers = []  # [(consumer layer idx, channel offset in its concatenated input, kind, position in its source list)]
         self.head = None     # nn.Conv2d 1x1 reading this layer's activation
 
 
@@ -107,9 +109,9 @@ def build_specs(model):
         node_out[node] = specs[-1].idx
     for s in specs:
         off = 0
-        for pi, kind, c in s.sources:
+        for j, (pi, kind, c) in enumerate(s.sources):
             if pi >= 0:
-                specs[pi].consumers.append((s.idx, off, kind))
+                specs[pi].consumers.append((s.idx, off, kind, j))
             off += c
     for head_name, node in model._heads:
         specs[node_out[node]].head = getattr(model, head_name)
@@ -186,7 +188,13 @@ class _State(object):
             self.ws = ops.BnWorkspace(device)
             self.device = device
             self.packs = {}
+            # one self-resetting last-CTA counter per layer and direction (BatchNorm finalisation in the producing kernel's tail)
+            self.counters = torch.zeros(2 * len(self.specs), dtype=torch.int32, device=device)
         return self.ws
+
+    def counter(self, spec, backward=False):
+        i = 2 * spec.idx + (1 if backward else 0)
+        return self.counters[i:i + 1]
 
     def pack(self, spec, plan, mode):
         w = spec.conv.weight
@@ -280,13 +288,13 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
     plan = ops.conv_plan(N, h, w, cinp, s.cout)
     stacked = _stacked(s, N, h, w, cinp) and all(sr.kind == L.SRC_ACT for sr in srcs)
     wp = st.pack(s, plan, L.PACK_FWD_C32 if stacked else L.PACK_FWD)
-    y, part = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=train, stacked=stacked)
     r = _Record()
-    r.y, r.h, r.w, r.a, r.a_up, r.a_pool = y, h, w, None, None, None
+    r.h, r.w, r.a, r.a_up, r.a_pool = h, w, None, None, None
     r.scale = torch.empty(s.cout, dtype=torch.float32, device=dev)
     r.shift = torch.empty(s.cout, dtype=torch.float32, device=dev)
     bn = s.bn
     if train:
+        # train-mode BatchNorm statistics come out of the conv epilogue and are finalised by the conv's last CTA (csrc/bn_tail.cuh)
         r.mean = torch.empty(s.cout, dtype=torch.float32, device=dev)
         r.invstd = torch.empty(s.cout, dtype=torch.float32, device=dev)
         momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
@@ -295,24 +303,26 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
         rv = bn.running_var if track else None
         count = float(N * h * w)
         if dp is None or not dp.sync_bn:
-            ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
-                                  r.mean, r.invstd)
+            tail = ops.bn_tail(st.counter(s), count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, r.scale, r.shift, r.mean, r.invstd)
+            r.y, _ = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=True, stacked=stacked, tail=tail)
         else:
             sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
-            ops.bn_finalize_train(part, count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, ws, r.scale, r.shift,
-                                  r.mean, r.invstd, sums_out=sums, finalize=False)
+            tail = ops.bn_tail(st.counter(s), count, None, None, None, None, None, momentum, bn.eps, None, None, None, None, sums_out=sums)
+            r.y, _ = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=True, stacked=stacked, tail=tail)
             dp.all_reduce_sum(sums)
             ops.bn_finalize_from_sums(sums, count * dp.world_size, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps,
                                       r.scale, r.shift, r.mean, r.invstd)
     else:
         r.mean = r.invstd = None
+        r.y, _ = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=False, stacked=stacked)
         ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
+    y = r.y
     # a block's first conv output and the pooled operand are only worth materialising where the TMA-fed kernels take them
     if (s.which == 2 or (MATERIALIZE_ALL and _tma_width(w))) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
         r.a = ops.bn_apply(y, r.scale, r.shift)
-        if MATERIALIZE_UPSAMPLED and any(k == L.SRC_UP for _, _, k in s.consumers):
+        if MATERIALIZE_UPSAMPLED and any(c[2] == L.SRC_UP for c in s.consumers):
             r.a_up = ops.upsample2x(r.a)
-        if MATERIALIZE_POOLED and _tma_width(w // 2) and any(k == L.SRC_POOL for _, _, k in s.consumers):
+        if MATERIALIZE_POOLED and _tma_width(w // 2) and any(c[2] == L.SRC_POOL for c in s.consumers):
             r.a_pool = ops.maxpool2x2(r.a)
     return r
 
@@ -379,7 +389,7 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
     dev = x.device
     ws = st.workspace(dev)
     dp = _world(model)
-    grads, dxs = {}, {}
+    grads, dxs, pre = {}, {}, {}   # dxs: layer -> per-source dense dgrad outputs; pre: layer -> g_z and BN-backward coefficients from a fused router
     main = torch.cuda.current_stream(dev)
     ms = st.streams(dev) if _use_level_streams(True) else None
     side = None
@@ -413,15 +423,17 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
         ready = []   # (param, grad) finished by this layer; announced on the caller's stream (bucket all-reduce launches there)
         with (torch.cuda.stream(S) if ms is not None else _NOCTX):
             if ms is not None:
-                for (m, _, _) in s.consumers:
-                    if specs[m].level != s.level:
-                        S.wait_event(dx_done[m])
+                for c_ in s.consumers:
+                    if specs[c_[0]].level != s.level:
+                        S.wait_event(dx_done[c_[0]])
+            fused = pre.pop(s.idx, None)   # this layer's router ran inside the epilogue of its consumer's dgrad
             cons = []
-            for (m, off, kind) in s.consumers:
-                if kind == L.SRC_UP:   # transposed bilinear gather in its own tiled kernel; the router then sees a dense SAME slice
-                    cons.append(ops.Consumer(ops.up_transpose(dxs[m], specs[m].cin_pad, off, N, h, w, s.cout), s.cout, 0, L.SRC_SAME))
+            for (m, off, kind, j) in (s.consumers if fused is None else ()):
+                dxm = dxs[m][j]            # the consumer's dgrad wrote our channels as one dense tensor
+                if kind == L.SRC_UP:   # transposed bilinear gather in its own kernel; the router then sees a dense SAME consumer
+                    cons.append(ops.Consumer(ops.up_transpose(dxm, s.cout, 0, N, h, w, s.cout), s.cout, 0, L.SRC_SAME))
                 else:
-                    cons.append(ops.Consumer(dxs[m], specs[m].cin_pad, off, kind))
+                    cons.append(ops.Consumer(dxm, s.cout, 0, kind))
             dl = wh = None
             if s.head is not None:
                 dl = grad_logits.get(s.idx)
@@ -431,19 +443,29 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                     dwh, dbh = galloc(s.head.weight), galloc(s.head.bias)
                     ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
                     ready += [(s.head.weight, dwh), (s.head.bias, dbh)]
-            if not cons and dl is None:
+            if not cons and dl is None and fused is None:
                 dl = torch.zeros((N, 1, h, w), dtype=torch.float32, device=dev)
                 wh = torch.zeros((1, s.cout), dtype=torch.float32, device=dev)
-            gz, rpart = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh)
-            dgamma, dbeta = galloc(s.bn.weight), galloc(s.bn.bias)
-            k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
             count = float(N * h * w)
-            lws = ms.ws[s.level] if ms is not None else ws
-            if dp is None or not dp.sync_bn:
-                ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, lws, dgamma, dbeta, k1, k2, k3)
+            if fused is not None:
+                gz, dgamma, dbeta, k1, k2, k3, sums = fused
+                if sums is not None:     # SyncBN: the fused router only produced this rank's sums
+                    dp.all_reduce_sum(sums)
+                    ops.bn_backward_from_sums(sums, count * dp.world_size, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3,
+                                              grad_scale=1.0 / dp.world_size)
+            else:
+                dgamma, dbeta = galloc(s.bn.weight), galloc(s.bn.bias)
+                k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
+            if fused is not None:
+                pass
+            elif dp is None or not dp.sync_bn:
+                # the router's last CTA reduces its partial sums and emits dgamma / dbeta / k1..k3 (csrc/bn_tail.cuh)
+                tail = ops.bn_bwd_tail(st.counter(s, True), count, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3)
+                gz, _ = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh, tail=tail)
             else:
                 sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
-                ops.bn_backward_reduce(rpart, count, s.bn.weight, r.mean, r.invstd, lws, dgamma, dbeta, k1, k2, k3, sums_out=sums, finalize=False)
+                tail = ops.bn_bwd_tail(st.counter(s, True), count, None, None, None, None, None, None, None, None, sums_out=sums)
+                gz, _ = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh, tail=tail)
                 dp.all_reduce_sum(sums)
                 # local gradients are those of the LOCAL mean loss (= world_size x the global-loss gradient); the all-reduced sums
                 # therefore give world_size x dgamma/dbeta on every rank: scale by 1/world so the later AVG keeps the true value
@@ -479,16 +501,32 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
             if s.sources[0][0] >= 0:
                 plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
                 wpd = st.pack(s, plan, L.PACK_DGRAD)
-                dxs[s.idx], _ = ops.conv3x3(N, h, w, [ops.Source(L.SRC_ACT, gy, s.cout)], s.cin_pad, wpd, cls="conv_dgrad")
+                gsrc = [ops.Source(L.SRC_ACT, gy, s.cout)]
+                if s.which == 2 and FUSE_BLOCK_ROUTER:
+                    # the block's first conv has exactly one consumer (this conv): its gradient router — ReLU mask, g_z, the two
+                    # BatchNorm-backward sums and (single GPU) their finalisation — runs in this dgrad's epilogue
+                    sp, rp = specs[s.idx - 1], recs[s.idx - 1]
+                    dg1, db1 = galloc(sp.bn.weight), galloc(sp.bn.bias)
+                    kk = [torch.empty(sp.cout, dtype=torch.float32, device=dev) for _ in range(3)]
+                    msk = ops.Mask(rp.y, rp.scale, rp.shift, rp.mean, rp.invstd)
+                    if dp is None or not dp.sync_bn:
+                        bt, sums1 = ops.bn_bwd_tail(st.counter(sp, True), count, sp.bn.weight, rp.mean, rp.invstd, dg1, db1, kk[0], kk[1], kk[2]), None
+                    else:
+                        sums1 = torch.empty((2, sp.cout), dtype=torch.float64, device=dev)
+                        bt = ops.bn_bwd_tail(st.counter(sp, True), count, None, None, None, None, None, None, None, None, sums_out=sums1)
+                    gz1, _ = ops.conv3x3(N, h, w, gsrc, s.cin_pad, wpd, cls="conv_dgrad", mask=msk, bwd_tail=bt)
+                    pre[sp.idx] = (gz1, dg1, db1, kk[0], kk[1], kk[2], sums1)
+                else:
+                    dxs[s.idx], _ = ops.conv3x3(N, h, w, gsrc, s.cin_pad, wpd, cls="conv_dgrad", out_segs=[c for _, _, c in s.sources])
                 if ms is not None:
                     dx_done[s.idx] = torch.cuda.Event()
                     dx_done[s.idx].record(S)
         for p_, g_ in ready:
             gdone(p_, g_)
         if ms is None:
-            for (m, _, _) in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
-                if specs[m].sources[0][0] == s.idx:
-                    dxs.pop(m, None)
+            for c_ in s.consumers:  # a consumer's dX is dead once its last (earliest) producer has routed it
+                if specs[c_[0]].sources[0][0] == s.idx:
+                    dxs.pop(c_[0], None)
     if ms is not None:
         ms.join(main, with_wg=True)
     if side is not None:

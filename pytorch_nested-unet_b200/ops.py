@@ -127,13 +127,51 @@ def pack_weights_batched(items):
     _call("pack", (len(items) + 63) // 64, None, "nunet_pack_weights_batched", L.lib().nunet_pack_weights_batched, C.cast(jobs, C.c_void_p), len(items), _stream())
 
 
-def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False, cls=None, stacked=False):
-    """Launches the fused implicit-GEMM conv. Returns (out bf16 [N,H,W,Cout], stat_part [grid_m,2,Cout] or None)."""
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def bn_tail(counter, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd, sums_out=None):
+    """nunet_bn_tail_t: BatchNorm finalisation in the tail of the conv that produced the statistics.  gamma None -> sums_out only."""
+    t = L.BnTail()
+    t.counter, t.count = counter.data_ptr(), float(count)
+    t.gamma, t.beta, t.conv_bias = _p(gamma), _p(beta), _p(conv_bias)
+    t.running_mean, t.running_var, t.momentum, t.eps = _p(running_mean), _p(running_var), float(momentum), float(eps)
+    t.scale, t.shift, t.save_mean, t.save_invstd, t.sums_out = _p(scale), _p(shift), _p(save_mean), _p(save_invstd), _p(sums_out)
+    return t
+
+
+def bn_bwd_tail(counter, count, gamma, save_mean, save_invstd, dgamma, dbeta, k1, k2, k3, grad_scale=1.0, sums_out=None):
+    """nunet_bn_bwd_tail_t: BatchNorm-backward coefficients in the tail of the kernel that produced the two sums."""
+    t = L.BnBwdTail()
+    t.counter, t.count = counter.data_ptr(), float(count)
+    t.gamma, t.save_mean, t.save_invstd = _p(gamma), _p(save_mean), _p(save_invstd)
+    t.dgamma, t.dbeta, t.k1, t.k2, t.k3 = _p(dgamma), _p(dbeta), _p(k1), _p(k2), _p(k3)
+    t.grad_scale, t.sums_out = float(grad_scale), _p(sums_out)
+    return t
+
+
+class Mask(object):
+    """Fused block-internal gradient router of a dgrad launch: the producer's raw output and BatchNorm coefficients."""
+    __slots__ = ("y", "scale", "shift", "mean", "invstd")
+
+    def __init__(self, y, scale, shift, mean, invstd):
+        self.y, self.scale, self.shift, self.mean, self.invstd = y, scale, shift, mean, invstd
+
+
+def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=False, cls=None, stacked=False, tail=None,
+            out_segs=None, mask=None, bwd_tail=None):
+    """Launches the fused implicit-GEMM conv. Returns (out bf16 [N,H,W,Cout] — or the list of per-segment tensors when out_segs
+    (channel counts) is given —, stat_part [grid_m,2,Cout] or None)."""
     cin = sum(s.cpad for s in sources)
     plan = conv_plan(N, H, W, cin, Cout)
     dev = sources[0].data.device
-    if out is None:
+    if out_segs is not None:
+        out = [torch.empty((N, H, W, c), dtype=torch.bfloat16, device=dev) for c in out_segs]
+    elif out is None:
         out = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=dev)
+    if mask is not None:
+        want_stats = True
     if want_stats and stat_part is None:
         stat_part = torch.empty((plan.grid_m, 2, Cout), dtype=torch.float32, device=dev)
     d = L.ConvDesc()
@@ -148,8 +186,20 @@ def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=
         d.src[i].kind = s.kind
     d.wpack = wpack.data_ptr()
     d.wpack_layout = 1 if stacked else 0
-    d.out = out.data_ptr()
+    if out_segs is not None:
+        d.num_out_seg = len(out)
+        for i, (t, c) in enumerate(zip(out, out_segs)):
+            d.out_seg[i], d.out_seg_c[i] = t.data_ptr(), c
+    else:
+        d.out = out.data_ptr()
     d.stat_part = stat_part.data_ptr() if stat_part is not None else None
+    if tail is not None:
+        d.bn = tail
+    if mask is not None:
+        d.mask_y, d.mask_scale, d.mask_shift = mask.y.data_ptr(), mask.scale.data_ptr(), mask.shift.data_ptr()
+        d.mask_mean, d.mask_invstd = mask.mean.data_ptr(), mask.invstd.data_ptr()
+        if bwd_tail is not None:
+            d.bn_bwd = bwd_tail
     if cls is None:
         cls = "conv_dgrad" if sources[0].kind == L.SRC_GRAD else "conv_fwd"
     _call(cls, 1, (N, H, W, cin, Cout), "nunet_conv3x3_fwd", L.lib().nunet_conv3x3_fwd, C.byref(d), _stream())
@@ -283,7 +333,7 @@ class Consumer(object):
         self.dx, self.pitch, self.coff, self.kind = dx, pitch, coff, kind
 
 
-def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, part=None, dlogits=None, wh=None):
+def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, part=None, dlogits=None, wh=None, tail=None):
     dev = y.device
     rows = L.lib().nunet_grad_router_rows(N, H, W, Cc)
     if gz is None:
@@ -299,6 +349,8 @@ def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, 
     if dlogits is not None:
         d.dlogits, d.wh, d.K = dlogits.data_ptr(), wh.data_ptr(), wh.shape[0]
     d.gz, d.part = gz.data_ptr(), part.data_ptr()
+    if tail is not None:
+        d.bn = tail
     _call("router", 1, (N, H, W, Cc, len(consumers)), "nunet_grad_router", L.lib().nunet_grad_router, C.byref(d), _stream())
     return gz, part
 

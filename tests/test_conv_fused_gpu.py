@@ -1,0 +1,138 @@
+"""Round-2 fusions of the conv kernel, each against the unfused launches it replaces (bitwise or to fp32 round-off):
+  * BatchNorm finalisation in the conv's tail (last CTA) == nunet_bn_finalize_train on the same partial sums
+  * dgrad with one dense output tensor per concatenated source == channel slices of the single wide output
+  * dgrad of a block's second conv with the block-internal gradient router fused into its epilogue == dgrad -> nunet_grad_router
+    -> nunet_bn_backward_reduce, including the BatchNorm-backward coefficients from the kernel's tail
+  * the gradient router's own tail == nunet_bn_backward_reduce
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bf(gen, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=gen, device=DEV) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,stacked", [(2, 32, 32, 32, 32, False), (16, 96, 96, 32, 32, False), (3, 16, 16, 64, 64, False),
+                                                     (2, 12, 12, 256, 256, False), (3, 6, 6, 512, 512, False), (4, 48, 80, 96, 32, True),
+                                                     (2, 32, 272, 32, 32, False)])
+def test_bn_tail_equals_separate_finalize(N, H, W, cin, cout, stacked):
+    import _lib as L
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(7 + cin + cout)
+    a = _bf(gen, N, H, W, cin).abs()
+    w = torch.randn(cout, cin, 3, 3, generator=gen, device=DEV) * 0.05
+    gamma, beta, bias = (torch.randn(cout, generator=gen, device=DEV) for _ in range(3))
+    plan = ops.conv_plan(N, H, W, cin, cout)
+    stacked = stacked and ops.c32_eligible(N, H, W, cin, cout)
+    wp = ops.pack_weights(w, L.PACK_FWD_C32 if stacked else L.PACK_FWD, plan)
+    src = [ops.Source(L.SRC_ACT, a, cin)]
+    f32 = lambda: torch.empty(cout, device=DEV)
+    # reference: statistics epilogue + separate finalize launch
+    y0, part = ops.conv3x3(N, H, W, src, cout, wp, want_stats=True, stacked=stacked)
+    rm0, rv0 = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+    sc0, sh0, mu0, is0 = f32(), f32(), f32(), f32()
+    ops.bn_finalize_train(part, float(N * H * W), gamma, beta, bias, rm0, rv0, 0.1, 1e-5, ops.BnWorkspace(DEV), sc0, sh0, mu0, is0)
+    # fused: the conv's last CTA finalises
+    rm1, rv1 = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+    sc1, sh1, mu1, is1 = f32(), f32(), f32(), f32()
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for rep in range(3):      # the counter resets itself: repeated launches keep working
+        rm1.zero_(); rv1.fill_(1.0)
+        tail = ops.bn_tail(counter, float(N * H * W), gamma, beta, bias, rm1, rv1, 0.1, 1e-5, sc1, sh1, mu1, is1)
+        y1, _ = ops.conv3x3(N, H, W, src, cout, wp, want_stats=True, stacked=stacked, tail=tail)
+        torch.cuda.synchronize()
+        assert int(counter) == 0
+        assert torch.equal(y0, y1)
+        # same partial rows, both reduced in fp64 (different association): agreement to fp32 round-off
+        for a_, b_ in ((sc0, sc1), (sh0, sh1), (mu0, mu1), (is0, is1), (rm0, rm1), (rv0, rv1)):
+            assert torch.allclose(a_, b_, rtol=2e-6, atol=1e-6), float((a_ - b_).abs().max())
+
+
+@pytest.mark.parametrize("N,H,W,cout,segs", [(2, 32, 32, 32, [32, 64]), (3, 48, 80, 32, [32, 32, 32, 32, 64]), (2, 16, 16, 64, [64, 64, 128]),
+                                             (2, 12, 12, 256, [256, 512]), (2, 8, 8, 128, [128, 128, 256]), (2, 32, 272, 32, [32, 64])])
+def test_dgrad_per_source_outputs_equal_slices_of_the_wide_output(N, H, W, cout, segs):
+    import _lib as L
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(11 + sum(segs))
+    cin = sum(segs)
+    gy = _bf(gen, N, H, W, cout)
+    w = torch.randn(cout, cin, 3, 3, generator=gen, device=DEV) * 0.05
+    plan = ops.conv_plan(N, H, W, cout, cin)
+    wpd = ops.pack_weights(w, L.PACK_DGRAD, plan)
+    src = [ops.Source(L.SRC_ACT, gy, cout)]
+    wide, _ = ops.conv3x3(N, H, W, src, cin, wpd, cls="conv_dgrad")
+    parts, _ = ops.conv3x3(N, H, W, src, cin, wpd, cls="conv_dgrad", out_segs=segs)
+    torch.cuda.synchronize()
+    off = 0
+    for t, c in zip(parts, segs):
+        assert t.shape == (N, H, W, c)
+        assert torch.equal(t, wide[..., off:off + c])
+        off += c
+
+
+@pytest.mark.parametrize("N,H,W,cmid,cout", [(2, 32, 32, 32, 32), (16, 96, 96, 32, 32), (3, 16, 24, 64, 64), (2, 12, 12, 256, 256), (3, 6, 6, 512, 512),
+                                             (2, 24, 24, 128, 128), (2, 32, 272, 32, 32)])
+def test_fused_block_router_equals_dgrad_then_router(N, H, W, cmid, cout):
+    """conv2's dgrad with mask = (y1, scale1, shift1, mean1, invstd1) must produce g_z of conv1 and its BatchNorm-backward
+    coefficients exactly as the separate launches do (the fused path masks the fp32 accumulator, the separate one the bf16 dX:
+    g_z agrees to the bf16 rounding of dX, i.e. bitwise after the same rounding; sums to fp32 round-off)."""
+    import _lib as L
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(5 + cmid + H)
+    gy2 = _bf(gen, N, H, W, cout)
+    y1 = _bf(gen, N, H, W, cmid, scale=1.5)
+    w2 = torch.randn(cout, cmid, 3, 3, generator=gen, device=DEV) * 0.05
+    sc, sh = torch.randn(cmid, generator=gen, device=DEV), torch.randn(cmid, generator=gen, device=DEV) * 0.5
+    mu, rs = torch.randn(cmid, generator=gen, device=DEV) * 0.3, torch.rand(cmid, generator=gen, device=DEV) + 0.5
+    gamma = torch.randn(cmid, generator=gen, device=DEV)
+    plan = ops.conv_plan(N, H, W, cout, cmid)
+    wpd = ops.pack_weights(w2, L.PACK_DGRAD, plan)
+    src = [ops.Source(L.SRC_ACT, gy2, cout)]
+    count = float(N * H * W)
+    f32 = lambda: torch.empty(cmid, device=DEV)
+    # separate launches
+    dx, _ = ops.conv3x3(N, H, W, src, cmid, wpd, cls="conv_dgrad")
+    gz0, part0 = ops.grad_router(N, H, W, cmid, y1, sc, sh, mu, rs, [ops.Consumer(dx, cmid, 0, L.SRC_SAME)])
+    dg0, db0, k10, k20, k30 = f32(), f32(), f32(), f32(), f32()
+    ops.bn_backward_reduce(part0, count, gamma, mu, rs, ops.BnWorkspace(DEV), dg0, db0, k10, k20, k30)
+    # fused
+    dg1, db1, k11, k21, k31 = f32(), f32(), f32(), f32(), f32()
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    bt = ops.bn_bwd_tail(counter, count, gamma, mu, rs, dg1, db1, k11, k21, k31)
+    gz1, _ = ops.conv3x3(N, H, W, src, cmid, wpd, cls="conv_dgrad", mask=ops.Mask(y1, sc, sh, mu, rs), bwd_tail=bt)
+    torch.cuda.synchronize()
+    assert int(counter) == 0
+    assert torch.equal(gz0, gz1)
+    # the separate path sums bf16-rounded g_z, the fused one the fp32 accumulators: relative to the per-channel scale of the sums
+    for a_, b_, name in ((dg0, dg1, "dgamma"), (db0, db1, "dbeta"), (k20, k21, "k2"), (k30, k31, "k3")):
+        tol = 4e-3 * float(a_.abs().max()) + 1e-6
+        assert float((a_ - b_).abs().max()) <= tol, (name, float((a_ - b_).abs().max()), tol)
+    assert torch.equal(k10, k11)
+
+
+@pytest.mark.parametrize("N,H,W,C,ncons", [(2, 32, 32, 32, 3), (3, 16, 16, 64, 1), (2, 12, 12, 256, 2), (3, 6, 6, 512, 1)])
+def test_router_tail_equals_separate_reduce(N, H, W, C, ncons):
+    import _lib as L
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(3 + C)
+    y = _bf(gen, N, H, W, C, scale=1.5)
+    sc, sh = torch.randn(C, generator=gen, device=DEV), torch.randn(C, generator=gen, device=DEV) * 0.5
+    mu, rs = torch.randn(C, generator=gen, device=DEV) * 0.3, torch.rand(C, generator=gen, device=DEV) + 0.5
+    gamma = torch.randn(C, generator=gen, device=DEV)
+    cons = [ops.Consumer(_bf(gen, N, H, W, C), C, 0, L.SRC_SAME) for _ in range(ncons)]
+    count = float(N * H * W)
+    f32 = lambda: torch.empty(C, device=DEV)
+    gz0, part0 = ops.grad_router(N, H, W, C, y, sc, sh, mu, rs, cons)
+    ref = [f32() for _ in range(5)]
+    ops.bn_backward_reduce(part0, count, gamma, mu, rs, ops.BnWorkspace(DEV), *ref)
+    got = [f32() for _ in range(5)]
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    gz1, _ = ops.grad_router(N, H, W, C, y, sc, sh, mu, rs, cons, tail=ops.bn_bwd_tail(counter, count, gamma, mu, rs, *got))
+    torch.cuda.synchronize()
+    assert int(counter) == 0 and torch.equal(gz0, gz1)
+    for a_, b_ in zip(ref, got):
+        assert torch.allclose(a_, b_, rtol=2e-6, atol=1e-7 * max(1.0, float(a_.abs().max()))), float((a_ - b_).abs().max())

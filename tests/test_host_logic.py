@@ -24,10 +24,10 @@ def test_engine_specs_match_reference_graph():
     assert by[("3_0", 1)].sources == [(by[("2_0", 2)].idx, L.SRC_POOL, 128)]
     # x0_0 is consumed by conv1_0 (pool) and conv0_1..conv0_4 (same, channel offset 0)
     cons = by[("0_0", 2)].consumers
-    assert sorted(k for _, _, k in cons) == sorted([L.SRC_POOL] + [L.SRC_SAME] * 4) and all(off == 0 for _, off, _ in cons)
+    assert sorted(c[2] for c in cons) == sorted([L.SRC_POOL] + [L.SRC_SAME] * 4) and all(c[1] == 0 for c in cons)
     # x1_2 enters conv0_3.conv1 upsampled at channel offset 3*32
-    c13 = [(m_, off, k) for (m_, off, k) in by[("1_2", 2)].consumers if specs[m_].node == "0_3"]
-    assert c13 == [(by[("0_3", 1)].idx, 96, L.SRC_UP)]
+    c13 = [c for c in by[("1_2", 2)].consumers if specs[c[0]].node == "0_3"]
+    assert c13 == [(by[("0_3", 1)].idx, 96, L.SRC_UP, 3)]      # ... as the fourth source (position 3) of that conv
     assert [s.node for s in specs if s.head is not None] == ["0_1", "0_2", "0_3", "0_4"]
     u = archs.UNet(1, 3)
     assert len(engine._state(u).specs) == 18 and [s.node for s in engine._state(u).specs if s.head is not None] == ["0_4"]
