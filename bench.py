@@ -181,7 +181,8 @@ def run_native(args):
     if world > 1:
         import dist as nunet_dist
         model = nunet_dist.DataParallel(model, sync_bn=not args.no_sync_bn)
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    import optim as nunet_optim
+    opt = nunet_optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)     # trains.py:229-231 defaults, fused step (optim.py)
     B, S = args.batch, args.size
     IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)  # albumentations Normalize(), trains.py:266
     g = torch.Generator().manual_seed(1 + rank)

@@ -162,6 +162,20 @@ int nunet_bn_apply(const void* y, const float* scale, const float* shift, long l
 /* out[N,2h,2w,C] = bilinear 2x (align_corners=True) of an activated bf16 NHWC tensor (nn.Upsample, finished/archs1.py:83),
  * for callers that prefer one materialised operand over the NUNET_SRC_UP* loaders. */
 int nunet_upsample2x(const void* in, int32_t N, int32_t h, int32_t w, int32_t C, void* out, void* stream);
+/* "Activate" (csrc/activate.cu): everything the consumers of a raw conv output need in ONE pass over y — a = relu(scale*y+shift)
+ * (finished/archs1.py:25-26,29-30), its 2x2 max-pool (:82), its bilinear 2x upsample (:83) and the 1x1 head's logits (:106-111,135-142,
+ * computed from the fp32 activation; C == 32, K <= 8, fp32 NCHW).  Any output pointer may be NULL (at least one must be given);
+ * replaces the separate nunet_bn_apply / nunet_maxpool2x2 / nunet_upsample2x / nunet_head_fwd launches. */
+typedef struct nunet_activate_desc_s {
+    const void* y; /* bf16 NHWC [N,H,W,C] */
+    int32_t N, H, W, C;
+    const float *scale, *shift;
+    void *a, *a_pool, *a_up; /* bf16 NHWC [N,H,W,C], [N,H/2,W/2,C], [N,2H,2W,C] */
+    const float *wh, *bh;    /* head: [K][32], [K] */
+    int32_t K, pad_;
+    float* logits;           /* [N,K,H,W] */
+} nunet_activate_desc_t;
+int nunet_bn_activate(const nunet_activate_desc_t* d, void* stream);
 /* Eval mode: scale = gamma*rsqrt(running_var+eps), shift = beta + (conv_bias - running_mean)*scale. */
 int nunet_bn_fold_eval(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
                        const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
@@ -208,6 +222,11 @@ typedef struct {
     void* gz;    /* out: g_z = g_a * [a>0], bf16 NHWC */
     float* part; /* out: [nunet_grad_router_rows()][2][C]: sum g_z, sum g_z*yhat */
     nunet_bn_bwd_tail_t bn; /* bn.counter != NULL: BatchNorm-backward coefficients in the kernel's tail */
+    /* head_part != NULL (needs dlogits, K == 1, C == 32, bn.counter, no POOL / UP consumer): the head's own parameter gradients
+     * dwh[c] = sum dlogit*a[c] ([32]) and dbh = sum dlogit ([1], may be NULL) are accumulated in the same pass and finished by the
+     * last CTA (replaces nunet_head_bwd_params).  head_part: [nunet_grad_router_rows()][33] fp32 scratch. */
+    float* head_part;
+    float *dwh, *dbh;
 } nunet_router_desc_t;
 int nunet_grad_router_rows(int32_t N, int32_t H, int32_t W, int32_t C);
 int nunet_grad_router(const nunet_router_desc_t* d, void* stream);
@@ -259,6 +278,25 @@ int nunet_maxpool2x2(const void* in, int32_t N, int32_t H, int32_t W, int32_t C,
 int nunet_input_to_nhwc32(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* out, void* stream);
 int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* plan);
 int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
+
+/* ---- fused optimizer step (trains.py:131-133 with the optimizers of trains.py:225-233; csrc/optim.cu) ---------------------------------
+ * One launch updates every parameter tensor of the model with torch.optim's arithmetic (SGD: momentum, dampening, weight decay,
+ * nesterov; Adam: betas, eps, weight decay).  tensors_dev: DEVICE array, one entry per parameter (grad == NULL: skipped); chunks_dev:
+ * DEVICE array of int32 pairs (tensor index, chunk index) — one CTA per nunet_optim_chunk_elems() elements; hyper_dev: DEVICE fp32
+ * [lr, momentum, dampening, weight_decay, nesterov] (SGD) or [lr, beta1, beta2, eps, weight_decay] (Adam), so a captured CUDA graph
+ * follows the host's learning-rate schedule; step_dev (Adam): DEVICE int32 step counter, incremented by the call. */
+enum { NUNET_OPTIM_SGD = 0, NUNET_OPTIM_ADAM = 1 };
+typedef struct {
+    float* param;       /* fp32 master, updated in place */
+    const float* grad;  /* fp32 gradient or NULL */
+    float* state1;      /* SGD: momentum buffer (zero-initialised; NULL if momentum == 0) ; Adam: exp_avg */
+    float* state2;      /* Adam: exp_avg_sq */
+    int64_t numel;      /* bit 62 set (SGD): this is the buffer's first step: buf = g' (torch clones the gradient; dampening is not applied) */
+} nunet_optim_tensor_t;
+#define NUNET_OPTIM_FIRST_STEP (1LL << 62)
+int nunet_optim_chunk_elems(void);
+int nunet_optim_step(const nunet_optim_tensor_t* tensors_dev, const int32_t* chunks_dev, int32_t nchunks, const float* hyper_dev,
+                     int32_t algo, int32_t* step_dev, void* stream);
 
 /* ---- fp32 check mode (forward and backward; csrc/check_fp32.cu) -----------------------------------------------------
  * The reference's fp32 arithmetic on CUDA cores: fp32 NHWC activations with a channel pitch, fp64 BatchNorm statistics.

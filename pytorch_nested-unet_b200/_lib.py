@@ -54,7 +54,8 @@ class RouterDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("y", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("num_cons", C.c_int32), ("cons", GradCons * 6), ("dlogits", C.c_void_p), ("wh", C.c_void_p),
-                ("K", C.c_int32), ("gz", C.c_void_p), ("part", C.c_void_p), ("bn", BnBwdTail)]
+                ("K", C.c_int32), ("gz", C.c_void_p), ("part", C.c_void_p), ("bn", BnBwdTail),
+                ("head_part", C.c_void_p), ("dwh", C.c_void_p), ("dbh", C.c_void_p)]
 
 
 class WgradPlan(C.Structure):
@@ -70,6 +71,12 @@ class WgradDesc(C.Structure):
 
 class PackJob(C.Structure):
     _fields_ = [("w", C.c_void_p), ("out", C.c_void_p)] + [(n, C.c_int32) for n in ("Cout", "Cin", "mode", "NT", "CK", "nchunks", "n_tiles", "pad_")]
+
+
+class ActivateDesc(C.Structure):   # nunet_activate_desc_t
+    _fields_ = [("y", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("scale", C.c_void_p),
+                ("shift", C.c_void_p), ("a", C.c_void_p), ("a_pool", C.c_void_p), ("a_up", C.c_void_p), ("wh", C.c_void_p), ("bh", C.c_void_p),
+                ("K", C.c_int32), ("pad_", C.c_int32), ("logits", C.c_void_p)]
 
 
 class NunetError(RuntimeError):
@@ -104,6 +111,9 @@ _SIGS = {
     "nunet_bn_backward_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 8 + [C.c_float, C.c_void_p], C.c_int),
     "nunet_conv3x3_wgrad_plan": ([C.c_int32] * 5 + [C.POINTER(WgradPlan)], C.c_int),
     "nunet_conv3x3_wgrad": ([C.POINTER(WgradDesc), C.c_void_p], C.c_int),
+    "nunet_optim_chunk_elems": ([], C.c_int),
+    "nunet_optim_step": ([C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_bn_activate": ([C.POINTER(ActivateDesc), C.c_void_p], C.c_int),
     "nunet_bn_apply": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_bwd_apply": ([C.c_void_p] * 5 + [C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_upsample2x": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p], C.c_int),

@@ -71,7 +71,8 @@ __device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int
 // total_ctas = CTAs of the grid (every one of them must come through here exactly once).
 // The reduction is latency-bound (one CTA, L2 loads): a thread owns four adjacent columns of the 2C-wide rows (one 16-byte load per
 // row) and every L-th row, and keeps eight loads in flight; the L row lanes are then combined in a fixed order.
-__device__ __forceinline__ void bn_tail_run(const BnTail& t, const float* part, int rows, int C, unsigned total_ctas, int tid, int bar_id,
+// Returns true in the (single) CTA that ran the finalisation, so that a caller can append further last-CTA work.
+__device__ __forceinline__ bool bn_tail_run(const BnTail& t, const float* part, int rows, int C, unsigned total_ctas, int tid, int bar_id,
                                             void* scratch) {
     double* sh = reinterpret_cast<double*>(scratch);                      // [L][2C] partial sums (<= 1024 doubles)
     volatile int* flag = reinterpret_cast<volatile int*>(sh + 1024);
@@ -79,7 +80,7 @@ __device__ __forceinline__ void bn_tail_run(const BnTail& t, const float* part, 
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
     if (tid == 0) *flag = (atomicAdd(t.counter, 1u) == total_ctas - 1) ? 1 : 0;   // ... before it is counted
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-    if (!*flag) return;
+    if (!*flag) return false;
     __threadfence();
     const int groups = C >> 1;              // 16-byte column groups per row (2C floats)
     const int L = 256 / groups;             // row lanes: 16 (C = 32) ... 1 (C = 512)
@@ -109,6 +110,7 @@ __device__ __forceinline__ void bn_tail_run(const BnTail& t, const float* part, 
         if (t.fin.gamma) bn_finalize_channel(t.fin, c, S, SS);
     }
     if (tid == 0) *t.counter = 0;   // self-resetting for the next launch
+    return true;
 }
 
 }  // namespace nunet

@@ -11,6 +11,7 @@
 //      reductions of nn.BatchNorm2d's backward (yhat = (y-mean)*invstd).
 // The affine rest of BN backward (g_y = k1*g_z + k2*y + k3) is folded into the loaders of dgrad / wgrad.
 #include "conv_common.cuh"
+#include "loaders.cuh"
 #include <cstdlib>
 
 namespace nunet {
@@ -31,6 +32,10 @@ struct RouterParams {
     __nv_bfloat16* gz;
     float* part;  // [gridDim.x][2][C]
     BnTail tail;  // BatchNorm-backward coefficients by the last CTA
+    // fused head parameter gradients (K == 1, C == 32): hpart [gridDim.x][33] per-CTA partials of dWh[c] = sum dl*a, dbh = sum dl;
+    // reduced into dwh [32] / dbh [1] by the last CTA (needs tail.counter)
+    float* hpart;
+    float *dwh, *dbh;
 };
 
 __device__ __forceinline__ void add8(float (&g)[8], const uint4& r, float w) {
@@ -325,6 +330,179 @@ __global__ void __launch_bounds__(256, HAS_POOL ? 3 : 4) grad_router_fast_kernel
     if (p.tail.counter) bn_tail_run(p.tail, p.part, (int)gridDim.x, p.C, gridDim.x, threadIdx.x, 0, &red[0][0]);
 }
 
+// ---- v2 (round 2): every consumer slice is now a DENSE tensor (the dgrads write one tensor per source), so
+//  * POOL: a thread owns a whole 2x2 window (4 pixels x 8 channels): the window's y values are loaded once (round 1: every pixel
+//    re-read its three neighbours), the arg-max is taken in registers, one pooled-gradient load serves four outputs;
+//  * HEAD (K == 1, the reference's default num_classes): the head weights live in registers and the head's own parameter gradients
+//    (dWh = sum dl*a, dbh = sum dl; round 1: a separate pass over y, nunet_head_bwd_params) are accumulated in the same pass and
+//    finished by the last CTA together with the BatchNorm-backward coefficients.
+template <int NS, bool POOL, bool HEAD>
+__global__ void __launch_bounds__(256, POOL ? (NS >= 3 ? 1 : 2) : 3) grad_router_v2_kernel(const RouterParams p) {
+    const int cgs = p.C >> 3;
+    const int cg = threadIdx.x & (cgs - 1);      // C/8 is a power of two; grid strides are multiples of it
+    const int ch = cg * 8;
+    const int HW = p.H * p.W;
+    float sc[8], sh[8], acc1[8], acc2[8], wh8[8], accw[8], accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = p.scale[ch + i];
+        sh[i] = p.shift[ch + i];
+        acc1[i] = 0.f;
+        acc2[i] = 0.f;
+        wh8[i] = HEAD ? p.wh[ch + i] : 0.f;
+        accw[i] = 0.f;
+    }
+    // one pixel: g (gathered gradient of the activation), yv (raw y) -> g_z store + BatchNorm sums (+ head parameter sums)
+    auto finish_pixel = [&](size_t pix, const float (&yv)[8], float (&g)[8], float dl) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(yv[i], sc[i], sh[i]);
+            if (HEAD) {
+                g[i] = fmaf(dl, wh8[i], g[i]);
+                accw[i] = fmaf(dl, fmaxf(z, 0.f), accw[i]);
+            }
+            const float gz = (z > 0.f) ? g[i] : 0.f;
+            g[i] = gz;
+            acc1[i] += gz;
+            acc2[i] = fmaf(gz, yv[i], acc2[i]);
+        }
+        if (HEAD && cg == 0) accb += dl;
+        *reinterpret_cast<uint4*>(p.gz + pix * p.C + ch) = pack8(g);
+    };
+    const int stride = gridDim.x * 256;
+    if constexpr (POOL) {
+        const int h = p.H >> 1, w = p.W >> 1;
+        const int items = p.N * h * w * cgs;
+        const int cg_shift = 31 - __clz(cgs);
+        const GradCons& pc = p.cons[NS];
+        for (int it = blockIdx.x * 256 + threadIdx.x; it < items; it += stride) {
+            const int win = it >> cg_shift;
+            const int x = win % w, t2 = win / w;
+            const int yy = t2 % h, n = t2 / h;
+            const size_t p00 = ((size_t)n * p.H + 2 * yy) * p.W + 2 * x;
+            const size_t off[4] = {0, 1, (size_t)p.W, (size_t)p.W + 1};
+            uint4 ry[4], rd[4][NS > 0 ? NS : 1];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ry[k] = __ldg(reinterpret_cast<const uint4*>(p.y + (p00 + off[k]) * p.C + ch));
+#pragma unroll
+                for (int ci = 0; ci < NS; ++ci)
+                    rd[k][ci] = __ldg(reinterpret_cast<const uint4*>(p.cons[ci].dx + (p00 + off[k]) * p.cons[ci].pitch + p.cons[ci].coff + ch));
+            }
+            const uint4 rp = __ldg(reinterpret_cast<const uint4*>(pc.dx + (size_t)win * pc.pitch + pc.coff + ch));
+            float yv[4][8], d[8];
+            unpack8f(rp, d);
+            int idx[8];
+            float best[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unpack8f(ry[k], yv[k]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float am = fmaxf(fmaf(yv[k][i], sc[i], sh[i]), 0.f);
+                    if (k == 0 || am > best[i]) { best[i] = am; idx[i] = k; }   // first maximum in window scan order, as ATen
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float g[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = (idx[i] == k) ? d[i] : 0.f;
+#pragma unroll
+                for (int ci = 0; ci < NS; ++ci) add8(g, rd[k][ci], 1.f);
+                float dl = 0.f;
+                if (HEAD) dl = __ldg(p.dlogits + (size_t)n * HW + (size_t)(2 * yy + (k >> 1)) * p.W + 2 * x + (k & 1));
+                finish_pixel(p00 + off[k], yv[k], g, dl);
+            }
+        }
+    } else {
+        const int items = p.N * HW * cgs;
+        const int cg_shift = 31 - __clz(cgs);
+        constexpr int U = (NS <= 2) ? 2 : 1;
+        for (int it0 = blockIdx.x * 256 + threadIdx.x; it0 < items; it0 += stride * U) {
+            uint4 ry[U], rd[U][NS > 0 ? NS : 1];
+            int pix[U];
+            float dl[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + u * stride;
+                pix[u] = (it < items) ? (it >> cg_shift) : -1;
+                dl[u] = 0.f;
+                if (pix[u] >= 0) {
+                    ry[u] = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)pix[u] * p.C + ch));
+#pragma unroll
+                    for (int ci = 0; ci < NS; ++ci)
+                        rd[u][ci] = __ldg(reinterpret_cast<const uint4*>(p.cons[ci].dx + (size_t)pix[u] * p.cons[ci].pitch + p.cons[ci].coff + ch));
+                    if (HEAD) dl[u] = __ldg(p.dlogits + pix[u]);     // K == 1: dlogits [N,1,H,W] is indexed by the pixel
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (pix[u] < 0) continue;
+                float yv[8], g[8];
+                unpack8f(ry[u], yv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < NS; ++ci) add8(g, rd[u][ci], 1.f);
+                finish_pixel((size_t)pix[u], yv, g, dl[u]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc2[i] = p.invstd[ch + i] * (acc2[i] - p.mean[ch + i] * acc1[i]);
+    // block reduction: threads with equal cg (tid % cgs) hold the same 8 channels
+    __shared__ float red[256][9];
+    for (int pass = 0; pass < (HEAD ? 3 : 2); ++pass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = pass == 0 ? acc1[i] : (pass == 1 ? acc2[i] : accw[i]);
+        if (pass == 2) red[threadIdx.x][8] = accb;
+        __syncthreads();
+        for (int c = threadIdx.x; c < p.C + (pass == 2 ? 1 : 0); c += 256) {
+            float s = 0.f;
+            if (c < p.C) {
+                const int g8 = c >> 3, e = c & 7;
+                for (int t = g8; t < 256; t += cgs) s += red[t][e];
+            } else {
+                for (int t = 0; t < 256; t += cgs) s += red[t][8];   // only the cg == 0 threads accumulated dbh
+            }
+            if (pass < 2) p.part[((size_t)blockIdx.x * 2 + pass) * p.C + c] = s;
+            else p.hpart[(size_t)blockIdx.x * 33 + c] = s;
+        }
+        __syncthreads();
+    }
+    if (p.tail.counter) {
+        const bool last = bn_tail_run(p.tail, p.part, (int)gridDim.x, p.C, gridDim.x, threadIdx.x, 0, &red[0][0]);
+        if (HEAD && last) {
+            // head parameter gradients: 33 columns x gridDim.x rows; 7 row lanes per column, eight loads in flight, fixed order
+            __syncthreads();
+            double* shd = reinterpret_cast<double*>(&red[0][0]);   // [7][33]
+            const int col = threadIdx.x % 33, lane = threadIdx.x / 33;
+            if (lane < 7) {
+                double a = 0.0;
+                for (int r0 = lane; r0 < (int)gridDim.x; r0 += 7 * 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = r0 + u * 7;
+                        v[u] = (r < (int)gridDim.x) ? __ldcg(p.hpart + (size_t)r * 33 + col) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a += (double)v[u];
+                }
+                shd[lane * 33 + col] = a;
+            }
+            __syncthreads();
+            if (threadIdx.x < 33) {
+                double a = 0.0;
+                for (int l = 0; l < 7; ++l) a += shd[l * 33 + threadIdx.x];
+                if (threadIdx.x < 32) p.dwh[threadIdx.x] = (float)a;
+                else if (p.dbh) p.dbh[0] = (float)a;
+            }
+        }
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -378,6 +556,22 @@ extern "C" int nunet_grad_router(const nunet_router_desc_t* d, void* stream) {
     const bool hp = n_pool > 0, hu = n_up > 0, hh = d->dlogits != nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     static const bool no_fast = getenv("NUNET_ROUTER_GENERIC") != nullptr;
+    static const bool no_v2 = getenv("NUNET_ROUTER_V1") != nullptr;
+    const bool fused_head = d->head_part != nullptr;
+    if (fused_head && (!hh || d->K != 1 || d->C != 32 || !d->dwh || !d->bn.counter || hu || hp)) return NUNET_E_BADARG;
+    p.hpart = d->head_part; p.dwh = d->dwh; p.dbh = d->dbh;
+    // v2 where it wins: a POOL consumer (window per thread) or the fused head; plain same-resolution sums stay on the 64-register kernel
+    if (!hu && !no_fast && !no_v2 && (hp || fused_head) && !(hp && hh)) {
+#define NUNET_V2_CASE(NS_, P_, H_) if (n_same == NS_ && hp == P_ && hh == H_) grad_router_v2_kernel<NS_, P_, H_><<<rows, 256, 0, st>>>(p)
+        NUNET_V2_CASE(0, false, true); NUNET_V2_CASE(1, false, false); NUNET_V2_CASE(1, false, true); NUNET_V2_CASE(2, false, false);
+        NUNET_V2_CASE(2, false, true); NUNET_V2_CASE(3, false, false); NUNET_V2_CASE(3, false, true); NUNET_V2_CASE(4, false, false);
+        NUNET_V2_CASE(0, true, false); NUNET_V2_CASE(1, true, false); NUNET_V2_CASE(2, true, false); NUNET_V2_CASE(3, true, false);
+        NUNET_V2_CASE(4, true, false); NUNET_V2_CASE(0, false, false);
+#undef NUNET_V2_CASE
+        cudaError_t e0 = cudaGetLastError();
+        return e0 == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e0;
+    }
+    if (fused_head) return NUNET_E_UNSUPPORTED;
     if (!hu && !no_fast) {
 #define NUNET_FAST_CASE(NS_, P_, H_) if (n_same == NS_ && hp == P_ && hh == H_) grad_router_fast_kernel<NS_, P_, H_><<<rows, 256, 0, st>>>(p)
 #define NUNET_FAST_NS(NS_) NUNET_FAST_CASE(NS_, false, false); NUNET_FAST_CASE(NS_, false, true); NUNET_FAST_CASE(NS_, true, false); NUNET_FAST_CASE(NS_, true, true)

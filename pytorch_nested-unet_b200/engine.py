@@ -167,6 +167,14 @@ def _cin_pad(s, packed_input):
     return 32 if (packed_input and s.sources[0][1] == L.SRC_INPUT) else s.cin_pad
 
 
+_WEIGHTS_EPOCH = 0   # bumped by the fused optimizers (optim.py), which update the fp32 masters through raw pointers (no autograd version bump)
+
+
+def weights_updated():
+    global _WEIGHTS_EPOCH
+    _WEIGHTS_EPOCH += 1
+
+
 _CAPTURING_TRAIN = False   # set while a training-step graph is being captured (fork/join of the level streams is capturable)
 
 
@@ -199,9 +207,9 @@ class _State(object):
     def pack(self, spec, plan, mode):
         w = spec.conv.weight
         key = (spec.idx, mode)
-        tag = (w._version, w.data_ptr(), plan.NT, plan.CK)
+        tag = (w._version, w.data_ptr(), plan.NT, plan.CK, _WEIGHTS_EPOCH)
         hit = self.packs.get(key)
-        if hit is not None and (hit[0] == tag or (_CAPTURING_TRAIN and hit[0][1:] == tag[1:])):
+        if hit is not None and (hit[0] == tag or (_CAPTURING_TRAIN and hit[0][1:4] == tag[1:4])):
             return hit[1]
         out = hit[1] if (hit is not None and hit[1].numel() == plan.wpack_elems and hit[1].device == w.device) else None
         out = ops.pack_weights(w, mode, plan, out)
@@ -229,7 +237,7 @@ class _State(object):
                 continue   # the per-layer path converts
             for mode, plan in modes:
                 key = (s.idx, mode)
-                tag = (wt._version, wt.data_ptr(), plan.NT, plan.CK)
+                tag = (wt._version, wt.data_ptr(), plan.NT, plan.CK, _WEIGHTS_EPOCH)
                 hit = self.packs.get(key)
                 if hit is not None and hit[0] == tag and not _CAPTURING_TRAIN:   # a captured step always re-packs (replayed after every update)
                     continue
@@ -257,7 +265,7 @@ def _world(model):
 
 
 class _Record(object):
-    __slots__ = ("y", "a", "a_up", "a_pool", "scale", "shift", "mean", "invstd", "h", "w")
+    __slots__ = ("y", "a", "a_up", "a_pool", "scale", "shift", "mean", "invstd", "h", "w", "logits")
 
 
 def _sources(spec, recs, x, x32=None):
@@ -317,13 +325,21 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
         r.y, _ = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=False, stacked=stacked)
         ops.bn_fold_eval(bn.weight, bn.bias, s.conv.bias, bn.running_mean, bn.running_var, bn.eps, r.scale, r.shift)
     y = r.y
-    # a block's first conv output and the pooled operand are only worth materialising where the TMA-fed kernels take them
-    if (s.which == 2 or (MATERIALIZE_ALL and _tma_width(w))) and MATERIALIZE_NODE_OUTPUTS and s.consumers:
-        r.a = ops.bn_apply(y, r.scale, r.shift)
-        if MATERIALIZE_UPSAMPLED and any(c[2] == L.SRC_UP for c in s.consumers):
-            r.a_up = ops.upsample2x(r.a)
-        if MATERIALIZE_POOLED and _tma_width(w // 2) and any(c[2] == L.SRC_POOL for c in s.consumers):
-            r.a_pool = ops.maxpool2x2(r.a)
+    # One "activate" pass over y writes whatever the consumers read: the activation itself (same-resolution consumers), its 2x2
+    # max-pool, its bilinear 2x upsample, and the logits of a 1x1 head.  (A block's first conv output and the pooled operand are
+    # only worth materialising where the TMA-fed kernels take them.)
+    r.logits = None
+    kinds = [c[2] for c in s.consumers]
+    mat = (s.which == 2 or (MATERIALIZE_ALL and _tma_width(w))) and MATERIALIZE_NODE_OUTPUTS and bool(kinds)
+    want_up = mat and MATERIALIZE_UPSAMPLED and L.SRC_UP in kinds
+    want_pool = mat and MATERIALIZE_POOLED and _tma_width(w // 2) and L.SRC_POOL in kinds
+    want_a = mat and (L.SRC_SAME in kinds or (L.SRC_UP in kinds and not want_up) or (L.SRC_POOL in kinds and not want_pool))
+    head = None
+    if s.head is not None and s.cout == 32 and s.head.out_channels <= 8 and not (want_up or want_pool):
+        K = s.head.out_channels
+        head = (s.head.weight.detach().view(K, -1), s.head.bias.detach() if s.head.bias is not None else None)
+    if want_a or want_up or want_pool or head is not None:
+        r.a, r.a_pool, r.a_up, r.logits = ops.bn_activate(y, r.scale, r.shift, want_a, want_pool, want_up, head)
     return r
 
 
@@ -372,6 +388,9 @@ def _forward(model, x, train, want_dgrad=False):
         if s.head is not None:
             r = recs[s.idx]
             K = s.head.out_channels
+            if r.logits is not None:      # came out of the node's activate pass
+                logits.append((s.idx, r.logits))
+                continue
             with (torch.cuda.stream(ms.lvl[s.level]) if ms is not None else _NOCTX):
                 logits.append((s.idx, ops.head_fwd(r.y, r.scale, r.shift, s.head.weight.detach().view(K, -1), s.head.bias.detach(), N, r.h, r.w)))
     if ms is not None:
@@ -427,6 +446,7 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                     if specs[c_[0]].level != s.level:
                         S.wait_event(dx_done[c_[0]])
             fused = pre.pop(s.idx, None)   # this layer's router ran inside the epilogue of its consumer's dgrad
+            head_grads = None
             cons = []
             for (m, off, kind, j) in (s.consumers if fused is None else ()):
                 dxm = dxs[m][j]            # the consumer's dgrad wrote our channels as one dense tensor
@@ -441,7 +461,11 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                     K = s.head.out_channels
                     wh = s.head.weight.detach().view(K, -1)
                     dwh, dbh = galloc(s.head.weight), galloc(s.head.bias)
-                    ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
+                    # one class (the reference's default): the head's own gradients are accumulated by the router pass itself
+                    if K == 1 and s.cout == 32 and (dp is None or not dp.sync_bn) and all(c[2] == L.SRC_SAME for c in s.consumers):
+                        head_grads = (dwh, dbh)
+                    else:
+                        ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
                     ready += [(s.head.weight, dwh), (s.head.bias, dbh)]
             if not cons and dl is None and fused is None:
                 dl = torch.zeros((N, 1, h, w), dtype=torch.float32, device=dev)
@@ -461,7 +485,8 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
             elif dp is None or not dp.sync_bn:
                 # the router's last CTA reduces its partial sums and emits dgamma / dbeta / k1..k3 (csrc/bn_tail.cuh)
                 tail = ops.bn_bwd_tail(st.counter(s, True), count, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3)
-                gz, _ = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh, tail=tail)
+                gz, _ = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh, tail=tail,
+                                        head_grads=head_grads)
             else:
                 sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
                 tail = ops.bn_bwd_tail(st.counter(s, True), count, None, None, None, None, None, None, None, None, sums_out=sums)
@@ -703,7 +728,11 @@ class _NetFunction(torch.autograd.Function):
             grads = _backward(ctx.model, tg.xs, tg.recs, tg.gl)
             tg.bwd_gen = ctx.gen
             return (None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
-        flat = tg.flat.clone()            # the caller owns its gradients; the graph's buffer is rewritten by the next replay
+        # The graph's flat gradient buffer is rewritten by the next replay.  When no parameter holds a gradient (the usual
+        # optimizer.zero_grad() before backward) autograd adopts the returned tensors as p.grad, and the next replay can only happen
+        # after the next zero_grad released them: hand out views of the buffer itself — stable addresses for the fused optimizer's
+        # pointer table, no 36 MB copy.  Otherwise (gradient accumulation) the caller gets a private copy.
+        flat = tg.flat if all(p.grad is None for p in ctx.params) else tg.flat.clone()
         out = []
         for p in ctx.params:
             if p.requires_grad:
@@ -724,7 +753,7 @@ class _EvalGraph(object):
 
 
 def _weights_tag(params):
-    return (params[0].data_ptr(), sum(p._version for p in params))
+    return (params[0].data_ptr(), sum(p._version for p in params), _WEIGHTS_EPOCH)
 
 
 def _graphed_eval(model, x, params):

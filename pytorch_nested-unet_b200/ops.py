@@ -240,6 +240,28 @@ def bn_apply(y, scale, shift, out=None):
     return out
 
 
+def bn_activate(y, scale, shift, want_a=True, want_pool=False, want_up=False, head=None):
+    """One pass over a raw conv output y (bf16 NHWC): returns (a, a_pool, a_up, logits), each None unless requested.
+    head = (wh [K,32] fp32, bh [K] fp32 or None): the 1x1 head's logits (fp32 NCHW) from the fp32 activation."""
+    N, H, W, Cc = y.shape
+    dev = y.device
+    bf = dict(dtype=torch.bfloat16, device=dev)
+    a = torch.empty((N, H, W, Cc), **bf) if want_a else None
+    ap = torch.empty((N, H // 2, W // 2, Cc), **bf) if want_pool else None
+    au = torch.empty((N, 2 * H, 2 * W, Cc), **bf) if want_up else None
+    d = L.ActivateDesc()
+    d.y, d.N, d.H, d.W, d.C, d.scale, d.shift = y.data_ptr(), N, H, W, Cc, scale.data_ptr(), shift.data_ptr()
+    d.a, d.a_pool, d.a_up = _p(a), _p(ap), _p(au)
+    logits = None
+    if head is not None:
+        wh, bh = head
+        logits = torch.empty((N, wh.shape[0], H, W), dtype=torch.float32, device=dev)
+        d.wh, d.bh, d.K, d.logits = wh.data_ptr(), _p(bh), wh.shape[0], logits.data_ptr()
+    _call("activate", 1, (N, H, W, Cc, int(want_a), int(want_pool), int(want_up), int(head is not None)), "nunet_bn_activate",
+          L.lib().nunet_bn_activate, C.byref(d), _stream())
+    return a, ap, au, logits
+
+
 def upsample2x(a, out=None):
     """bf16 NHWC [N,h,w,C] -> [N,2h,2w,C], bilinear align_corners=True."""
     N, h, w, Cc = a.shape
@@ -333,7 +355,8 @@ class Consumer(object):
         self.dx, self.pitch, self.coff, self.kind = dx, pitch, coff, kind
 
 
-def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, part=None, dlogits=None, wh=None, tail=None):
+def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, part=None, dlogits=None, wh=None, tail=None, head_grads=None):
+    """head_grads = (dwh [K,32], dbh [K] or None): also produce the head's parameter gradients in this pass (K == 1 only; needs tail)."""
     dev = y.device
     rows = L.lib().nunet_grad_router_rows(N, H, W, Cc)
     if gz is None:
@@ -351,6 +374,9 @@ def grad_router(N, H, W, Cc, y, scale, shift, mean, invstd, consumers, gz=None, 
     d.gz, d.part = gz.data_ptr(), part.data_ptr()
     if tail is not None:
         d.bn = tail
+    if head_grads is not None:
+        hp = torch.empty((rows, 33), dtype=torch.float32, device=dev)
+        d.head_part, d.dwh, d.dbh = hp.data_ptr(), head_grads[0].data_ptr(), _p(head_grads[1])
     _call("router", 1, (N, H, W, Cc, len(consumers)), "nunet_grad_router", L.lib().nunet_grad_router, C.byref(d), _stream())
     return gz, part
 

@@ -17,7 +17,7 @@ if HERE not in sys.path:
     sys.path.insert(0, HERE)
 
 import torch
-import torch.optim as optim
+import optim
 import yaml
 from torch.optim import lr_scheduler
 
@@ -169,6 +169,8 @@ def main(argv=None):
         model = nunet_dist.DataParallel(model.cuda())
 
     params = filter(lambda p: p.requires_grad, model.parameters())
+    # same constructors as trains.py:225-233; `optim` here is this package's drop-in (torch.optim subclasses whose step() is one
+    # fused multi-tensor launch, optim.py)
     if config['optimizer'] == 'Adam':
         optimizer = optim.Adam(params, lr=config['lr'], weight_decay=config['weight_decay'])
     else:

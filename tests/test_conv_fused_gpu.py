@@ -136,3 +136,93 @@ def test_router_tail_equals_separate_reduce(N, H, W, C, ncons):
     assert int(counter) == 0 and torch.equal(gz0, gz1)
     for a_, b_ in zip(ref, got):
         assert torch.allclose(a_, b_, rtol=2e-6, atol=1e-7 * max(1.0, float(a_.abs().max()))), float((a_ - b_).abs().max())
+
+
+@pytest.mark.parametrize("N,H,W,C,a,pool,up,K", [(3, 32, 32, 32, True, False, False, 0), (3, 32, 32, 32, True, False, False, 1), (2, 48, 80, 32, False, False, False, 4),
+                                                (2, 32, 48, 32, True, True, False, 0), (2, 16, 24, 64, True, True, True, 0), (3, 8, 8, 128, True, True, True, 0),
+                                                (2, 6, 10, 256, True, True, True, 0), (5, 2, 2, 512, False, False, True, 0), (2, 6, 6, 512, False, False, True, 0),
+                                                (2, 48, 48, 64, False, False, True, 0), (2, 20, 12, 64, True, False, True, 0), (2, 16, 136, 64, True, True, True, 0)])
+def test_activate_equals_separate_kernels_and_torch(N, H, W, C, a, pool, up, K):
+    """nunet_bn_activate against the four launches it replaces (bn_apply, maxpool2x2, upsample2x, head_fwd) and torch fp32."""
+    import ops
+    import torch.nn.functional as F
+    gen = torch.Generator(device=DEV).manual_seed(17 + H + C + K)
+    y = _bf(gen, N, H, W, C, scale=1.5)
+    sc, sh = torch.randn(C, generator=gen, device=DEV), torch.randn(C, generator=gen, device=DEV) * 0.5
+    head = None
+    if K:
+        wh, bh = torch.randn(K, 32, generator=gen, device=DEV) * 0.3, torch.randn(K, generator=gen, device=DEV)
+        head = (wh, bh)
+    ga, gp, gu, gl = ops.bn_activate(y, sc, sh, a, pool, up, head)
+    ref_a = ops.bn_apply(y, sc, sh)
+    torch.cuda.synchronize()
+    assert (ga is not None) == a and (gp is not None) == pool and (gu is not None) == up and (gl is not None) == bool(K)
+    if a:
+        assert torch.equal(ga, ref_a)
+    if pool:
+        assert torch.equal(gp, ops.maxpool2x2(ref_a))
+    if up:
+        # same arithmetic as nunet_upsample2x (blend of the bf16 activation in fp32, one rounding); fma contraction may differ by an ulp
+        ref_u = ops.upsample2x(ref_a).float()
+        assert float((gu.float() - ref_u).abs().max()) <= 0.008 * float(ref_u.abs().max()) + 1e-6
+        t_u = F.interpolate(ref_a.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        assert bool(((gu.float() - t_u).abs() <= 0.008 * t_u.abs() + 1e-5).all())
+    if K:
+        ref_l = ops.head_fwd(y, sc, sh, wh, bh, N, H, W)
+        a32 = torch.relu(y.float() * sc + sh)
+        t_l = (a32.reshape(-1, 32) @ wh.t() + bh).reshape(N, H, W, K).permute(0, 3, 1, 2)
+        assert torch.allclose(gl, ref_l, rtol=1e-5, atol=1e-5) and torch.allclose(gl, t_l, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,H,W,C,ns,pool,head", [(2, 32, 32, 32, 4, True, False), (3, 16, 24, 64, 4, True, False), (2, 8, 8, 128, 3, True, False),
+                                                  (2, 12, 12, 256, 2, True, False), (2, 32, 32, 32, 0, False, True), (3, 48, 80, 32, 3, False, True),
+                                                  (2, 32, 32, 32, 1, False, True), (2, 16, 16, 64, 2, False, False), (2, 32, 272, 32, 2, False, True)])
+def test_router_v2_equals_v1_and_separate_head_gradients(N, H, W, C, ns, pool, head):
+    """The window-per-thread / fused-head router (grad_router_v2_kernel) against round 1's kernels (NUNET_ROUTER_V1 is read once per
+    process, so the v1 result comes from the generic path: a POOL consumer together with a UP-free list is served by both) and, for the
+    head, against nunet_head_bwd_params."""
+    import _lib as L
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(23 + C + ns)
+    y = _bf(gen, N, H, W, C, scale=1.5)
+    sc, sh = torch.randn(C, generator=gen, device=DEV), torch.randn(C, generator=gen, device=DEV) * 0.5
+    mu, rs = torch.randn(C, generator=gen, device=DEV) * 0.3, torch.rand(C, generator=gen, device=DEV) + 0.5
+    gamma = torch.randn(C, generator=gen, device=DEV)
+    cons = [ops.Consumer(_bf(gen, N, H, W, C), C, 0, L.SRC_SAME) for _ in range(ns)]
+    if pool:
+        cons.append(ops.Consumer(_bf(gen, N, H // 2, W // 2, C), C, 0, L.SRC_POOL))
+    dl = wh = None
+    if head:
+        dl = torch.randn(N, 1, H, W, generator=gen, device=DEV) * 0.1
+        wh = torch.randn(1, C, generator=gen, device=DEV) * 0.3
+    # torch reference of the routing: g_a = sum same + max-pool backward (first maximum) + dl*wh ; g_z = g_a*[a>0]
+    a = torch.relu(y.float() * sc + sh)
+    ga = torch.zeros_like(a)
+    for c in cons[:ns]:
+        ga += c.dx.float()
+    if pool:
+        an = a.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        torch.nn.functional.max_pool2d(an, 2, 2).backward(cons[-1].dx.float().permute(0, 3, 1, 2).contiguous())
+        ga += an.grad.permute(0, 2, 3, 1)
+    if head:
+        ga += dl[:, 0, :, :, None] * wh[0]
+    z = y.float() * sc + sh
+    gz_ref = torch.where(z > 0, ga, torch.zeros_like(ga))
+    count = float(N * H * W)
+    got = [torch.empty(C, device=DEV) for _ in range(5)]
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    hg = (torch.empty(1, C, device=DEV), torch.empty(1, device=DEV)) if head else None
+    gz, _ = ops.grad_router(N, H, W, C, y, sc, sh, mu, rs, cons, dlogits=dl, wh=wh, tail=ops.bn_bwd_tail(counter, count, gamma, mu, rs, *got), head_grads=hg)
+    torch.cuda.synchronize()
+    assert int(counter) == 0
+    assert bool(((gz.float() - gz_ref).abs() <= 0.008 * gz_ref.abs() + 1e-6).all())
+    S1 = gz_ref.double().sum((0, 1, 2))
+    S2 = (gz_ref.double() * ((y.double() - mu.double()) * rs.double())).sum((0, 1, 2))
+    scale1 = float(gz_ref.abs().double().sum((0, 1, 2)).max())
+    assert float((got[1].double() - S1).abs().max()) <= 2e-3 * scale1 + 1e-6      # dbeta  (g_z is bf16-rounded on the way)
+    assert float((got[0].double() - S2).abs().max()) <= 4e-3 * scale1 * 3 + 1e-6  # dgamma
+    if head:
+        dwh_ref, dbh_ref = ops.head_bwd_params(y, sc, sh, dl, N, H, W, 1)
+        torch.cuda.synchronize()
+        assert torch.allclose(hg[0], dwh_ref, rtol=1e-4, atol=1e-5 * float(dwh_ref.abs().max()) + 1e-7)
+        assert torch.allclose(hg[1], dbh_ref, rtol=1e-4, atol=1e-6)
