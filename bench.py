@@ -184,14 +184,13 @@ def run_native(args):
     import optim as nunet_optim
     opt = nunet_optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)     # trains.py:229-231 defaults, fused step (optim.py)
     B, S = args.batch, args.size
-    IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)  # albumentations Normalize(), trains.py:266
+    # Synthetic batch in the form the reference's loader reads it from disk: uint8 HWC images and 0/255 masks (dataset.py:58-68).  The
+    # loader's per-pixel arithmetic — albumentations Normalize() (trains.py:266), the extra /255 (dataset.py:71), mask/255 and the
+    # HWC->CHW transposes (dataset.py:72-74) — runs on the GPU (ops.input_u8 / ops.mask_u8), so a step ships 4x fewer bytes.
     g = torch.Generator().manual_seed(1 + rank)
-    u8 = torch.randint(0, 256, (B, 3, S, S), generator=g).float()
-    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
-    x_host = (((u8 / 255.0 - mean) / std) / 255.0).pin_memory()
-    t_host = (torch.rand(B, 1, S, S, generator=g) > 0.5).float().pin_memory()
-    x_dev, t_dev = x_host.to(dev), t_host.to(dev)
+    x_host = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()
+    t_host = ((torch.rand(B, S, S, 1, generator=g) > 0.5).to(torch.uint8) * 255).pin_memory()
+    x_dev, t_dev = x_host.to(dev), ops.mask_u8(t_host.to(dev))
 
     def step(x, t):
         outputs = model(x)
@@ -249,13 +248,13 @@ def run_native(args):
     #      and reads the loss and the two IoU counts back to the host.  (Issuing the copy of batch i+1 on a second stream before
     #      batch i is consumed, utils.DevicePrefetcher, measured no better and noisier on this box: tools/e2e_ab.py.)
     for _ in range(2):
-        step(x_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True))
+        step(x_host.to(dev, non_blocking=True), ops.mask_u8(t_host.to(dev, non_blocking=True)))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
         xb = x_host.to(dev, non_blocking=True)
-        tb = t_host.to(dev, non_blocking=True)
+        tb = ops.mask_u8(t_host.to(dev, non_blocking=True))
         loss, counts = step(xb, tb)
         lv = loss.item()
         i_, u_ = counts.tolist()
@@ -336,7 +335,7 @@ def run_native(args):
                                    "(fwd + BCEDice + IoU + bwd + SGD)" % (args.arch, ds, S, S, B),
                        "global_batch": B * world, "parallelism": "dp%d%s" % (world, "" if world == 1 else ("+syncbn" if not args.no_sync_bn else "")),
                        "l2": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4) * world,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size() + t_host.numel() * t_host.element_size()) * world,
                     "d2h_bytes_per_step": (4 + 16) * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": sampler.summary(),

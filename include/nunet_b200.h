@@ -276,6 +276,13 @@ typedef struct {
 int nunet_maxpool2x2(const void* in, int32_t N, int32_t H, int32_t W, int32_t C, void* out, void* stream);
 /* fp32 NCHW network input [N,C,H,W], C <= 32 -> bf16 NHWC [N,H,W,32] with zero channels >= C (stem conv operand). */
 int nunet_input_to_nhwc32(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* out, void* stream);
+/* Device-side input pipeline (csrc/input.cu): uint8 NHWC image -> ((u8/max_pixel - mean)/std)/post_div (albumentations Normalize(),
+ * trains.py:266, then dataset.py:71's /255; IEEE fp32 divisions in that order) as out_kind 0: bf16 NHWC with 32 zero-padded channels
+ * (the stem conv's operand) or 1: fp32 NCHW.  mean == NULL (out_kind 1 only): value/max_pixel — the mask path of dataset.py:73-74.
+ * aug: optional [N] uint8 per-image geometric augmentation, bits 0-1 = np.rot90 quarter turns (trains.py:257, needs H == W), bit 2 /
+ * bit 3 = horizontal / vertical flip (trains.py:258), applied after the turns. */
+int nunet_input_u8(const uint8_t* img, int32_t N, int32_t H, int32_t W, int32_t C, const float* mean, const float* stdv, float max_pixel,
+                   float post_div, const uint8_t* aug, void* out, int32_t out_kind, void* stream);
 int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout, nunet_wgrad_plan_t* plan);
 int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
 

@@ -37,7 +37,14 @@ class _EngineModel(nn.Module):
     _heads = None
 
     def forward(self, input):
+        """input: fp32 NCHW [N,C,H,W] as in the reference (trains.py:117) — or, with the device-side input pipeline, the raw uint8
+        NHWC image batch [N,H,W,C] (normalised on the GPU with the loader's arithmetic, see set_input_normalization)."""
         return engine.run_model(self, input)
+
+    def set_input_normalization(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), max_pixel=255.0, post_div=255.0):
+        """How a uint8 image batch becomes the network input: ((u8/max_pixel - mean)/std)/post_div.  The defaults are the reference
+        loader's: albumentations Normalize() (trains.py:266) followed by dataset.py:71's `/ 255`."""
+        self.__dict__["_nunet_input_norm"] = dict(mean=tuple(mean), std=tuple(std), max_pixel=float(max_pixel), post_div=float(post_div))
 
 
 class UNet(_EngineModel):

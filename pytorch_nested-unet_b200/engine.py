@@ -349,9 +349,19 @@ def _forward(model, x, train, want_dgrad=False):
     if x.dim() != 4:
         raise ValueError("expected NCHW input")
     ops.require_cuda(x, "input")
-    if x.dtype != torch.float32 or not x.is_contiguous():
-        x = x.float().contiguous()
-    N, Cin, H, W = x.shape
+    # Accepted inputs: the reference's fp32 NCHW tensor (trains.py:113-117); and, as the device-side input pipeline (ops.input_u8),
+    # a raw uint8 NHWC image batch (normalised here with the loader's arithmetic) or its already packed bf16 NHWC32 form.
+    x32 = None
+    if x.dtype == torch.uint8:
+        N, H, W, Cin = x.shape
+        x = x.contiguous()
+    elif x.dtype == torch.bfloat16 and x.shape[-1] == 32 and x.is_contiguous():
+        N, H, W, _ = x.shape
+        Cin, x32 = specs[0].cin_real, x
+    else:
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        N, Cin, H, W = x.shape
     if Cin != specs[0].cin_real:
         raise ValueError("expected %d input channels, got %d" % (specs[0].cin_real, Cin))
     if H % 16 or W % 16:
@@ -362,7 +372,17 @@ def _forward(model, x, train, want_dgrad=False):
     recs = []
     packed_input = PACK_INPUT and _tma_width(W)
     st.pack_all(N, H, W, want_dgrad, packed_input)
-    x32 = ops.input_to_nhwc32(x) if packed_input else None
+    norm = model.__dict__.get("_nunet_input_norm") or {}
+    if x32 is not None:
+        if not packed_input:
+            raise L.NunetError("pre-packed bf16 NHWC32 input needs rows of at most 254 pixels")
+    elif x.dtype == torch.uint8:
+        if packed_input:
+            x32 = ops.input_u8(x, nhwc32=True, **norm)
+        else:
+            x = ops.input_u8(x, nhwc32=False, **norm)
+    elif packed_input:
+        x32 = ops.input_to_nhwc32(x)
     ms = st.streams(dev) if _use_level_streams(train) else None
     main = torch.cuda.current_stream(dev)
     done = {}   # layer idx of a node output -> event recorded after the node's last forward launch
@@ -395,7 +415,7 @@ def _forward(model, x, train, want_dgrad=False):
                 logits.append((s.idx, ops.head_fwd(r.y, r.scale, r.shift, s.head.weight.detach().view(K, -1), s.head.bias.detach(), N, r.h, r.w)))
     if ms is not None:
         ms.join(main)
-    return (x, x32), recs, logits
+    return (x, x32, (N, H, W)), recs, logits
 
 
 def _backward(model, xs, recs, grad_logits, grad_alloc=None):
@@ -403,8 +423,7 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
     (captured steps: views of one flat buffer); default: a fresh tensor, or the data-parallel bucket view."""
     st = _state(model)
     specs = st.specs
-    x, x32 = xs
-    N, _, H, W = x.shape
+    x, x32, (N, H, W) = xs
     dev = x.device
     ws = st.workspace(dev)
     dp = _world(model)
@@ -589,7 +608,7 @@ def _train_graph(model, x, params):
         return None
     if _world(model) is not None and not GRAPH_TRAIN_DP:      # data parallel: the NCCL collectives are captured with the step
         return None
-    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous()):
+    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.uint8, torch.bfloat16) and x.is_contiguous()):
         return None
     if torch.cuda.is_current_stream_capturing():
         return None
@@ -597,7 +616,7 @@ def _train_graph(model, x, params):
     if any(s.bn.momentum is None for s in st.specs):      # cumulative moving average: the factor changes every step
         return None
     graphs = st.__dict__.setdefault("train_graphs", {})
-    key = (tuple(x.shape), x.device.index, tuple(p.data_ptr() for p in params), tuple(p.requires_grad for p in params))
+    key = (tuple(x.shape), x.dtype, x.device.index, tuple(p.data_ptr() for p in params), tuple(p.requires_grad for p in params))
     tg = graphs.get(key)
     if tg is None:
         if len(graphs) >= 4:                               # each slot pins one step's activations
@@ -759,7 +778,7 @@ def _weights_tag(params):
 def _graphed_eval(model, x, params):
     st = _state(model)
     graphs = st.__dict__.setdefault("graphs", {})
-    key = (tuple(x.shape), x.device.index)
+    key = (tuple(x.shape), x.dtype, x.device.index)
     tag = _weights_tag(params)
     g = graphs.get(key)
     if g is None or g.tag != tag:
@@ -800,6 +819,8 @@ def _forward_check(model, x, train, keep=False):
     st = _state(model)
     specs = st.specs
     ops.require_cuda(x, "input")
+    if x.dtype == torch.uint8:      # raw NHWC image batch: the device-side input pipeline in its fp32 NCHW form
+        x = ops.input_u8(x.contiguous(), nhwc32=False, **(model.__dict__.get("_nunet_input_norm") or {}))
     x = x.float().contiguous()
     N, Cin, H, W = x.shape
     if Cin != specs[0].cin_real or H % 16 or W % 16:
@@ -941,7 +962,7 @@ def run_model(model, x):
         return list(outs) if model._returns_list else outs[0]
     if need_grad:
         outs = _NetFunction.apply(model, x, *params)
-    elif (GRAPH_EVAL and not model.training and torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32
+    elif (GRAPH_EVAL and not model.training and torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.uint8)
           and x.is_contiguous() and not torch.cuda.is_current_stream_capturing() and _world(model) is None):
         outs = _graphed_eval(model, x, params)
     else:

@@ -283,9 +283,50 @@ def maxpool2x2(a, out=None):
 def input_to_nhwc32(x, out=None):
     """fp32 NCHW network input -> bf16 NHWC with 32 channels (zero-padded)."""
     N, Cc, H, W = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise L.NunetError("input_to_nhwc32 expects a contiguous fp32 NCHW tensor")
     if out is None:
         out = torch.empty((N, H, W, 32), dtype=torch.bfloat16, device=x.device)
     _call("input_pack", 1, None, "nunet_input_to_nhwc32", L.lib().nunet_input_to_nhwc32, _ptr(x), N, Cc, H, W, _ptr(out), _stream())
+    return out
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # albumentations Normalize() defaults (trains.py:266)
+_NORM_CACHE = {}
+
+
+def _norm_tensors(mean, std, C_, dev):
+    key = (tuple(mean), tuple(std), C_, dev)
+    t = _NORM_CACHE.get(key)
+    if t is None:
+        m = torch.tensor([mean[i % len(mean)] for i in range(C_)], dtype=torch.float32, device=dev)
+        s_ = torch.tensor([std[i % len(std)] for i in range(C_)], dtype=torch.float32, device=dev)
+        t = _NORM_CACHE[key] = (m, s_)
+    return t
+
+
+def input_u8(img, mean=IMAGENET_MEAN, std=IMAGENET_STD, max_pixel=255.0, post_div=255.0, aug=None, nhwc32=True):
+    """uint8 NHWC image batch -> the network input: bf16 NHWC32 (stem operand) or fp32 NCHW; aug: optional uint8 [N] (see header)."""
+    require_cuda(img, "image batch")
+    if img.dtype != torch.uint8 or img.dim() != 4 or not img.is_contiguous():
+        raise L.NunetError("input_u8 expects a contiguous uint8 NHWC tensor")
+    N, H, W, Cc = img.shape
+    m, s_ = _norm_tensors(mean, std, Cc, img.device)
+    out = torch.empty((N, H, W, 32), dtype=torch.bfloat16, device=img.device) if nhwc32 else torch.empty((N, Cc, H, W), dtype=torch.float32, device=img.device)
+    _call("input_pack", 1, None, "nunet_input_u8", L.lib().nunet_input_u8, _ptr(img), N, H, W, Cc, _ptr(m), _ptr(s_), float(max_pixel), float(post_div),
+          _ptr(aug), _ptr(out), 0 if nhwc32 else 1, _stream())
+    return out
+
+
+def mask_u8(mask, max_pixel=255.0, aug=None):
+    """uint8 NHWC mask stack [N,H,W,K] -> fp32 NCHW mask/255 (dataset.py:73-74), with the same geometric augmentation as the image."""
+    require_cuda(mask, "mask batch")
+    if mask.dtype != torch.uint8 or mask.dim() != 4 or not mask.is_contiguous():
+        raise L.NunetError("mask_u8 expects a contiguous uint8 NHWC tensor")
+    N, H, W, K = mask.shape
+    out = torch.empty((N, K, H, W), dtype=torch.float32, device=mask.device)
+    _call("input_pack", 1, None, "nunet_input_u8", L.lib().nunet_input_u8, _ptr(mask), N, H, W, K, _ptr(None), _ptr(None), float(max_pixel), 1.0,
+          _ptr(aug), _ptr(out), 1, _stream())
     return out
 
 

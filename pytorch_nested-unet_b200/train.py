@@ -24,7 +24,7 @@ from torch.optim import lr_scheduler
 import archs
 import losses
 from metrics import iou_score
-from utils import AverageMeter, str2bool
+from utils import AverageMeter, device_target, str2bool
 
 ARCH_NAMES = archs.__all__
 LOSS_NAMES = losses.__all__ + ['BCEWithLogitsLoss']
@@ -69,7 +69,34 @@ def parse_args(argv=None):
     parser.add_argument('--num_workers', default=4, type=int)
     # synthetic-data extension (not in the reference)
     parser.add_argument('--synthetic_batches', default=8, type=int, help='batches per epoch when --dataset synthetic')
+    parser.add_argument('--u8_input', default=True, type=str2bool,
+                        help='synthetic loader yields raw uint8 NHWC images / masks; Normalize() + /255 run on the GPU (4x fewer H2D bytes)')
     return parser.parse_args(argv)
+
+
+def _world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def _rank():
+    import torch.distributed as dist
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def _iou(output, target):
+    """metrics.iou_score (metrics.py:6-18); under data parallelism over the GLOBAL batch (integer counts are all-reduced)."""
+    if _world_size() > 1:
+        import dist as nunet_dist
+        return nunet_dist.global_iou_score(output, target)
+    return iou_score(output, target)
+
+
+def _global_mean(value, device):
+    if _world_size() > 1:
+        import dist as nunet_dist
+        return nunet_dist.global_mean(value, device)
+    return value
 
 
 def _loss_and_iou(config, model, criterion, input, target):
@@ -80,11 +107,11 @@ def _loss_and_iou(config, model, criterion, input, target):
         for output in outputs:
             loss += criterion(output, target)
         loss /= len(outputs)
-        iou = iou_score(outputs[-1], target)
+        iou = _iou(outputs[-1], target)
     else:
         output = model(input)
         loss = criterion(output, target)
-        iou = iou_score(output, target)
+        iou = _iou(output, target)
     return loss, iou
 
 
@@ -94,12 +121,12 @@ def train(config, train_loader, model, criterion, optimizer):
     model.train()
     for input, target, _ in train_loader:
         input = input.cuda(non_blocking=True)
-        target = target.cuda(non_blocking=True)
+        target = device_target(target.cuda(non_blocking=True))
         loss, iou = _loss_and_iou(config, model, criterion, input, target)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
-        avg_meters['loss'].update(loss.item(), input.size(0))
+        avg_meters['loss'].update(_global_mean(loss.item(), input.device), input.size(0))
         avg_meters['iou'].update(iou, input.size(0))
     return OrderedDict([('loss', avg_meters['loss'].avg), ('iou', avg_meters['iou'].avg)])
 
@@ -111,9 +138,9 @@ def validate(config, val_loader, model, criterion):
     with torch.no_grad():
         for input, target, _ in val_loader:
             input = input.cuda(non_blocking=True)
-            target = target.cuda(non_blocking=True)
+            target = device_target(target.cuda(non_blocking=True))
             loss, iou = _loss_and_iou(config, model, criterion, input, target)
-            avg_meters['loss'].update(loss.item(), input.size(0))
+            avg_meters['loss'].update(_global_mean(loss.item(), input.device), input.size(0))
             avg_meters['iou'].update(iou, input.size(0))
     return OrderedDict([('loss', avg_meters['loss'].avg), ('iou', avg_meters['iou'].avg)])
 
@@ -121,8 +148,8 @@ def validate(config, val_loader, model, criterion):
 class SyntheticLoader(object):
     """Yields (img, mask, meta) batches with the shape/distribution of dataset.py:55-76 after trains.py:266."""
 
-    def __init__(self, batches, batch_size, channels, classes, h, w, seed):
-        self.batches, self.shape, self.classes, self.seed = batches, (batch_size, channels, h, w), classes, seed
+    def __init__(self, batches, batch_size, channels, classes, h, w, seed, u8=False):
+        self.batches, self.shape, self.classes, self.seed, self.u8 = batches, (batch_size, channels, h, w), classes, seed, u8
 
     def __len__(self):
         return self.batches
@@ -133,40 +160,50 @@ class SyntheticLoader(object):
         mean = torch.tensor([(0.485, 0.456, 0.406)[i % 3] for i in range(c)]).view(1, c, 1, 1)
         std = torch.tensor([(0.229, 0.224, 0.225)[i % 3] for i in range(c)]).view(1, c, 1, 1)
         for b in range(self.batches):
-            u8 = torch.randint(0, 256, (n, c, h, w), generator=g).float()
-            x = (((u8 / 255.0 - mean) / std) / 255.0).pin_memory()
+            raw = torch.randint(0, 256, (n, c, h, w), generator=g, dtype=torch.uint8)
+            u8 = raw.float()
             # blob-like masks correlated with the image so that the IoU can actually improve
-            t = (torch.nn.functional.avg_pool2d(u8[:, :1], 9, 1, 4) > 128).float().repeat(1, self.classes, 1, 1).pin_memory()
-            yield x, t, {'img_id': ['syn%d_%d' % (b, i) for i in range(n)]}
+            t = (torch.nn.functional.avg_pool2d(u8[:, :1], 9, 1, 4) > 128).float().repeat(1, self.classes, 1, 1)
+            meta = {'img_id': ['syn%d_%d' % (b, i) for i in range(n)]}
+            if self.u8:   # what cv2.imread yields (HWC uint8, dataset.py:58-68): Normalize() + /255 then run on the GPU
+                yield raw.permute(0, 2, 3, 1).contiguous().pin_memory(), (t * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory(), meta
+            else:
+                yield (((u8 / 255.0 - mean) / std) / 255.0).pin_memory(), t.pin_memory(), meta
 
 
 def main(argv=None):
     config = vars(parse_args(argv))
     if config['name'] is None:
         config['name'] = '%s_%s_%s' % (config['dataset'], config['arch'], 'wDS' if config['deep_supervision'] else 'woDS')
-    os.makedirs('models/%s' % config['name'], exist_ok=True)
-    print('-' * 20)
-    for key in config:
-        print('%s: %s' % (key, config[key]))
-    print('-' * 20)
-    with open('models/%s/config.yml' % config['name'], 'w') as f:
-        yaml.dump(config, f)
+    # multi-GPU (torchrun): every rank trains on its own shard of the data; rank 0 alone writes config.yml / log.csv / model.pth
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if rank == 0:
+        os.makedirs('models/%s' % config['name'], exist_ok=True)
+        print('-' * 20)
+        for key in config:
+            print('%s: %s' % (key, config[key]))
+        print('-' * 20)
+        with open('models/%s/config.yml' % config['name'], 'w') as f:
+            yaml.dump(config, f)
 
     if config['loss'] == 'BCEWithLogitsLoss':
         criterion = torch.nn.BCEWithLogitsLoss().cuda()
     else:
         criterion = losses.__dict__[config['loss']]().cuda()
 
-    print("=> creating model %s" % config['arch'])
-    model = archs.__dict__[config['arch']](config['num_classes'], config['input_channels'], config['deep_supervision'])
-    model = model.cuda()
-    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+    if rank == 0:
+        print("=> creating model %s" % config['arch'])
+    if world > 1:
         import torch.distributed as dist
-        import dist as nunet_dist
         if not dist.is_initialized():
             torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
             dist.init_process_group('nccl')
-        model = nunet_dist.DataParallel(model.cuda())
+    model = archs.__dict__[config['arch']](config['num_classes'], config['input_channels'], config['deep_supervision'])
+    model = model.cuda()
+    if world > 1:
+        import dist as nunet_dist
+        model = nunet_dist.DataParallel(model)
 
     params = filter(lambda p: p.requires_grad, model.parameters())
     # same constructors as trains.py:225-233; `optim` here is this package's drop-in (torch.optim subclasses whose step() is one
@@ -189,19 +226,29 @@ def main(argv=None):
     if config['dataset'] != 'synthetic' and os.path.isdir(data_dir):
         raise NotImplementedError("the cv2/albumentations file loader of dataset.py is outside this build's scope; use --dataset synthetic")
     mk = lambda seed, nb: SyntheticLoader(nb, config['batch_size'], config['input_channels'], config['num_classes'],
-                                          config['input_h'], config['input_w'], seed)
-    train_loader, val_loader = mk(41, config['synthetic_batches']), mk(42, max(1, config['synthetic_batches'] // 4))
+                                          config['input_h'], config['input_w'], seed, u8=config.get('u8_input', False))
+    # each rank draws its own batches (seed offset by the rank): the global batch is world x batch_size distinct images
+    train_loader, val_loader = mk(41 + 1000 * rank, config['synthetic_batches']), mk(42 + 1000 * rank, max(1, config['synthetic_batches'] // 4))
 
     log = OrderedDict([('epoch', []), ('lr', []), ('loss', []), ('iou', []), ('val_loss', []), ('val_iou', [])])
     best_iou, trigger = 0, 0
     for epoch in range(config['epochs']):
-        print('Epoch [%d/%d]' % (epoch, config['epochs']))
+        if rank == 0:
+            print('Epoch [%d/%d]' % (epoch, config['epochs']))
         train_log = train(config, train_loader, model, criterion, optimizer)
         val_log = validate(config, val_loader, model, criterion)
         if config['scheduler'] == 'CosineAnnealingLR' or config['scheduler'] == 'MultiStepLR':
             scheduler.step()
         elif config['scheduler'] == 'ReduceLROnPlateau':
             scheduler.step(val_log['loss'])
+        if rank != 0:       # metrics above are already global (all-reduced); only rank 0 logs and checkpoints
+            trigger += 1
+            if val_log['iou'] > best_iou:
+                best_iou, trigger = val_log['iou'], 0
+            if config['early_stopping'] >= 0 and trigger >= config['early_stopping']:
+                break
+            torch.cuda.empty_cache()
+            continue
         print('loss %.4f - iou %.4f - val_loss %.4f - val_iou %.4f' % (train_log['loss'], train_log['iou'], val_log['loss'], val_log['iou']))
         log['epoch'].append(epoch)
         log['lr'].append(config['lr'])

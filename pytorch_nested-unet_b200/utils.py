@@ -74,3 +74,13 @@ class DevicePrefetcher(object):
                     b.record_stream(cur)
             nxt = load()
             yield out
+
+
+def device_target(target, aug=None):
+    """Loss / metric target from what the loader yields: the reference's fp32 NCHW mask tensor is passed through; a raw uint8 NHWC mask
+    stack [N,H,W,K] (0 / 255, before dataset.py:73-74's transpose and /255) is converted on the GPU (ops.mask_u8)."""
+    import torch
+    if torch.is_tensor(target) and target.dtype == torch.uint8:
+        import ops
+        return ops.mask_u8(target.contiguous(), aug=aug)
+    return target
