@@ -350,6 +350,9 @@ def run_native(args):
 
 def main():
     args = parse()
+    # the step runs on ten CUDA streams (five levels + their weight-gradient streams): give each its own hardware queue, so that the
+    # peer-waiting SyncBN tails of one stream can never sit in front of another stream's kernels (must be set before CUDA initialises)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner) are sent to stderr
     sys.stdout.flush()
     real_stdout = os.dup(1)

@@ -53,6 +53,18 @@ typedef struct {
  * counter: ONE zero-initialised uint32 owned by this layer (self-resetting; launches that may overlap need distinct counters).
  * Forward (nn.BatchNorm2d train-mode statistics, finished/archs1.py:19,21): fields as nunet_bn_finalize_train.
  * gamma == NULL: only sums_out ([2][C] fp64) is written — the SyncBN exchange point. */
+/* SyncBN inside the tail (csrc/bn_tail.cuh): world > 1 makes the last CTA exchange its [2][C] fp64 sums with the other ranks of the
+ * node through peer-mapped memory (flags with release / acquire at system scope, peer loads over NVLink, summed in rank order) before
+ * it finalises with `count` = the GLOBAL element count.  data[q]: rank q's slot of THIS layer and direction, [2 epoch parities][2][C]
+ * fp64; flags[q]: rank q's 8 flag words of this slot (word r is written by rank r), zero-initialised once; seq: local epoch counter
+ * of the slot (device memory, zero-initialised once).  Every pointer must be dereferenceable from this device. */
+typedef struct {
+    int32_t world, rank;
+    double* data[8];
+    uint32_t* flags[8];
+    uint32_t* seq;
+} nunet_bn_exchange_t;
+
 typedef struct {
     uint32_t* counter;
     double count;
@@ -61,6 +73,7 @@ typedef struct {
     float momentum, eps;
     float *scale, *shift, *save_mean, *save_invstd;
     double* sums_out;
+    nunet_bn_exchange_t xch;
 } nunet_bn_tail_t;
 /* Backward (sums of nunet_grad_router): fields as nunet_bn_backward_reduce / nunet_bn_backward_from_sums. */
 typedef struct {
@@ -70,6 +83,7 @@ typedef struct {
     float *dgamma, *dbeta, *k1, *k2, *k3;
     float grad_scale;
     double* sums_out;
+    nunet_bn_exchange_t xch;
 } nunet_bn_bwd_tail_t;
 
 /* One fused 3x3 convolution:  out[n,y,x,co] = sum_{src, ci, r, s} T_src(a_src)[n,y+r-1,x+s-1,ci] * W[co,ci,r,s]

@@ -19,16 +19,21 @@ class Src(C.Structure):
                 ("k2", C.c_void_p), ("C", C.c_int32), ("kind", C.c_int32)]
 
 
+class BnExchange(C.Structure):  # nunet_bn_exchange_t
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("data", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("seq", C.c_void_p)]
+
+
 class BnTail(C.Structure):      # nunet_bn_tail_t
     _fields_ = [("counter", C.c_void_p), ("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("conv_bias", C.c_void_p),
                 ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p), ("sums_out", C.c_void_p)]
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p), ("sums_out", C.c_void_p),
+                ("xch", BnExchange)]
 
 
 class BnBwdTail(C.Structure):   # nunet_bn_bwd_tail_t
     _fields_ = [("counter", C.c_void_p), ("count", C.c_double), ("gamma", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p),
                 ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p), ("k3", C.c_void_p),
-                ("grad_scale", C.c_float), ("sums_out", C.c_void_p)]
+                ("grad_scale", C.c_float), ("sums_out", C.c_void_p), ("xch", BnExchange)]
 
 
 class ConvDesc(C.Structure):

@@ -30,11 +30,36 @@ struct BnFinalizeArgs {
     float grad_scale;  // mode 1: multiplies dgamma / dbeta (1/world_size under SyncBN, see dist.py)
 };
 
+// SyncBN across the ranks of one node, INSIDE the tail (no collective launch): every rank's last CTA publishes its [2][C] fp64
+// sums in its own peer-mapped slot, raises a flag in every peer's flag row (release, system scope), waits for the peers' flags
+// (acquire) and sums all ranks' slots in rank order over NVLink peer loads — identical bits on every rank.  `seq` is a device
+// counter of this slot, so replayed CUDA graphs keep exchanging fresh epochs; slots are double-buffered by epoch parity (a peer can
+// only be one epoch ahead: it needs our flag of epoch e+1 before it may overwrite what we read at epoch e).
+struct BnExchange {
+    int world, rank;      // world <= 1: no exchange
+    double* data[8];      // per rank: this slot's [2 parities][2][C] fp64 (peer-mapped)
+    unsigned* flags[8];   // per rank: this slot's [8] flag words, word r written by rank r
+    unsigned* seq;        // local epoch counter of this slot
+};
+
 struct BnTail {
     unsigned* counter;   // nullptr: no tail (the caller launches nunet_bn_finalize_train / nunet_bn_backward_reduce itself)
     double* sums_out;    // optional [2][C] fp64 (SyncBN exchange buffer)
     BnFinalizeArgs fin;  // fin.gamma == nullptr: only sums_out is produced
+    BnExchange xch;      // in-kernel cross-rank reduction of the sums (fin.count is then the GLOBAL count)
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // BatchNorm backward (nn.BatchNorm2d, train): dbeta = S1, dgamma = S2,
 //   g_y = gamma*r*(g_z - S1/M - yhat*S2/M),  yhat = (y-mean)*r   =>   g_y = k1*g_z + k2*y + k3.
@@ -103,13 +128,46 @@ __device__ __forceinline__ bool bn_tail_run(const BnTail& t, const float* part, 
         for (int e = 0; e < 4; ++e) sh[(size_t)lane * 2 * C + g * 4 + e] = acc[e];
     }
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    const bool exchange = t.xch.world > 1;
+    unsigned epoch = 0;
+    if (exchange) {
+        epoch = *t.xch.seq + 1;                              // same value on every rank: all ranks run the same launches
+        double* mine = t.xch.data[t.xch.rank] + (size_t)(epoch & 1u) * 2 * C;
+        for (int c = tid; c < C; c += 256) {
+            double S = 0.0, SS = 0.0;
+            for (int l = 0; l < L; ++l) { S += sh[(size_t)l * 2 * C + c]; SS += sh[(size_t)l * 2 * C + C + c]; }
+            mine[c] = S;
+            mine[C + c] = SS;
+        }
+        __threadfence_system();
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        if (tid < t.xch.world && tid != t.xch.rank) {
+            st_release_sys(t.xch.flags[tid] + t.xch.rank, epoch);           // "rank `rank` has published epoch `epoch`"
+            unsigned spins = 0;
+            while ((int)(ld_acquire_sys(t.xch.flags[t.xch.rank] + tid) - epoch) < 0) {
+                if (++spins > (1u << 28)) { __trap(); }                      // a missing peer must not hang the GPU
+            }
+        }
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    }
     for (int c = tid; c < C; c += 256) {
         double S = 0.0, SS = 0.0;
-        for (int l = 0; l < L; ++l) { S += sh[(size_t)l * 2 * C + c]; SS += sh[(size_t)l * 2 * C + C + c]; }
+        if (exchange) {
+            for (int q = 0; q < t.xch.world; ++q) {          // rank order: bitwise identical totals on every rank
+                const double* src = t.xch.data[q] + (size_t)(epoch & 1u) * 2 * C;
+                S += ld_relaxed_sys_f64(src + c);
+                SS += ld_relaxed_sys_f64(src + C + c);
+            }
+        } else {
+            for (int l = 0; l < L; ++l) { S += sh[(size_t)l * 2 * C + c]; SS += sh[(size_t)l * 2 * C + C + c]; }
+        }
         if (t.sums_out) { t.sums_out[c] = S; t.sums_out[C + c] = SS; }
         if (t.fin.gamma) bn_finalize_channel(t.fin, c, S, SS);
     }
-    if (tid == 0) *t.counter = 0;   // self-resetting for the next launch
+    if (tid == 0) {
+        *t.counter = 0;   // self-resetting for the next launch
+        if (exchange) *t.xch.seq = epoch;
+    }
     return true;
 }
 

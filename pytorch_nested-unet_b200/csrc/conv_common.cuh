@@ -41,8 +41,20 @@ struct ConvParams {
 };
 
 // host: C-ABI descriptor -> kernel parameter block
+static inline void copy_exchange(BnExchange& x, const nunet_bn_exchange_t& e) {
+    x.world = e.world; x.rank = e.rank; x.seq = e.seq;
+    for (int i = 0; i < 8; ++i) { x.data[i] = e.data[i]; x.flags[i] = e.flags[i]; }
+}
+static inline bool exchange_ok(const nunet_bn_exchange_t& e) {
+    if (e.world <= 1) return true;
+    if (e.world > 8 || e.rank < 0 || e.rank >= e.world || !e.seq) return false;
+    for (int i = 0; i < e.world; ++i)
+        if (!e.data[i] || !e.flags[i]) return false;
+    return true;
+}
 static inline BnTail make_bn_tail(const nunet_bn_tail_t& b) {
     BnTail t{};
+    copy_exchange(t.xch, b.xch);
     t.counter = b.counter;
     t.sums_out = b.sums_out;
     t.fin.mode = 0; t.fin.count = b.count; t.fin.gamma = b.gamma; t.fin.beta = b.beta; t.fin.conv_bias = b.conv_bias;
@@ -52,7 +64,7 @@ static inline BnTail make_bn_tail(const nunet_bn_tail_t& b) {
 }
 static inline bool bn_tail_ok(const nunet_bn_tail_t& b, const float* stat_part) {
     if (!b.counter) return true;
-    if (!stat_part || b.count <= 0) return false;
+    if (!stat_part || b.count <= 0 || !exchange_ok(b.xch)) return false;
     if (b.gamma) return b.beta && b.scale && b.shift;
     return b.sums_out != nullptr;
 }

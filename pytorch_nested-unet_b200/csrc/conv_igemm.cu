@@ -793,6 +793,8 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
             p.tail.fin.save_mean = const_cast<float*>(b.save_mean); p.tail.fin.save_invstd = const_cast<float*>(b.save_invstd);
             p.tail.fin.dgamma = b.dgamma; p.tail.fin.dbeta = b.dbeta; p.tail.fin.k1 = b.k1; p.tail.fin.k2 = b.k2; p.tail.fin.k3 = b.k3;
             p.tail.fin.grad_scale = b.grad_scale;
+            if (!exchange_ok(b.xch)) return NUNET_E_BADARG;
+            copy_exchange(p.tail.xch, b.xch);
         }
     }
     p.res_b = (pl.nchunks == 1 && resident_weights(pl.NT)) ? 1 : 0;

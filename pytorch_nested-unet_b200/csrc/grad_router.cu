@@ -551,6 +551,8 @@ extern "C" int nunet_grad_router(const nunet_router_desc_t* d, void* stream) {
         p.tail.fin.save_mean = const_cast<float*>(b.save_mean); p.tail.fin.save_invstd = const_cast<float*>(b.save_invstd);
         p.tail.fin.dgamma = b.dgamma; p.tail.fin.dbeta = b.dbeta; p.tail.fin.k1 = b.k1; p.tail.fin.k2 = b.k2; p.tail.fin.k3 = b.k3;
         p.tail.fin.grad_scale = b.grad_scale;
+        if (!exchange_ok(b.xch)) return NUNET_E_BADARG;
+        copy_exchange(p.tail.xch, b.xch);
     }
     const int rows = nunet_grad_router_rows(d->N, d->H, d->W, d->C);
     const bool hp = n_pool > 0, hu = n_up > 0, hh = d->dlogits != nullptr;

@@ -80,6 +80,41 @@ class GradBuckets(object):
         self.works = []
 
 
+class PeerExchange(object):
+    """Peer-mapped exchange slots for the in-kernel SyncBN reduction (csrc/bn_tail.cuh): one symmetric allocation per rank
+    (torch.distributed._symmetric_memory: CUDA VMM handles exchanged over the process group, every rank maps every peer's buffer),
+    carved into per-(layer, direction) slots of [2 epoch parities][2][Cmax] fp64 sums plus 8 flag words, and a local epoch counter
+    per slot.  Nothing here launches a collective: the conv / router kernels' last CTAs talk to each other through these pointers."""
+    CMAX = 512
+
+    def __init__(self, num_slots, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("the in-kernel SyncBN exchange covers one node (<= 8 ranks)")
+        self.slot_bytes = 2 * 2 * self.CMAX * 8
+        self.data_bytes = num_slots * self.slot_bytes
+        total = self.data_bytes + num_slots * 8 * 4
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.seq = torch.zeros(num_slots, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every rank's slots and flags are zero before the first kernel touches a peer
+
+    def slot(self, i):
+        import _lib as L
+        x = L.BnExchange()
+        x.world, x.rank = self.world, self.rank
+        for q in range(self.world):
+            x.data[q] = self.ptrs[q] + i * self.slot_bytes
+            x.flags[q] = self.ptrs[q] + self.data_bytes + i * 32
+        x.seq = self.seq.data_ptr() + 4 * i
+        return x
+
+
 class DataParallel(nn.Module):
     """Wraps archs.UNet / archs.NestedUNet for one-process-per-GPU data parallelism.
 
@@ -103,6 +138,17 @@ class DataParallel(nn.Module):
                 order += [s.head.weight, s.head.bias]
             order += [s.bn.weight, s.bn.bias, s.conv.weight] + ([s.conv.bias] if s.conv.bias is not None else [])
         self.buckets = GradBuckets(order, bucket_bytes, process_group)
+        # SyncBN inside the kernels that produce the sums (no collective launch, CUDA-graph capturable); NCCL all-reduce otherwise
+        self.exchange = None
+        import os
+        dev = next(module.parameters()).device
+        if self.sync_bn and self.world_size > 1 and dev.type == "cuda" and dist.get_backend(process_group) == "nccl" \
+                and os.environ.get("NUNET_PEER_SYNCBN", "1") == "1":
+            try:
+                self.exchange = PeerExchange(2 * len(engine._state(module).specs), dev, process_group)
+            except Exception as exc:    # no peer access / symmetric memory on this system: the NCCL path stays
+                import warnings
+                warnings.warn("nunet: peer-memory SyncBN exchange unavailable (%s); using NCCL all-reduces" % (exc,))
         module.__dict__["_nunet_dp"] = self
 
     # ---- engine hooks

@@ -313,6 +313,11 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
         if dp is None or not dp.sync_bn:
             tail = ops.bn_tail(st.counter(s), count, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, r.scale, r.shift, r.mean, r.invstd)
             r.y, _ = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=True, stacked=stacked, tail=tail)
+        elif dp.exchange is not None:
+            # SyncBN inside the conv's tail: the last CTAs of all ranks exchange their sums through peer memory (dist.PeerExchange)
+            tail = ops.bn_tail(st.counter(s), count * dp.world_size, bn.weight, bn.bias, s.conv.bias, rm, rv, momentum, bn.eps, r.scale, r.shift,
+                               r.mean, r.invstd, xch=dp.exchange.slot(2 * s.idx))
+            r.y, _ = ops.conv3x3(N, h, w, srcs, s.cout, wp, want_stats=True, stacked=stacked, tail=tail)
         else:
             sums = torch.empty((2, s.cout), dtype=torch.float64, device=dev)
             tail = ops.bn_tail(st.counter(s), count, None, None, None, None, None, momentum, bn.eps, None, None, None, None, sums_out=sums)
@@ -435,7 +440,8 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
         side = st.__dict__.get("side_stream")
         if side is None:
             side = st.__dict__["side_stream"] = torch.cuda.Stream(device=dev)
-    buckets = dp.buckets if dp is not None else None
+    # captured steps write into the slot's flat buffer; its single all-reduce is issued after the replay (_NetFunction.backward)
+    buckets = dp.buckets if (dp is not None and grad_alloc is None) else None
     if buckets is not None:
         buckets.begin(dev)
         buckets.side = ms.all(True) if ms is not None else side
@@ -481,7 +487,7 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                     wh = s.head.weight.detach().view(K, -1)
                     dwh, dbh = galloc(s.head.weight), galloc(s.head.bias)
                     # one class (the reference's default): the head's own gradients are accumulated by the router pass itself
-                    if K == 1 and s.cout == 32 and (dp is None or not dp.sync_bn) and all(c[2] == L.SRC_SAME for c in s.consumers):
+                    if K == 1 and s.cout == 32 and (dp is None or not dp.sync_bn or dp.exchange is not None) and all(c[2] == L.SRC_SAME for c in s.consumers):
                         head_grads = (dwh, dbh)
                     else:
                         ops.head_bwd_params(r.y, r.scale, r.shift, dl, N, h, w, K, dwh, dbh)
@@ -501,9 +507,13 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                 k1, k2, k3 = (torch.empty(s.cout, dtype=torch.float32, device=dev) for _ in range(3))
             if fused is not None:
                 pass
-            elif dp is None or not dp.sync_bn:
-                # the router's last CTA reduces its partial sums and emits dgamma / dbeta / k1..k3 (csrc/bn_tail.cuh)
-                tail = ops.bn_bwd_tail(st.counter(s, True), count, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3)
+            elif dp is None or not dp.sync_bn or dp.exchange is not None:
+                # the router's last CTA reduces its partial sums and emits dgamma / dbeta / k1..k3 (csrc/bn_tail.cuh); under SyncBN the
+                # last CTAs of all ranks first exchange their sums through peer memory.  Local gradients are those of the LOCAL mean
+                # loss (= world x the global-loss gradient): dgamma / dbeta are scaled by 1/world so the later AVG keeps the true value
+                wsz = dp.world_size if (dp is not None and dp.sync_bn) else 1
+                tail = ops.bn_bwd_tail(st.counter(s, True), count * wsz, s.bn.weight, r.mean, r.invstd, dgamma, dbeta, k1, k2, k3, grad_scale=1.0 / wsz,
+                                       xch=dp.exchange.slot(2 * s.idx + 1) if wsz > 1 else None)
                 gz, _ = ops.grad_router(N, h, w, s.cout, r.y, r.scale, r.shift, r.mean, r.invstd, cons, dlogits=dl, wh=wh, tail=tail,
                                         head_grads=head_grads)
             else:
@@ -553,8 +563,10 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                     dg1, db1 = galloc(sp.bn.weight), galloc(sp.bn.bias)
                     kk = [torch.empty(sp.cout, dtype=torch.float32, device=dev) for _ in range(3)]
                     msk = ops.Mask(rp.y, rp.scale, rp.shift, rp.mean, rp.invstd)
-                    if dp is None or not dp.sync_bn:
-                        bt, sums1 = ops.bn_bwd_tail(st.counter(sp, True), count, sp.bn.weight, rp.mean, rp.invstd, dg1, db1, kk[0], kk[1], kk[2]), None
+                    if dp is None or not dp.sync_bn or dp.exchange is not None:
+                        wsz = dp.world_size if (dp is not None and dp.sync_bn) else 1
+                        bt, sums1 = ops.bn_bwd_tail(st.counter(sp, True), count * wsz, sp.bn.weight, rp.mean, rp.invstd, dg1, db1, kk[0], kk[1], kk[2],
+                                                    grad_scale=1.0 / wsz, xch=dp.exchange.slot(2 * sp.idx + 1) if wsz > 1 else None), None
                     else:
                         sums1 = torch.empty((2, sp.cout), dtype=torch.float64, device=dev)
                         bt = ops.bn_bwd_tail(st.counter(sp, True), count, None, None, None, None, None, None, None, None, sums_out=sums1)
@@ -606,8 +618,9 @@ def _train_graph(model, x, params):
     """The graph slot of this (shape, parameter set), or None when the step has to run eagerly."""
     if not GRAPH_TRAIN or ops.kernel_timing_enabled():
         return None
-    if _world(model) is not None and not GRAPH_TRAIN_DP:      # data parallel: the NCCL collectives are captured with the step
-        return None
+    dp_ = _world(model)
+    if dp_ is not None and not GRAPH_TRAIN_DP and not (dp_.sync_bn and dp_.exchange is not None or not dp_.sync_bn):
+        return None      # SyncBN through NCCL all-reduces: 60 collectives inside the step, runs eagerly
     if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.uint8, torch.bfloat16) and x.is_contiguous()):
         return None
     if torch.cuda.is_current_stream_capturing():
@@ -717,7 +730,7 @@ class _NetFunction(torch.autograd.Function):
             tg.views = offs
             if tg.failed:
                 pass
-            elif _world(ctx.model) is None:
+            elif _world(ctx.model) is None or not GRAPH_TRAIN_DP:
                 try:
                     tg.bwd, _, tg.launches_b = _capture(tg, ctx.model, lambda: _backward(ctx.model, tg.xs, tg.recs, tg.gl, grad_alloc=alloc))
                 except Exception as exc:
@@ -743,6 +756,13 @@ class _NetFunction(torch.autograd.Function):
             tg.bwd.replay()
             ops.add_launches(tg.launches_b)
             tg.bwd_gen = ctx.gen
+            dp_ = _world(ctx.model)
+            if dp_ is not None and not GRAPH_TRAIN_DP:
+                # data parallel: ONE all-reduce (AVG) of the flat gradient buffer over NCCL / NVLink right behind the captured backward
+                import torch.distributed as _dist
+                _dist.all_reduce(tg.flat, op=_dist.ReduceOp.AVG if _dist.get_backend(dp_.group) == "nccl" else _dist.ReduceOp.SUM, group=dp_.group)
+                if _dist.get_backend(dp_.group) != "nccl":
+                    tg.flat.div_(dp_.world_size)
         else:                         # backward capture failed earlier: eager backward on the captured forward's activations
             grads = _backward(ctx.model, tg.xs, tg.recs, tg.gl)
             tg.bwd_gen = ctx.gen

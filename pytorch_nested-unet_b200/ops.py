@@ -131,9 +131,13 @@ def _p(t):
     return t.data_ptr() if t is not None else None
 
 
-def bn_tail(counter, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd, sums_out=None):
-    """nunet_bn_tail_t: BatchNorm finalisation in the tail of the conv that produced the statistics.  gamma None -> sums_out only."""
+def bn_tail(counter, count, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd, sums_out=None,
+            xch=None):
+    """nunet_bn_tail_t: BatchNorm finalisation in the tail of the conv that produced the statistics.  gamma None -> sums_out only.
+    xch (L.BnExchange): cross-rank SyncBN inside the tail; `count` is then the global count."""
     t = L.BnTail()
+    if xch is not None:
+        t.xch = xch
     t.counter, t.count = counter.data_ptr(), float(count)
     t.gamma, t.beta, t.conv_bias = _p(gamma), _p(beta), _p(conv_bias)
     t.running_mean, t.running_var, t.momentum, t.eps = _p(running_mean), _p(running_var), float(momentum), float(eps)
@@ -141,9 +145,11 @@ def bn_tail(counter, count, gamma, beta, conv_bias, running_mean, running_var, m
     return t
 
 
-def bn_bwd_tail(counter, count, gamma, save_mean, save_invstd, dgamma, dbeta, k1, k2, k3, grad_scale=1.0, sums_out=None):
+def bn_bwd_tail(counter, count, gamma, save_mean, save_invstd, dgamma, dbeta, k1, k2, k3, grad_scale=1.0, sums_out=None, xch=None):
     """nunet_bn_bwd_tail_t: BatchNorm-backward coefficients in the tail of the kernel that produced the two sums."""
     t = L.BnBwdTail()
+    if xch is not None:
+        t.xch = xch
     t.counter, t.count = counter.data_ptr(), float(count)
     t.gamma, t.save_mean, t.save_invstd = _p(gamma), _p(save_mean), _p(save_invstd)
     t.dgamma, t.dbeta, t.k1, t.k2, t.k3 = _p(dgamma), _p(dbeta), _p(k1), _p(k2), _p(k3)

@@ -172,6 +172,7 @@ class SyntheticLoader(object):
 
 
 def main(argv=None):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per engine stream (see bench.py)
     config = vars(parse_args(argv))
     if config['name'] is None:
         config['name'] = '%s_%s_%s' % (config['dataset'], config['arch'], 'wDS' if config['deep_supervision'] else 'woDS')
