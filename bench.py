@@ -79,6 +79,53 @@ def conv_flops_per_image(arch, size, input_channels=3):
     return fwd, train
 
 
+def network_roofline(arch, size, batch, ds, peaks_, num_classes=1, input_channels=3):
+    """per-layer-max roofline of one training step, t = sum over the conv launches (forward, dgrad, wgrad) of
+    max(FLOPs / P_tensor, algorithmic bytes / BW_hbm), plus the heads / loss as HBM traffic.  Byte model (bf16 activations): a conv
+    reads each concatenated source at its STORED resolution (same-level M*C, pooled 4*M*C, upsampled M*C/4 elements), its weights, and
+    writes one bf16 raw output; dgrad reads dy, y (ReLU mask / BatchNorm backward) and the weights and writes dx per source at stored
+    resolution; wgrad reads the sources and dy and writes the fp32 dW.  Heads + loss per head and pixel: activation read twice (logits,
+    dWh), logits / dlogits / target in fp32.  Reproduces the survey's 25.5 MB/img forward; 90.3 MB/img training (survey: 91.0)."""
+    import engine
+    graph = engine.nested_graph() if arch == "NestedUNet" else engine.unet_graph()
+    nb = engine.NB_FILTER
+    out = {"bytes": 0.0, "flops": 0.0, "hbm_bound_ms": {}, "ms": {}}
+    tot = {k: 0.0 for k in ("burst", "sustained")}
+    hbm_part = {k: 0.0 for k in ("burst", "sustained")}
+    for node, srcs in graph:
+        lvl = int(node[0])
+        m = float(batch) * (size >> lvl) ** 2
+        cout = nb[lvl]
+        for which in (1, 2):
+            src = [(kind, input_channels if kind == "input" else nb[int(s_[0])]) for s_, kind in srcs] if which == 1 else [("same", cout)]
+            cin = sum(c for _, c in src)
+            rd = sum({"input": 2 * m * c, "same": 2 * m * c, "pool": 8 * m * c, "up": 0.5 * m * c}[k] for k, c in src)
+            wb = 2.0 * 9 * cin * cout
+            fl = 2.0 * m * cout * 9 * cin
+            stem = src[0][0] == "input"
+            launches = [(fl, rd + 2 * m * cout + wb)]                                   # forward
+            if not stem:
+                launches.append((fl, 4 * m * cout + wb + rd))                           # dgrad
+            launches.append((fl, rd + 2 * m * cout + 4.0 * 9 * cin * cout))             # wgrad
+            for f, b in launches:
+                out["flops"] += f
+                out["bytes"] += b
+                for key, ptc in (("burst", peaks_["tc_burst"]), ("sustained", peaks_["tc_sustained"])):
+                    t_tc, t_hbm = f / (ptc * 1e12), b / (peaks_["hbm"] * 1e9)
+                    tot[key] += max(t_tc, t_hbm)
+                    if t_hbm >= t_tc:
+                        hbm_part[key] += t_hbm
+    heads = 4 if (ds and arch == "NestedUNet") else 1
+    hb = heads * float(batch) * size * size * (2 * 64 + 20 * num_classes)
+    out["bytes"] += hb
+    for key in tot:
+        tot[key] += hb / (peaks_["hbm"] * 1e9)
+        hbm_part[key] += hb / (peaks_["hbm"] * 1e9)
+        out["ms"][key] = tot[key] * 1e3
+        out["hbm_bound_ms"][key] = hbm_part[key] * 1e3
+    return out
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -121,15 +168,18 @@ def cpu_reference_step_rate(arch, ds, n, size, steps, warmup):
     x, t = O.synthetic_batch(n, size, size, 1, 3, 1, "dsb")
     bufs = {}
     times = []
+    first = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        sd, loss, iou, _, _ = O.train_step(sd, x, t, arch, ds, bufs=bufs)
+        sd, loss, iou, _, outs = O.train_step(sd, x, t, arch, ds, bufs=bufs)
         dt = time.perf_counter() - t0
+        if first is None:
+            first = (x, outs if isinstance(outs, list) else [outs], loss)     # step-0 logits at default init: the numerics check of the native arm
         if i >= warmup:
             times.append(dt)
     times.sort()
     med = times[len(times) // 2]
-    return n / med, med, torch.get_num_threads()
+    return n / med, med, torch.get_num_threads(), first
 
 
 def run_reference(args):
@@ -140,7 +190,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 5))
     warm = 1
     ds = not args.no_ds
-    rate, med, cores = cpu_reference_step_rate(args.arch, ds, n, args.size, steps, warm)
+    rate, med, cores, _ = cpu_reference_step_rate(args.arch, ds, n, args.size, steps, warm)
     sample = "oracle port of trains.py:113-136, %s ds=%s, batch %d @%dx%d fp32 on CPU, median of %d steps after %d warm-up" % (
         args.arch, ds, n, args.size, args.size, steps, warm)
     line = {
@@ -298,34 +348,65 @@ def run_native(args):
         total_ms = sum(timing["by_class"].values())
         _, train_fl = conv_flops_per_image(args.arch, S)
         tflops = train_fl * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        traffic = None
-        try:  # DRAM bytes of the same kernels, from the committed ncu pass (profiles/r01b_traffic.json; batch 256 @96x96 only)
-            tfile = os.path.join(ROOT, "profiles", "r01b_traffic.json")
-            if not os.path.exists(tfile):
-                tfile = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        net = network_roofline(args.arch, S, B, ds, pk)
+        step_ms = ms / args.steps
+        # the dominant kernel: the generic tcgen05 implicit-GEMM conv (forward of the non-stacked layers + every dgrad)
+        dom = [r for r in timing["launches"] if r["class"] in ("conv_fwd", "conv_dgrad") and r["meta"] and r["meta"][-1] == "igemm"]
+        dom_ms = sum(r["ms"] for r in dom)
+        dom_fl = sum(2.0 * r["meta"][0] * r["meta"][1] * r["meta"][2] * r["meta"][3] * r["meta"][4] * 9 for r in dom)
+        dom_by = sum(2.0 * r["meta"][0] * r["meta"][1] * r["meta"][2] * (r["meta"][3] + r["meta"][4]) for r in dom)
+        traffic, tsrc = None, None
+        try:  # DRAM bytes per step from the committed ncu pass of this command (batch 256 @96x96 DS only)
+            tfile = os.path.join(ROOT, "profiles", "r02_traffic.json")
             with open(tfile) as f:
                 tj = json.load(f)
             if tj.get("batch") == B and tj.get("size") == S and args.arch == "NestedUNet" and ds:
-                traffic = tj["conv_dram_bytes_per_step"]
+                traffic, tsrc = tj["all_dram_bytes_per_step"], "profiles/r02_traffic.json (ncu dram__bytes_read+write over one step of this command; not re-measured in this run)"
         except Exception:
             pass
-        roof = {"bound": "tensor", "achieved": tflops, "peak": pk["tc_sustained"], "unit": "TFLOP/s", "frac": tflops / pk["tc_sustained"],
-                "traffic": traffic, "traffic_note": "dram__bytes_read+write summed over the step's conv launches (ncu, profiles/r01b_ncu_launches_step.csv); "
-                                                    "the unit of `achieved` is likewise one step's conv launches",
-                "algorithmic_flops_per_step": train_fl * B, "kernel": "conv3x3_igemm_kernel (forward, dgrad) + conv3x3_wgrad_tma_kernel: all 89 conv launches of one step",
-                "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
-                "kernel_ms_per_step": conv_ms, "all_kernels_ms_per_step": total_ms,
-                "class_ms": {k: round(v, 4) for k, v in sorted(timing["by_class"].items())}}
+        hbm_share = net["hbm_bound_ms"]["sustained"] / net["ms"]["sustained"]
+        roof = {
+            # SURVEY 8d aggregate: sum over layers of max(FLOPs/P_tensor, bytes/BW_hbm) divided by the measured step
+            "bound": "hbm" if hbm_share >= 0.5 else "tensor",
+            "frac": net["ms"]["sustained"] / step_ms,
+            "frac_burst_peaks": net["ms"]["burst"] / step_ms,
+            "achieved": net["bytes"] / (step_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+            "frac_note": "frac = per-layer-max network roofline (%.2f ms with the sustained bf16 peak, %.2f ms with the burst peak; %.0f %% of it in "
+                         "HBM-bound layers) / measured ms_per_step; achieved = algorithmic bytes of the step / step time" % (
+                             net["ms"]["sustained"], net["ms"]["burst"], 100 * hbm_share),
+            "network_roofline_ms": net["ms"], "algorithmic_bytes_per_step": net["bytes"], "algorithmic_flops_per_step": train_fl * B,
+            "traffic": traffic, "traffic_source": tsrc,
+            "peak_source": pk["src"],
+            "dominant_kernel": {"name": "conv3x3_igemm_kernel (tcgen05 implicit GEMM: forward of the non-stacked layers + every dgrad)",
+                                "launches": len(dom), "ms_per_step": dom_ms, "share_of_kernel_time": dom_ms / total_ms if total_ms else None,
+                                "achieved_tflops": dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms else None,
+                                "frac_of_tensor_sustained": dom_fl / (dom_ms * 1e-3) / 1e12 / pk["tc_sustained"] if dom_ms else None,
+                                "achieved_gbs_algorithmic": dom_by / (dom_ms * 1e-3) / 1e9 if dom_ms else None},
+            "conv_class": {"ms_per_step": conv_ms, "achieved_tflops": tflops, "frac_of_tensor_sustained": tflops / pk["tc_sustained"]},
+            "all_kernels_ms_per_step": total_ms,
+            "class_ms": {k: round(v, 4) for k, v in sorted(timing["by_class"].items())}}
         layer_rows = timing["launches"]
         if args.profile_layers:
             os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
             with open(os.path.join(ROOT, "profiles", "layers_latest.json"), "w") as f:
                 json.dump({"batch": B, "size": S, "arch": args.arch, "launches": layer_rows}, f, indent=1)
     cpu = None
+    numerics = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, med, cores = cpu_reference_step_rate(args.arch, ds, 16, S, 3, 1)
+        rate, med, cores, first = cpu_reference_step_rate(args.arch, ds, 16, S, 3, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle port of the reference train step, %s ds=%s batch 16 @%dx%d fp32, median of 3 steps (%.2f s/step)" % (args.arch, ds, S, S, med)}
+        # numerics of this arm on that very batch and initialisation (train mode, default init, the loader's input distribution)
+        torch.manual_seed(0)
+        m0 = getattr(archs, args.arch)(1, 3, ds).to(dev).train()
+        with torch.no_grad():
+            o0 = m0(first[0].to(dev))
+        o0 = o0 if isinstance(o0, list) else [o0]
+        numerics = {"train_mode_logits_relmax_per_head": [float((a_.cpu() - r_).abs().max() / r_.abs().max()) for a_, r_ in zip(o0, first[1])],
+                    "train_mode_logits_rel_l2_per_head": [float((a_.cpu() - r_).norm() / r_.norm()) for a_, r_ in zip(o0, first[1])],
+                    "against": "fp32 CPU oracle port, batch 16, default init (north_star: <= 2e-2 in bf16; an ideal bf16-operand pipeline gives "
+                               "1e-2 .. 4e-2 from head 1 to head 4 in train mode at default init, SURVEY.md 8c finding 2)"}
+        del m0
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_run": warm_run,
@@ -341,6 +422,7 @@ def run_native(args):
             "clocks": sampler.summary(),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "numerics": numerics,
             "last_loss": float(lv), "last_iou": float(iou),
         }
         print(json.dumps(line))

@@ -208,6 +208,8 @@ int nunet_loss_iou_fwd(const float* logits, const float* target, int32_t N, int3
                        double* sums, float* loss, long long* counts, void* stream);
 /* metrics.iou_score counts only: counts[0] = |o & t|, counts[1] = |o | t| with o = sigmoid(logit) > 0.5, t = target > 0.5. */
 int nunet_iou_counts(const float* logits, const float* target, long long total, unsigned long long* counts, void* stream);
+/* val.py:100-105 output stage: out[i] = (uint8)(sigmoid(logits[i]) * 255) (numpy astype('uint8') truncation), same NCHW order. */
+int nunet_sigmoid_u8(const float* logits, long long total, uint8_t* out, void* stream);
 /* dlogits = (gscale ? *gscale : 1) * gmul * d(loss)/d(logits). */
 int nunet_loss_bwd(const float* logits, const float* target, const double* sums, const float* gscale, float gmul, int32_t N,
                    int32_t E, float* dlogits, void* stream);

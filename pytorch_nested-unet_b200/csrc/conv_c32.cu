@@ -34,7 +34,9 @@ struct C32Params {
     int N, H, W, PW;
     int ry, gpi, groups_total;   // rows per group, groups per image
     int box_rows, S, nch, num_src;
-    int dbg;                     // experiment knob NUNET_C32_DBG: 1 = skip the activation tensor loads, 2 = skip the MMAs (wrong results)
+#ifdef NUNET_EXPERIMENT
+    int dbg;                     // experiment builds only (NUNET_C32_DBG): 1 = skip the activation tensor loads, 2 = skip the MMAs (wrong results)
+#endif
     int res_b;                   // 1: all weight chunks resident; 0: one chunk per pipeline stage (keeps >= 3 activation stages in flight)
     int srcC[NUNET_MAX_SRC];
     int a_stage_bytes;
@@ -44,6 +46,11 @@ struct C32Params {
     BnTail tail;                 // BatchNorm finalisation by the last CTA
 };
 
+#ifdef NUNET_EXPERIMENT
+#define C32_DBG(bit) ((p.dbg & (bit)) != 0)
+#else
+#define C32_DBG(bit) false
+#endif
 constexpr int kC32Threads = 320;
 constexpr uint32_t kC32BBytes = 3u * 4u * 96u * 16u;   // one chunk of stacked weights
 constexpr int kC32MaxTiles = 5;
@@ -111,8 +118,8 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                     const int cglob = c * 32;
                     while (cglob >= c0 + p.srcC[si]) { c0 += p.srcC[si]; ++si; }
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], ((p.dbg & 1) ? 0u : a_box_bytes) + (p.res_b ? 0u : kC32BBytes));
-                    if (!(p.dbg & 1)) tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, -1, y0 - 1, n, &full[s]);
+                    mbar_arrive_expect_tx(&full[s], (C32_DBG(1) ? 0u : a_box_bytes) + (p.res_b ? 0u : kC32BBytes));
+                    if (!C32_DBG(1)) tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, -1, y0 - 1, n, &full[s]);
                     if (!p.res_b) bulk_g2s(sB + (size_t)s * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, &full[s]);
                 }
             }
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                         const uint32_t a_t = a_base + (uint32_t)(t * 126) * 4u;    // 64 B per position
 #pragma unroll
                         for (int dr = 0; dr < 3; ++dr) {
-                            if ((p.dbg & 2) && (c | dr) != 0) continue;
+                            if (C32_DBG(2) && (c | dr) != 0) continue;
                             const uint32_t a_lo = a_t + (uint32_t)dr * pw4;
                             const uint32_t b_lo = b_base + (uint32_t)dr * 384u;     // 4 k-groups x 96 rows x 16 B
                             umma_bf16_lohi(d_addr, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)((c | dr) != 0));
@@ -329,11 +336,13 @@ int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStr
     }
     cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem_bytes);
     if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+#ifdef NUNET_EXPERIMENT   // experiment builds only (tools/dbg_c32.py); never compiled into the shipped library
     if (const char* dg = getenv("NUNET_C32_DBG")) p.dbg = (p.stat_part == nullptr) ? atoi(dg) : 0;
-    if (const char* g = getenv("NUNET_C32_GRID")) {   // experiment knob (tools/dbg_c32.py): fewer CTAs -> is the L2->SM path per-SM or chip-wide bound?
+    if (const char* g = getenv("NUNET_C32_GRID")) {   // fewer CTAs -> is the L2->SM path per-SM or chip-wide bound?
         const int v = atoi(g);
         if (v >= 1 && v < grid && p.stat_part == nullptr) grid = v;
     }
+#endif
     conv3x3_c32_kernel<<<grid, kC32Threads, t.smem_bytes, stream>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;

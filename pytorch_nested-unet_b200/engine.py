@@ -788,7 +788,9 @@ GRAPH_EVAL = _os.environ.get("NUNET_GRAPH_EVAL", "1") == "1"
 
 
 class _EvalGraph(object):
-    __slots__ = ("tag", "graph", "x", "outs")
+    __slots__ = ("tag", "graph", "x", "outs", "packs")
+
+MAX_EVAL_GRAPHS = 8      # each slot pins one forward's activations and its own packed-weight images
 
 
 def _weights_tag(params):
@@ -802,15 +804,27 @@ def _graphed_eval(model, x, params):
     tag = _weights_tag(params)
     g = graphs.get(key)
     if g is None or g.tag != tag:
-        with torch.no_grad():
-            _forward(model, x, False)                      # eager warm-up: fills the packed-weight cache, loads kernels
-        torch.cuda.current_stream().synchronize()
+        # A captured graph holds raw pointers to the packed weight images it was captured with.  The shared cache (st.packs) re-packs an
+        # image IN PLACE when another input shape needs a different tiling (CK / NT), which would silently corrupt a graph of this
+        # shape replayed later: every slot owns its images, like the training slots do.
+        graphs.pop(key, None)
+        while len(graphs) >= MAX_EVAL_GRAPHS:
+            graphs.pop(next(iter(graphs)))
         g = _EvalGraph()
-        g.tag = tag
-        g.x = x.clone()
-        g.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(g.graph):
-            _, _, logits = _forward(model, g.x, False)
+        g.packs = {}
+        st.workspace(x.device)       # (re)initialise the per-device state BEFORE the slot's cache is swapped in: it resets st.packs
+        saved_packs, st.packs = st.packs, g.packs
+        try:
+            with torch.no_grad():
+                _forward(model, x, False)                  # eager warm-up: fills this slot's packed-weight cache, loads kernels
+            torch.cuda.current_stream().synchronize()
+            g.tag = tag
+            g.x = x.clone()
+            g.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(g.graph):
+                _, _, logits = _forward(model, g.x, False)
+        finally:
+            st.packs = saved_packs
         g.outs = tuple(t for _, t in logits)
         graphs[key] = g
     g.x.copy_(x)
@@ -966,6 +980,116 @@ class _CheckFunction(torch.autograd.Function):
         grads = _backward_check(ctx.model, ctx.N, ctx.recs, gl)
         ctx.recs = None
         return (None, None) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+# ------------------------------------------------------------------------------------------------ a VGGBlock on its own
+class _BlockFunction(torch.autograd.Function):
+    """conv3x3 -> BN -> ReLU, twice (finished/archs1.py:23-32) as four launches forward (two convs with BatchNorm tails, two activate
+    passes) and the matching backward; the block's input is treated as an already activated bf16 NHWC source."""
+
+    @staticmethod
+    def forward(ctx, block, x, *params):
+        N, Cin, H, W = x.shape
+        dev = x.device
+        cpad = (Cin + 31) // 32 * 32
+        a0 = torch.zeros((N, H, W, cpad), dtype=torch.bfloat16, device=dev)
+        a0[..., :Cin] = x.detach().permute(0, 2, 3, 1)          # layout change only: NCHW fp32 -> bf16 NHWC, channels padded to 32
+        train = block.training
+        st = block.__dict__.setdefault("_nunet_block", {})
+        cnt = st.get("counters")
+        if cnt is None or cnt.device != dev:
+            cnt = st["counters"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        recs, src, cin = [], a0, cpad
+        for i, (conv, bn) in enumerate(((block.conv1, block.bn1), (block.conv2, block.bn2))):
+            cout = conv.out_channels
+            if cout % 32:
+                raise L.NunetError("a standalone VGGBlock needs output channels in multiples of 32")
+            plan = ops.conv_plan(N, H, W, cin, cout)
+            wpk = ops.pack_weights(conv.weight, L.PACK_FWD, plan)
+            scale, shift = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
+            mean = invstd = None
+            srcs = [ops.Source(L.SRC_ACT, src, cin)]
+            if train:
+                mean, invstd = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
+                track = bn.track_running_stats and bn.running_mean is not None
+                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(int(bn.num_batches_tracked) + 1)
+                tail = ops.bn_tail(cnt[i:i + 1], float(N * H * W), bn.weight, bn.bias, conv.bias, bn.running_mean if track else None,
+                                   bn.running_var if track else None, momentum, bn.eps, scale, shift, mean, invstd)
+                y, _ = ops.conv3x3(N, H, W, srcs, cout, wpk, want_stats=True, tail=tail)
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+            else:
+                y, _ = ops.conv3x3(N, H, W, srcs, cout, wpk)
+                ops.bn_fold_eval(bn.weight, bn.bias, conv.bias, bn.running_mean, bn.running_var, bn.eps, scale, shift)
+            a, _, _, _ = ops.bn_activate(y, scale, shift)
+            recs.append((src, cin, y, scale, shift, mean, invstd))
+            src, cin = a, cout
+        ctx.block, ctx.recs, ctx.shape, ctx.params, ctx.train = block, recs, (N, Cin, H, W), params, train
+        return src.permute(0, 3, 1, 2).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        block, (N, Cin, H, W) = ctx.block, ctx.shape
+        if not ctx.train:
+            raise L.NunetError("backward through a standalone VGGBlock needs train mode (batch statistics)")
+        dev = gout.device
+        cnt = block.__dict__["_nunet_block"]["counters"]
+        grads = {}
+        g = gout.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)     # gradient w.r.t. the block's output activation
+        count = float(N * H * W)
+        convs = ((block.conv1, block.bn1), (block.conv2, block.bn2))
+        gz2 = None
+        for i in (1, 0):
+            conv, bn = convs[i]
+            src, cin, y, scale, shift, mean, invstd = ctx.recs[i]
+            cout = conv.out_channels
+            dgam, dbet, k1, k2, k3 = (torch.empty(cout, device=dev) for _ in range(5))
+            if i == 1:
+                tail = ops.bn_bwd_tail(cnt[2:3], count, bn.weight, mean, invstd, dgam, dbet, k1, k2, k3)
+                gz, _ = ops.grad_router(N, H, W, cout, y, scale, shift, mean, invstd, [ops.Consumer(g, cout, 0, L.SRC_SAME)], tail=tail)
+            else:
+                gz, dgam, dbet, k1, k2, k3 = gz2
+            gy = ops.bn_bwd_apply(gz, y, k1, k2, k3, out=gz)
+            dw = torch.empty((cout, cin, 3, 3), device=dev)
+            ops.conv3x3_wgrad(N, H, W, [ops.Source(L.SRC_ACT, src, cin)], cout, gy, dw)
+            grads[id(conv.weight)] = dw[:, :conv.in_channels].contiguous()
+            grads[id(bn.weight)], grads[id(bn.bias)] = dgam, dbet
+            if conv.bias is not None:
+                grads[id(conv.bias)] = torch.zeros_like(conv.bias)     # train-mode BatchNorm cancels the conv bias exactly
+            plan = ops.conv_plan(N, H, W, cout, cin)
+            wpd = ops.pack_weights(conv.weight, L.PACK_DGRAD, plan)
+            if i == 1:      # the first conv's gradient router runs in this dgrad's epilogue
+                _, _, y1, sc1, sh1, mu1, rs1 = ctx.recs[0]
+                c1 = convs[0][0].out_channels
+                d1 = [torch.empty(c1, device=dev) for _ in range(5)]
+                bt = ops.bn_bwd_tail(cnt[3:4], count, convs[0][1].weight, mu1, rs1, *d1)
+                gz1, _ = ops.conv3x3(N, H, W, [ops.Source(L.SRC_ACT, gy, cout)], cin, wpd, cls="conv_dgrad", mask=ops.Mask(y1, sc1, sh1, mu1, rs1), bwd_tail=bt)
+                gz2 = (gz1, *d1)
+            else:
+                dx, _ = ops.conv3x3(N, H, W, [ops.Source(L.SRC_ACT, gy, cout)], cin, wpd, cls="conv_dgrad")
+        gx = dx[..., :Cin].permute(0, 3, 1, 2).float() if ctx.needs_input_grad[1] else None
+        ctx.recs = None
+        return (None, gx) + tuple(grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+
+
+def run_block(block, x):
+    """VGGBlock.forward (finished/archs1.py:23-32) outside a UNet / NestedUNet."""
+    L.lib()
+    ops.require_cuda(x, "input")
+    if x.dim() != 4 or x.shape[1] != block.conv1.in_channels:
+        raise ValueError("expected NCHW input with %d channels" % block.conv1.in_channels)
+    if x.shape[3] + 2 > 256 * 64:
+        raise L.NunetError("unsupported width")
+    x = x.float().contiguous()
+    params = [p for p in block.parameters()]
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)) and block.training:
+        return _BlockFunction.apply(block, x, *params)
+    with torch.no_grad():
+        return _BlockFunction.forward(_NoCtxObj(), block, x, *params)
+
+
+class _NoCtxObj(object):
+    pass
 
 
 def run_model(model, x):

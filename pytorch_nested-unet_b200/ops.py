@@ -208,7 +208,7 @@ def conv3x3(N, H, W, sources, Cout, wpack, out=None, stat_part=None, want_stats=
             d.bn_bwd = bwd_tail
     if cls is None:
         cls = "conv_dgrad" if sources[0].kind == L.SRC_GRAD else "conv_fwd"
-    _call(cls, 1, (N, H, W, cin, Cout), "nunet_conv3x3_fwd", L.lib().nunet_conv3x3_fwd, C.byref(d), _stream())
+    _call(cls, 1, (N, H, W, cin, Cout, "c32" if stacked else "igemm"), "nunet_conv3x3_fwd", L.lib().nunet_conv3x3_fwd, C.byref(d), _stream())
     return out, stat_part
 
 
@@ -370,6 +370,16 @@ def iou_counts(logits, target):
     counts = torch.empty(2, dtype=torch.int64, device=logits.device)
     _call("iou", 1, None, "nunet_iou_counts", L.lib().nunet_iou_counts, _ptr(logits), _ptr(target), logits.numel(), _ptr(counts), _stream())
     return counts
+
+
+def sigmoid_u8(logits):
+    """(sigmoid(logits) * 255).astype('uint8') on the device (val.py:100-105), same shape."""
+    require_cuda(logits, "logits")
+    x = logits.detach()
+    x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _call("val_out", 1, None, "nunet_sigmoid_u8", L.lib().nunet_sigmoid_u8, _ptr(x), x.numel(), _ptr(out), _stream())
+    return out
 
 
 def loss_bwd(logits, target, sums, gscale, gmul=1.0, dlogits=None):

@@ -52,6 +52,37 @@ def grad_sensitivity(archs, losses, g):
             "worst_norm_rel": max(abs(float(b[k].norm()) - float(a[k].norm())) / float(a[k].norm()) for k in a if not k.endswith(skip))}
 
 
+def checkpoint_interchange(archs):
+    """model.pth interchange (trains.py:344-346 / val.py:58-59), recorded from the REFERENCE side:
+      * manifest: key -> (shape, dtype) of the state_dict the unmodified reference modules save, in order;
+      * the reference modules load (strict) a state_dict saved by this repository's archs modules;
+      * logits of the reference in eval mode on a checkpoint written HERE (values are re-created from the seed in the test)."""
+    import io
+    sys.path.insert(0, os.path.join(G.ROOT, "pytorch_nested-unet_b200"))
+    import archs as ours
+    rec = {}
+    for name, args in (("NestedUNet_ds", ("NestedUNet", 1, 3, True)), ("NestedUNet", ("NestedUNet", 1, 3, False)), ("UNet", ("UNet", 1, 3, False)),
+                       ("NestedUNet_c4_ds", ("NestedUNet", 4, 3, True))):
+        arch, k, c, ds = args
+        torch.manual_seed(7)
+        ref = getattr(archs, arch)(k, c, ds)
+        buf = io.BytesIO()
+        torch.save(ref.state_dict(), buf)          # what trains.py:345 writes
+        buf.seek(0)
+        ref_sd = torch.load(buf)
+        torch.manual_seed(7)
+        mine = getattr(ours, arch)(k, c, ds)
+        mine.load_state_dict(ref_sd, strict=True)   # the reference's checkpoint loads here ...
+        buf2 = io.BytesIO()
+        torch.save(mine.state_dict(), buf2)
+        buf2.seek(0)
+        ref2 = getattr(archs, arch)(k, c, ds)
+        ref2.load_state_dict(torch.load(buf2), strict=True)   # ... and a checkpoint written here loads in the reference
+        same = all(torch.equal(a, b) for a, b in zip(ref.state_dict().values(), ref2.state_dict().values()))
+        rec[name] = {"manifest": [(key, tuple(v.shape), str(v.dtype)) for key, v in ref_sd.items()], "round_trip_equal": bool(same)}
+    return rec
+
+
 def main():
     archs, losses, metrics = G.load_ref()
     out = {}
@@ -80,6 +111,7 @@ def main():
         print(name, "gradient sensitivity to a 1e-7 input perturbation: worst rel-L2 %.2e, worst norm %.2e" % (
             max(sens[name]["rell2"].values()), sens[name]["worst_norm_rel"]))
     out["_grad_sensitivity"] = sens
+    out["_checkpoints"] = checkpoint_interchange(archs)
     path = os.path.join(G.ROOT, "tests", "golden", "steps_r02.pt")
     torch.save(out, path)
     print("steps_r02.pt", os.path.getsize(path))

@@ -148,3 +148,28 @@ def test_kernel_selection_policy_for_materialised_operands():
     u = archs.UNet(1, 3)
     us = engine._state(u).specs
     assert [(s.node, s.cin_pad) for s in us if engine._stacked(s, 2, 64 >> s.level, 64 >> s.level, engine._cin_pad(s, True))] == [("0_4", 96)]
+
+
+def test_checkpoint_layout_interchanges_with_the_reference():
+    """model.pth interchange (trains.py:344-346, val.py:58-59).  tests/golden/make_golden_r02.py recorded, with the UNMODIFIED reference
+    modules: the (key, shape, dtype) manifest of the state_dict they save, and that a checkpoint they wrote loads (strict) in this
+    repository's modules, is saved again here and loads (strict) back in the reference with identical values.  Here: every model
+    this package builds has exactly that manifest, and a checkpoint survives torch.save / torch.load / load_state_dict bit for bit."""
+    import io
+    import archs
+    import goldens
+    rec = goldens.load("steps_r02.pt")["_checkpoints"]
+    for name, (arch, k, ds) in (("NestedUNet_ds", ("NestedUNet", 1, True)), ("NestedUNet", ("NestedUNet", 1, False)), ("UNet", ("UNet", 1, False)),
+                                ("NestedUNet_c4_ds", ("NestedUNet", 4, True))):
+        assert rec[name]["round_trip_equal"]
+        torch.manual_seed(1)
+        m = getattr(archs, arch)(k, 3, ds)
+        mine = [(key, tuple(v.shape), str(v.dtype)) for key, v in m.state_dict().items()]
+        assert mine == [tuple(x) for x in rec[name]["manifest"]], name
+        buf = io.BytesIO()
+        torch.save(m.state_dict(), buf)
+        buf.seek(0)
+        torch.manual_seed(2)
+        m2 = getattr(archs, arch)(k, 3, ds)
+        m2.load_state_dict(torch.load(buf), strict=True)
+        assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
