@@ -307,7 +307,8 @@ int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream);
  * nesterov; Adam: betas, eps, weight decay).  tensors_dev: DEVICE array, one entry per parameter (grad == NULL: skipped); chunks_dev:
  * DEVICE array of int32 pairs (tensor index, chunk index) — one CTA per nunet_optim_chunk_elems() elements; hyper_dev: DEVICE fp32
  * [lr, momentum, dampening, weight_decay, nesterov] (SGD) or [lr, beta1, beta2, eps, weight_decay] (Adam), so a captured CUDA graph
- * follows the host's learning-rate schedule; step_dev (Adam): DEVICE int32 step counter, incremented by the call. */
+ * follows the host's learning-rate schedule; step_dev (Adam): DEVICE int32 [ntensors] step counters (torch keeps one per parameter),
+ * advanced by the call for every tensor that had a gradient. */
 enum { NUNET_OPTIM_SGD = 0, NUNET_OPTIM_ADAM = 1 };
 typedef struct {
     float* param;       /* fp32 master, updated in place */
@@ -318,8 +319,8 @@ typedef struct {
 } nunet_optim_tensor_t;
 #define NUNET_OPTIM_FIRST_STEP (1LL << 62)
 int nunet_optim_chunk_elems(void);
-int nunet_optim_step(const nunet_optim_tensor_t* tensors_dev, const int32_t* chunks_dev, int32_t nchunks, const float* hyper_dev,
-                     int32_t algo, int32_t* step_dev, void* stream);
+int nunet_optim_step(const nunet_optim_tensor_t* tensors_dev, int32_t ntensors, const int32_t* chunks_dev, int32_t nchunks,
+                     const float* hyper_dev, int32_t algo, int32_t* step_dev, void* stream);
 
 /* ---- fp32 check mode (forward and backward; csrc/check_fp32.cu) -----------------------------------------------------
  * The reference's fp32 arithmetic on CUDA cores: fp32 NHWC activations with a channel pitch, fp64 BatchNorm statistics.

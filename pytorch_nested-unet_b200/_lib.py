@@ -119,7 +119,7 @@ _SIGS = {
     "nunet_sigmoid_u8": ([C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_input_u8": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p], C.c_int),
     "nunet_optim_chunk_elems": ([], C.c_int),
-    "nunet_optim_step": ([C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_optim_step": ([C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_activate": ([C.POINTER(ActivateDesc), C.c_void_p], C.c_int),
     "nunet_bn_apply": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_bn_bwd_apply": ([C.c_void_p] * 5 + [C.c_longlong, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),

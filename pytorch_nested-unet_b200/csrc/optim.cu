@@ -43,15 +43,15 @@ __global__ void __launch_bounds__(256) optim_sgd_kernel(const nunet_optim_tensor
     }
 }
 
-// hyper: lr, beta1, beta2, eps, weight_decay ; step: device counter (incremented once per launch by block 0 AFTER all blocks read it:
-// every block reads step[0] + 1 as the step number, the update of the counter happens in a separate tiny kernel launched after)
+// hyper: lr, beta1, beta2, eps, weight_decay ; step: one device counter per tensor; every block reads step[tensor] + 1 as the step
+// number, the counters are advanced by a separate tiny kernel launched behind this one
 __global__ void __launch_bounds__(256) optim_adam_kernel(const nunet_optim_tensor_t* __restrict__ tensors, const int2* __restrict__ chunks,
                                                          const float* __restrict__ hyper, const int* __restrict__ step) {
     const int2 ck = chunks[blockIdx.x];
     const nunet_optim_tensor_t t = tensors[ck.x];
     if (!t.grad) return;
     const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4];
-    const double tstep = (double)(step[0] + 1);
+    const double tstep = (double)(step[ck.x] + 1);     // per-tensor step count, as torch keeps it (a tensor without gradient skips the step)
     // torch.optim.adam (_multi_tensor_adam, capturable=False): python-float bias corrections, applied as fp32 scalars
     const double bc1 = 1.0 - pow((double)beta1, tstep), bc2 = 1.0 - pow((double)beta2, tstep);
     const float step_size_neg = (float)(-(double)lr / bc1);
@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) optim_adam_kernel(const nunet_optim_tenso
         t.param[i] = __fmaf_rn(step_size_neg, __fdiv_rn(m, denom), p);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
     }
 }
-__global__ void optim_step_inc_kernel(int* step) { step[0] += 1; }
+__global__ void optim_step_inc_kernel(const nunet_optim_tensor_t* __restrict__ tensors, int ntensors, int* step) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntensors; i += gridDim.x * blockDim.x)
+        if (tensors[i].grad) step[i] += 1;
+}
 
 }  // namespace nunet
 
@@ -83,16 +86,16 @@ using namespace nunet;
 
 extern "C" int nunet_optim_chunk_elems(void) { return kOptChunk; }
 
-extern "C" int nunet_optim_step(const nunet_optim_tensor_t* tensors_dev, const int32_t* chunks_dev, int32_t nchunks, const float* hyper_dev,
-                                int32_t algo, int32_t* step_dev, void* stream) {
-    if (!tensors_dev || !chunks_dev || nchunks < 1 || !hyper_dev || (algo != NUNET_OPTIM_SGD && algo != NUNET_OPTIM_ADAM)) return NUNET_E_BADARG;
+extern "C" int nunet_optim_step(const nunet_optim_tensor_t* tensors_dev, int32_t ntensors, const int32_t* chunks_dev, int32_t nchunks,
+                                const float* hyper_dev, int32_t algo, int32_t* step_dev, void* stream) {
+    if (!tensors_dev || ntensors < 1 || !chunks_dev || nchunks < 1 || !hyper_dev || (algo != NUNET_OPTIM_SGD && algo != NUNET_OPTIM_ADAM)) return NUNET_E_BADARG;
     if (algo == NUNET_OPTIM_ADAM && !step_dev) return NUNET_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (algo == NUNET_OPTIM_SGD) {
         optim_sgd_kernel<<<nchunks, 256, 0, st>>>(tensors_dev, reinterpret_cast<const int2*>(chunks_dev), hyper_dev);
     } else {
         optim_adam_kernel<<<nchunks, 256, 0, st>>>(tensors_dev, reinterpret_cast<const int2*>(chunks_dev), hyper_dev, step_dev);
-        optim_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+        optim_step_inc_kernel<<<(ntensors + 255) / 256, 256, 0, st>>>(tensors_dev, ntensors, step_dev);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;

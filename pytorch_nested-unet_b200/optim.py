@@ -70,7 +70,7 @@ class _FusedMixin(object):
 
     def _launch(self, tab, chunks, n, hyper, step_dev=None):
         ops._call("optimizer", 1 if step_dev is None else 2, None, "nunet_optim_step", L.lib().nunet_optim_step, C.c_void_p(tab.data_ptr()),
-                  C.c_void_p(chunks.data_ptr()), n, C.c_void_p(hyper.data_ptr()), self._algo,
+                  tab.shape[0], C.c_void_p(chunks.data_ptr()), n, C.c_void_p(hyper.data_ptr()), self._algo,
                   C.c_void_p(step_dev.data_ptr()) if step_dev is not None else C.c_void_p(0), ops._stream())
         import engine
         engine.weights_updated()     # the packed bf16 weight images are stale now
@@ -139,13 +139,13 @@ class Adam(_FusedMixin, torch.optim.Adam):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 states.append((st["exp_avg"], st["exp_avg_sq"]))
             step_dev = self.__dict__.setdefault("_step_dev", {}).get(gi)
-            if step_dev is None or step_dev.device != dev:
-                first = self.state[params[0]]["step"]
-                step_dev = self._step_dev[gi] = torch.tensor([int(first)], dtype=torch.int32, device=dev)
+            if step_dev is None or step_dev.device != dev:     # one counter per parameter, seeded from torch's (host) state
+                step_dev = self._step_dev[gi] = torch.tensor([int(self.state[p]["step"]) for p in params], dtype=torch.int32, device=dev)
             tab, chunks, n = self._group_tables(gi, group, states)
             b1, b2 = group["betas"]
             hyper = self._hyper(gi, (group["lr"], b1, b2, group["eps"], group["weight_decay"]), dev)
             self._launch(tab, chunks, n, hyper, step_dev)
             for p in params:                     # torch's per-parameter step counters (host tensors; kept for state_dict compatibility)
-                self.state[p]["step"] += 1
+                if p.grad is not None:
+                    self.state[p]["step"] += 1
         return loss

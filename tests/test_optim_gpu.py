@@ -62,7 +62,8 @@ def test_fused_adam_matches_torch_adam(kw):
         oa.step(); ob.step()
         for x, y in zip(a, b):
             # same operations in the same order; IEEE division / square root vs the fast-math variants of the foreach kernels: a few ulp
-            assert torch.allclose(x, y, rtol=2e-6, atol=1e-9), (step, x.shape, float(((x - y).abs() / (y.abs() + 1e-12)).max()))
+            # (the update is ~lr per element: 1e-8 absolute is 1e-5 of one step's change)
+            assert torch.allclose(x, y, rtol=2e-6, atol=1e-8), (step, tuple(x.shape), float((x - y).abs().max()))
 
 
 def test_no_cpu_fallback():

@@ -1,5 +1,5 @@
 """Summarises an ncu launch list (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv) of
-`bench.py --steps 1 --warmup 2`: isolates ONE steady-state training step (between two input_to_nhwc32 launches), and writes
+`bench.py --steps 1 --warmup 2`: isolates ONE steady-state training step (between two input-pack launches), and writes
 per-kernel-class time shares and DRAM bytes.
 
     python tools/summarize_ncu.py gpurun_out/launches.csv profiles/r01b
@@ -31,7 +31,7 @@ for r in rows:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
         d[m] = v * scale
 L = list(launches.values())
-starts = [k for k, d in enumerate(L) if "input_to_nhwc32" in d["name"]]
+starts = [k for k, d in enumerate(L) if "input_to_nhwc32" in d["name"] or "input_u8_nhwc32" in d["name"]]
 if len(starts) < 3:
     raise SystemExit("need at least 3 steps in the capture, found %d" % len(starts))
 a, b = starts[-2], starts[-1]        # the last complete step of the run (steady state: after the warm-up steps)
@@ -40,8 +40,8 @@ step = L[a - 1:b - 1]                 # the batched weight-pack launch precedes 
 
 def cls(name):
     for key, c in (("conv3x3_wgrad", "conv_wgrad"), ("wgrad_reduce", "conv_wgrad"), ("conv3x3_igemm", "conv_fwd+dgrad"), ("conv3x3_c32", "conv_fwd+dgrad"), ("grad_router", "router"),
-                   ("up_transpose", "up_transpose"), ("upsample2x", "upsample2x"), ("bn_bwd_apply", "bn_bwd_apply"), ("bn_apply", "bn_apply"),
-                   ("bn_", "bn_small"), ("head_", "head"), ("loss_", "loss"), ("iou_", "loss"), ("pack_weights", "pack"), ("input_to", "input_pack"),
+                   ("up_transpose", "up_transpose"), ("upsample2x", "upsample2x"), ("activate_", "activate"), ("optim_", "optimizer"), ("bn_bwd_apply", "bn_bwd_apply"), ("bn_apply", "bn_apply"),
+                   ("bn_", "bn_small"), ("head_", "head"), ("loss_", "loss"), ("iou_", "loss"), ("pack_weights", "pack"), ("input_to", "input_pack"), ("input_u8", "input_pack"),
                    ("maxpool", "maxpool"), ("nccl", "nccl")):
         if key in name:
             return c
