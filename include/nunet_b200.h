@@ -213,6 +213,15 @@ int nunet_sigmoid_u8(const float* logits, long long total, uint8_t* out, void* s
 /* dlogits = (gscale ? *gscale : 1) * gmul * d(loss)/d(logits). */
 int nunet_loss_bwd(const float* logits, const float* target, const double* sums, const float* gscale, float gmul, int32_t N,
                    int32_t E, float* dlogits, void* stream);
+/* LovaszHingeLoss (losses.py:49-96,120-129; csrc/lovasz.cu): logits / target [N][P] fp32 (P = C*H*W of one image, target in {0,1});
+ * per image a descending sort of the hinge errors, the Jaccard gradient of the sorted labels, loss = mean_n dot(relu(e_sorted), grad).
+ * coef [N][P]: d loss_image / d logit (kept for the backward pass); loss_img [N] fp64; loss: fp32 scalar.  scratch:
+ * nunet_lovasz_scratch_elems(N, P) uint64 (0 when an image's pairs fit shared memory: P <= 16384).
+ * bwd: dlogits = coef * (gscale ? *gscale : 1) * gmul   (gmul = 1/N). */
+long long nunet_lovasz_scratch_elems(int32_t N, int32_t P);
+int nunet_lovasz_hinge_fwd(const float* logits, const float* target, int32_t N, int32_t P, unsigned long long* scratch, float* coef,
+                           double* loss_img, float* loss, void* stream);
+int nunet_lovasz_hinge_bwd(const float* coef, const float* gscale, float gmul, long long total, float* dlogits, void* stream);
 /* Head parameter gradients: dwh[k][c] = sum dlogit*a, dbh[k] = sum dlogit. part: [nunet_head_bwd_params_rows()][K][33]. */
 int nunet_head_bwd_params_rows(void);
 int nunet_head_bwd_params(const void* y, const float* scale, const float* shift, const float* dlogits, int32_t N, int32_t H,

@@ -5,6 +5,7 @@ Every function cites the reference lines it restates (paths relative to the refe
   finished/archs1.py:35-71   UNet          -> unet_forward
   finished/archs1.py:74-143  NestedUNet    -> nested_unet_forward
   losses.py:103-117          BCEDiceLoss   -> bce_dice_loss
+  losses.py:49-96,120-129    LovaszHingeLoss -> lovasz_hinge_loss
   metrics.py:6-18            iou_score     -> iou_score / iou_counts
   trains.py:113-136          train step    -> train_step
   trains.py:159-177, val.py:87-98  eval    -> eval_step
@@ -176,6 +177,29 @@ def bce_dice_loss(logits, target):
     dice = (2.0 * inter + smooth) / (p.sum(1) + tt.sum(1) + smooth)
     dice = 1 - dice.sum() / num
     return 0.5 * bce + dice
+
+
+def lovasz_hinge_loss(logits, target):
+    """LovaszHingeLoss.forward (losses.py:120-129) = lovasz_hinge(input.squeeze(1), target.squeeze(1), per_image=True)
+    (losses.py:62-75): per image, errors = 1 - logits*signs sorted descending, the Jaccard gradient of the sorted labels
+    (lovasz_grad, losses.py:49-60), loss = dot(relu(errors_sorted), grad) (lovasz_hinge_flat, losses.py:78-96); mean over images."""
+    x = logits.squeeze(1)
+    t = target.squeeze(1)
+    total = 0
+    for xi, ti in zip(x, t):
+        xi, ti = xi.reshape(-1), ti.reshape(-1)
+        signs = 2.0 * ti.float() - 1.0
+        errors = 1.0 - xi * signs
+        errors_sorted, perm = torch.sort(errors, dim=0, descending=True)
+        gt_sorted = ti[perm]
+        gts = gt_sorted.sum()
+        intersection = gts - gt_sorted.float().cumsum(0)
+        union = gts + (1 - gt_sorted).float().cumsum(0)
+        jaccard = 1.0 - intersection / union
+        if len(gt_sorted) > 1:
+            jaccard = torch.cat([jaccard[:1], jaccard[1:] - jaccard[:-1]])
+        total = total + torch.dot(torch.relu(errors_sorted), jaccard.detach())
+    return total / x.shape[0]
 
 
 def iou_counts(logits, target):

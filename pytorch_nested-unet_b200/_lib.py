@@ -116,6 +116,9 @@ _SIGS = {
     "nunet_bn_backward_from_sums": ([C.c_void_p, C.c_int32, C.c_double] + [C.c_void_p] * 8 + [C.c_float, C.c_void_p], C.c_int),
     "nunet_conv3x3_wgrad_plan": ([C.c_int32] * 5 + [C.POINTER(WgradPlan)], C.c_int),
     "nunet_conv3x3_wgrad": ([C.POINTER(WgradDesc), C.c_void_p], C.c_int),
+    "nunet_lovasz_scratch_elems": ([C.c_int32, C.c_int32], C.c_longlong),
+    "nunet_lovasz_hinge_fwd": ([C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5, C.c_int),
+    "nunet_lovasz_hinge_bwd": ([C.c_void_p, C.c_void_p, C.c_float, C.c_longlong, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_sigmoid_u8": ([C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_input_u8": ([C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p], C.c_int),
     "nunet_optim_chunk_elems": ([], C.c_int),

@@ -372,6 +372,27 @@ def iou_counts(logits, target):
     return counts
 
 
+def lovasz_hinge_fwd(logits, target):
+    """Returns (loss 0-dim fp32, coef [N,P] fp32 = d loss_image / d logit).  logits / target: [N, ...] fp32, flattened per image."""
+    N = logits.shape[0]
+    P = logits.numel() // N
+    dev = logits.device
+    n_scr = L.lib().nunet_lovasz_scratch_elems(N, P)
+    scratch = torch.empty(n_scr, dtype=torch.int64, device=dev) if n_scr else None
+    coef = torch.empty((N, P), dtype=torch.float32, device=dev)
+    limg = torch.empty(N, dtype=torch.float64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _call("loss_fwd", 2, None, "nunet_lovasz_hinge_fwd", L.lib().nunet_lovasz_hinge_fwd, _ptr(logits), _ptr(target), N, P, _ptr(scratch), _ptr(coef),
+          _ptr(limg), _ptr(loss), _stream())
+    return loss, coef
+
+
+def lovasz_hinge_bwd(coef, gscale, gmul, shape):
+    d = torch.empty(shape, dtype=torch.float32, device=coef.device)
+    _call("loss_bwd", 1, None, "nunet_lovasz_hinge_bwd", L.lib().nunet_lovasz_hinge_bwd, _ptr(coef), _ptr(gscale), float(gmul), coef.numel(), _ptr(d), _stream())
+    return d
+
+
 def sigmoid_u8(logits):
     """(sigmoid(logits) * 255).astype('uint8') on the device (val.py:100-105), same shape."""
     require_cuda(logits, "logits")

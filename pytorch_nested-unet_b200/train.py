@@ -27,7 +27,7 @@ from metrics import iou_score
 from utils import AverageMeter, device_target, str2bool
 
 ARCH_NAMES = archs.__all__
-LOSS_NAMES = losses.__all__ + ['BCEWithLogitsLoss']
+LOSS_NAMES = losses.__all__ + ['BCEWithLogitsLoss']      # trains.py:27-28
 
 
 def parse_args(argv=None):

@@ -112,6 +112,19 @@ def main():
             max(sens[name]["rell2"].values()), sens[name]["worst_norm_rel"]))
     out["_grad_sensitivity"] = sens
     out["_checkpoints"] = checkpoint_interchange(archs)
+    lov = {}
+    for name, seed, shape in (("n3_16", 31, (3, 1, 16, 16)), ("n2_96", 32, (2, 1, 96, 96)), ("c4_n2", 33, (2, 4, 16, 32)), ("n1_160", 34, (1, 1, 160, 160))):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(shape, generator=g) * 2
+        t = (torch.rand(shape, generator=g) > 0.6).float()
+        if name == "n3_16":
+            t[1] = 0.0                 # an image without foreground
+        xr = x.clone().requires_grad_(True)
+        loss = losses.LovaszHingeLoss()(xr, t)
+        loss.backward()
+        lov[name] = {"logits": x, "target": t.to(torch.uint8), "loss": float(loss.detach()), "dlogits": xr.grad.clone()}
+        print("lovasz", name, lov[name]["loss"])
+    out["_lovasz"] = lov
     path = os.path.join(G.ROOT, "tests", "golden", "steps_r02.pt")
     torch.save(out, path)
     print("steps_r02.pt", os.path.getsize(path))

@@ -82,3 +82,14 @@ def test_graphs_have_reference_topology():
     assert ng["3_0"] == [("2_0", "pool")]
     ug = dict(O.unet_graph())
     assert len(ug) == 9 and ug["2_2"] == [("2_0", "same"), ("3_1", "up")]
+
+
+@pytest.mark.parametrize("name", ["n3_16", "n2_96", "c4_n2", "n1_160"])
+def test_oracle_lovasz_hinge_matches_reference(name):
+    import goldens
+    g = goldens.load("steps_r02.pt")["_lovasz"][name]
+    x = g["logits"].clone().requires_grad_(True)
+    loss = O.lovasz_hinge_loss(x, g["target"].float())
+    loss.backward()
+    assert abs(float(loss) - g["loss"]) < 1e-6
+    assert torch.allclose(x.grad, g["dlogits"], rtol=1e-5, atol=1e-8)
