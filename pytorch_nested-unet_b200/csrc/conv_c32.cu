@@ -17,11 +17,15 @@
 // swizzle = the K-major SWIZZLE_64B operand with 64-byte rows; tap row dr and tile t are start-address offsets.
 // Weights: [chunk][dr][k-group][dc*32+co][8] (NUNET_PACK_*_C32): all chunks fetched once per CTA and kept resident when three
 // activation stages still fit beside them, else one 18 KB chunk travels with every stage.
-// Warps: 0-7 epilogue (TMEM quadrant x channel half), 8 MMA issuer + TMEM owner, 9 TMA / weight fetcher.  TMEM holds the up
-// to five tiles of a group (480 columns) with one full/empty barrier pair PER TILE: the issuer starts tile t of the next group as
-// soon as the epilogue has drained tile t of the current one, so the epilogue overlaps the following group's MMAs.
-// Epilogue: tcgen05.ld, neighbour exchange by warp shuffles (+ a 2 KB shared-memory hand-off between the four quadrant
-// warps), bf16 NHWC store, per-thread BatchNorm sums reduced once at the end (fixed order: deterministic).
+// Warps: 0-15 epilogue (TMEM lane quadrant x channel quarter), 16 MMA issuer + TMEM owner, 17 TMA / weight fetcher.  TMEM holds
+// the up to five tiles of a group (480 columns) with one full/empty barrier pair PER TILE: the issuer starts tile t of the next
+// group as soon as the epilogue has read tile t of the current one, so the epilogue overlaps the following group's MMAs.
+// Epilogue (round 2: no CTA-wide barrier per tile): tcgen05.ld of the three column blocks, the accumulator is RELEASED as soon as
+// its values sit in registers, neighbour exchange by warp shuffles; the two rows a quadrant needs from its neighbours travel
+// through an eight-deep shared-memory ring with one sequence flag per warp (a warp only ever waits for its two neighbours, and only
+// if they are behind), bf16 NHWC store, per-thread BatchNorm sums reduced once at the end (fixed order: deterministic).
+// Optional fused block-internal gradient router (dgrad of a block's second conv): out = z * [mask_scale*y1 + mask_shift > 0] and
+// the BatchNorm-backward sums, exactly as in conv_igemm.cu.
 #include "conv_common.cuh"
 #include "loaders.cuh"
 #include "tma.cuh"
@@ -44,6 +48,8 @@ struct C32Params {
     __nv_bfloat16* out;
     float* stat_part;            // [gridDim.x][2][32] or null
     BnTail tail;                 // BatchNorm finalisation by the last CTA
+    const __nv_bfloat16* mask_y; // fused block-internal gradient router (see conv_igemm.cu) or null
+    const float *mask_scale, *mask_shift, *mask_mean, *mask_invstd;
 };
 
 #ifdef NUNET_EXPERIMENT
@@ -51,7 +57,9 @@ struct C32Params {
 #else
 #define C32_DBG(bit) false
 #endif
-constexpr int kC32Threads = 320;
+constexpr int kC32Threads = 576;
+constexpr int kC32EpiWarps = 16, kC32MmaWarp = 16, kC32TmaWarp = 17;
+constexpr int kC32Ring = 8;                              // exchange slots per warp (> the five tiles a warp can run ahead of a neighbour)
 constexpr uint32_t kC32BBytes = 3u * 4u * 96u * 16u;   // one chunk of stacked weights
 constexpr int kC32MaxTiles = 5;
 
@@ -60,9 +68,10 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)p.S * p.a_stage_bytes;                         // [nch] resident weight chunks
-    float* s_ex = reinterpret_cast<float*>(sB + (size_t)(p.res_b ? p.nch : p.S) * kC32BBytes);   // [2 parity][4 lq][2 half][2 side][16]
-    float* s_red = s_ex + 2 * 4 * 2 * 2 * 16;                                  // [8 warps][2][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8 * 2 * 16);
+    float* s_ex = reinterpret_cast<float*>(sB + (size_t)(p.res_b ? p.nch : p.S) * kC32BBytes);   // [ring][16 warps][2 sides][8]
+    float* s_red = s_ex + kC32Ring * kC32EpiWarps * 2 * 8;                     // [16 warps][2][8]
+    unsigned* s_flag = reinterpret_cast<unsigned*>(s_red + kC32EpiWarps * 2 * 8);   // [16 warps]: last tile sequence number published
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_flag + kC32EpiWarps);
     uint64_t* full = bars;
     uint64_t* empty = bars + p.S;
     uint64_t* acc_full = bars + 2 * p.S;      // [kC32MaxTiles] MMA -> epilogue, per tile
@@ -70,7 +79,8 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
     uint64_t* b_full = acc_empty + kC32MaxTiles;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
-    if (warp == 8) {
+    if (threadIdx.x < kC32EpiWarps) s_flag[threadIdx.x] = 0u;
+    if (warp == kC32MmaWarp) {
         if (lane == 0) {
             for (int s = 0; s < p.S; ++s) {
                 mbar_init(&full[s], 1);
@@ -78,7 +88,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
             }
             for (int t = 0; t < kC32MaxTiles; ++t) {
                 mbar_init(&acc_full[t], 1);
-                mbar_init(&acc_empty[t], 8);
+                mbar_init(&acc_empty[t], kC32EpiWarps);
             }
             mbar_init(b_full, 1);
             mbar_init_fence();
@@ -94,9 +104,9 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 9) {
+    if (warp == kC32TmaWarp) {
         // =============================== tensor loads + weights
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             for (int si = 0; si < p.num_src; ++si) tma_prefetch_desc(&p.xmap[si]);
             const uint32_t a_box_bytes = (uint32_t)p.box_rows * (uint32_t)p.PW * 64u;
             if ((int)blockIdx.x >= p.groups_total) {
@@ -125,9 +135,9 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
             }
         }
         __syncwarp();
-    } else if (warp == 8) {
+    } else if (warp == kC32MmaWarp) {
         // =============================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             const uint32_t idesc = umma_idesc_bf16(128, 96, kMajorK, kMajorK);
             const uint32_t a_hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B (8 positions), version 1, SWIZZLE_64B
             const uint32_t b_hi = umma_desc_hi(128u);                      // no swizzle: 8-row groups 128 B apart
@@ -171,74 +181,115 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
             }
         }
         __syncwarp();
-    } else {
-        // =============================== epilogue
-        const int lq = warp & 3, half = warp >> 2;
+    } else if (warp < kC32EpiWarps) {
+        // =============================== epilogue: warp = cq*4 + lq (TMEM lane quadrant lq, channels cq*8 .. cq*8+7)
+        const int lq = warp & 3, cq = warp >> 2;
         const int m = lq * 32 + lane;
         const bool want_stats = p.stat_part != nullptr;
-        float ssum[16], ssq[16];
+        const bool masked = p.mask_y != nullptr;
+        float msc[8], msh[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
-        int par = 0;
+        for (int i = 0; i < 8; ++i) {
+            msc[i] = masked ? p.mask_scale[cq * 8 + i] : 0.f;
+            msh[i] = masked ? p.mask_shift[cq * 8 + i] : 0.f;
+        }
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        unsigned seq = 0;
         uint32_t tile_phase = 0;
+        volatile unsigned* vflag = s_flag;
         for (int g = blockIdx.x; g < p.groups_total; g += gridDim.x) {
             const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
             const int rows = min(p.ry, p.H - y0);
             const int ntile = (rows * p.PW + 125) / 126;
-            for (int t = 0; t < ntile; ++t, par ^= 1) {
+            for (int t = 0; t < ntile; ++t) {
+                ++seq;
                 mbar_wait(&acc_full[t], (tile_phase >> t) & 1u);
                 tile_phase ^= 1u << t;
                 tc_fence_after();
-                uint32_t z0[16], z1[16], z2[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * 96 + half * 16);
-                tmem_ld16(taddr, z0);
-                tmem_ld16(taddr + 32u, z1);
-                tmem_ld16(taddr + 64u, z2);
+                uint32_t z0[8], z1[8], z2[8];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * 96 + cq * 8);
+                tmem_ld8(taddr, z0);
+                tmem_ld8(taddr + 32u, z1);
+                tmem_ld8(taddr + 64u, z2);
                 tmem_ld_wait();
-                float* ex = s_ex + (size_t)par * (4 * 2 * 2 * 16);
+                // the accumulator's values are in registers: hand it back to the MMA issuer before the arithmetic and the stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[t]);
+                // publish the two rows the neighbouring quadrants need (ring slot seq % 8, then this warp's sequence flag)
+                float* ex = s_ex + ((size_t)((seq & (kC32Ring - 1)) * kC32EpiWarps + warp) * 2) * 8;
                 if (lane == 31) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) ex[((lq * 2 + half) * 2 + 0) * 16 + i] = __uint_as_float(z0[i]);
+                    for (int i = 0; i < 8; ++i) ex[i] = __uint_as_float(z0[i]);
                 }
                 if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) ex[((lq * 2 + half) * 2 + 1) * 16 + i] = __uint_as_float(z2[i]);
+                    for (int i = 0; i < 8; ++i) ex[8 + i] = __uint_as_float(z2[i]);
                 }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    vflag[warp] = seq;
+                }
                 // this lane's output position inside the group (index u holds pixel u % PW - 1 of row u / PW)
                 const int u = t * 126 + m;
                 const int row = u / p.PW, px = u - row * p.PW - 1;
                 const bool valid = (m >= 1) && (m <= 126) && (row < rows) && (px >= 0) && (px < p.W);
-                float y[16];
+                const size_t pix = ((size_t)n * p.H + (y0 + row)) * p.W + px;
+                uint4 ym = make_uint4(0, 0, 0, 0);
+                if (masked && valid) ym = __ldg(reinterpret_cast<const uint4*>(p.mask_y + pix * 32 + cq * 8));
+                float y[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float l = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[i]), 1);
-                    float r = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[i]), 1);
-                    if (lane == 0 && lq > 0) l = ex[(((lq - 1) * 2 + half) * 2 + 0) * 16 + i];
-                    if (lane == 31 && lq < 3) r = ex[(((lq + 1) * 2 + half) * 2 + 1) * 16 + i];
-                    y[i] = l + __uint_as_float(z1[i]) + r;
+                for (int i = 0; i < 8; ++i) {
+                    const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[i]), 1);
+                    const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[i]), 1);
+                    y[i] = l + __uint_as_float(z1[i]);     // lane 0: l is its own z0 (replaced below); lane 31: r likewise
+                    z2[i] = __float_as_uint(r);
                 }
-                if (valid) {
-                    __nv_bfloat16* dst = p.out + (((size_t)n * p.H + (y0 + row)) * p.W + px) * 32 + half * 16;
-                    uint4 o0, o1;
-                    o0.x = pack_bf16x2(y[0], y[1]); o0.y = pack_bf16x2(y[2], y[3]); o0.z = pack_bf16x2(y[4], y[5]); o0.w = pack_bf16x2(y[6], y[7]);
-                    o1.x = pack_bf16x2(y[8], y[9]); o1.y = pack_bf16x2(y[10], y[11]); o1.z = pack_bf16x2(y[12], y[13]); o1.w = pack_bf16x2(y[14], y[15]);
-                    reinterpret_cast<uint4*>(dst)[0] = o0;
-                    reinterpret_cast<uint4*>(dst)[1] = o1;
-                    if (want_stats) {
+                if (lane == 0 && lq > 0) {                 // z0 of the previous quadrant's last row
+                    unsigned spins = 0;
+                    while ((int)(vflag[warp - 1] - seq) < 0) { if (++spins > (1u << 26)) __trap(); }
+                    __threadfence_block();
+                    const volatile float* src = s_ex + ((size_t)((seq & (kC32Ring - 1)) * kC32EpiWarps + warp - 1) * 2) * 8;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { ssum[i] += y[i]; ssq[i] = fmaf(y[i], y[i], ssq[i]); }
-                    }
+                    for (int i = 0; i < 8; ++i) y[i] = src[i] + __uint_as_float(z1[i]);
                 }
-                tc_fence_before();
+                if (lane == 31 && lq < 3) {                // z2 of the next quadrant's first row
+                    unsigned spins = 0;
+                    while ((int)(vflag[warp + 1] - seq) < 0) { if (++spins > (1u << 26)) __trap(); }
+                    __threadfence_block();
+                    const volatile float* src = s_ex + ((size_t)((seq & (kC32Ring - 1)) * kC32EpiWarps + warp + 1) * 2) * 8 + 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) z2[i] = __float_as_uint(src[i]);
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[t]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] += __uint_as_float(z2[i]);
+                if (valid) {
+                    if (masked) {
+                        float yv[8];
+                        unpack8(ym, yv);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float zz = fmaf(yv[i], msc[i], msh[i]);
+                            y[i] = (zz > 0.f) ? y[i] : 0.f;
+                            ssum[i] += y[i];
+                            ssq[i] = fmaf(y[i], yv[i], ssq[i]);
+                        }
+                    } else if (want_stats) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { ssum[i] += y[i]; ssq[i] = fmaf(y[i], y[i], ssq[i]); }
+                    }
+                    *reinterpret_cast<uint4*>(p.out + pix * 32 + cq * 8) = pack8(y);
+                }
             }
         }
         if (want_stats) {
-            // warp butterfly (fixed order), then the four quadrant warps of a channel half are summed in a fixed order
+            // warp butterfly (fixed order), then the four quadrant warps of a channel quarter are summed in a fixed order
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], off);
@@ -247,23 +298,25 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
             }
             if (lane == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { s_red[(warp * 2 + 0) * 16 + i] = ssum[i]; s_red[(warp * 2 + 1) * 16 + i] = ssq[i]; }
+                for (int i = 0; i < 8; ++i) { s_red[(warp * 2 + 0) * 8 + i] = ssum[i]; s_red[(warp * 2 + 1) * 8 + i] = ssq[i]; }
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (threadIdx.x < 64) {
-                const int which = threadIdx.x >> 5, c = threadIdx.x & 31, h = c >> 4, i = c & 15;
-                float a = 0.f;
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (threadIdx.x < 32) {
+                const int c = threadIdx.x, q = c >> 3, i = c & 7;
+                float a = 0.f, b = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a += s_red[((h * 4 + q) * 2 + which) * 16 + i];
-                p.stat_part[((size_t)blockIdx.x * 2 + which) * 32 + c] = a;
+                for (int l4 = 0; l4 < 4; ++l4) { a += s_red[((q * 4 + l4) * 2 + 0) * 8 + i]; b += s_red[((q * 4 + l4) * 2 + 1) * 8 + i]; }
+                if (masked) b = p.mask_invstd[c] * (b - p.mask_mean[c] * a);     // sum g_z * yhat
+                p.stat_part[((size_t)blockIdx.x * 2 + 0) * 32 + c] = a;
+                p.stat_part[((size_t)blockIdx.x * 2 + 1) * 32 + c] = b;
             }
-            if (p.tail.counter) bn_tail_run(p.tail, p.stat_part, (int)gridDim.x, 32, gridDim.x, threadIdx.x, 2, sA);   // operand stages are idle: free scratch
+            if (p.tail.counter && threadIdx.x < 256) bn_tail_run(p.tail, p.stat_part, (int)gridDim.x, 32, gridDim.x, threadIdx.x, 3, sA);   // operand stages are idle: free scratch
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem_base);
+    if (warp == kC32MmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace nunet
@@ -288,7 +341,7 @@ static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
         const int a = ((box_rows * PW * 64) + 1023) & ~1023;
         // weights resident if that still leaves three activation stages in flight (the 56 KB tensor loads need ~2 stages of
         // latency cover), otherwise one weight chunk travels with every stage
-        const int misc = 2048 + 1024 + 256;
+        const int misc = kC32Ring * kC32EpiWarps * 2 * 8 * 4 + kC32EpiWarps * 2 * 8 * 4 + kC32EpiWarps * 4 + 256;   // exchange ring, stat slots, flags, barriers
         int res_b = 1, S = 4;
         while (S >= 3 && S * a + nch * (int)kC32BBytes + misc > budget) --S;
         if (S < 3) {
@@ -316,20 +369,24 @@ static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
 extern "C" int nunet_conv3x3_c32_eligible(int32_t N, int32_t H, int32_t W, int32_t cin_total, int32_t Cout) {
     static const bool off = getenv("NUNET_NO_C32") != nullptr;
     C32Tiling t;
-    // Cin = 32 (one chunk) measured slower than the generic kernel (0.128 vs 0.104 ms at 96x96, batch 256: the per-tile epilogue
-    // is not hidden behind six MMAs), Cin >= 96 faster (0.199 vs 0.254, 0.323 vs 0.479 ms): tools/dbg_c32.py
-    if (off || Cout != 32 || cin_total < 64 || cin_total % 32 != 0 || N < 1 || H < 1 || W < 1) return 0;
+    // Single-chunk layers (Cin = 32) stay on the generic kernel: 0.097 ms there against 0.166 ms here at 96x96, batch 256, also with the
+    // barrier-free sixteen-warp epilogue of round 2 (tools/ab_epilogue.py; NUNET_C32_MIN_CIN=32 to compare) — with one chunk per group
+    // the single accumulator set serialises tensor loads, MMAs and the drain.  Cin >= 96: 0.193 vs 0.226, 0.318 vs 0.37 ms.
+    static const int min_cin = getenv("NUNET_C32_MIN_CIN") ? atoi(getenv("NUNET_C32_MIN_CIN")) : 64;
+    if (off || Cout != 32 || cin_total < min_cin || cin_total % 32 != 0 || N < 1 || H < 1 || W < 1) return 0;
     return c32_tiling(H, W, cin_total / 32, &t) ? 1 : 0;
 }
 
-int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStream_t stream) {
+int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, const BnTail& tail, cudaStream_t stream) {
     C32Tiling t;
     if (!c32_tiling(d->H, d->W, cin / 32, &t)) return NUNET_E_UNSUPPORTED;
     C32Params p{};
     p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
     p.box_rows = t.box_rows; p.S = t.S; p.res_b = t.res_b; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
     p.wpack = d->wpack; p.out = (__nv_bfloat16*)d->out; p.stat_part = d->stat_part;
-    p.tail = make_bn_tail(d->bn);
+    p.tail = tail;
+    p.mask_y = (const __nv_bfloat16*)d->mask_y; p.mask_scale = d->mask_scale; p.mask_shift = d->mask_shift; p.mask_mean = d->mask_mean;
+    p.mask_invstd = d->mask_invstd;
     for (int i = 0; i < d->num_src; ++i) {
         p.srcC[i] = d->src[i].C;
         if (encode_nhwc_map(&p.xmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, t.PW, 64, t.box_rows, 1) != 0) return NUNET_E_UNSUPPORTED;

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.NT, kMajorK, kMajorK);
             const uint32_t a_lbo = (uint32_t)p.P * 16u, b_lbo = (uint32_t)p.NT * 16u;
             const uint32_t hi = umma_desc_hi(128u);          // SBO = 128 B for both operands
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
         __syncwarp();
     } else if (warp == kFetchWarp) {
         // =============================== weight fetcher (bulk async copy engine)
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)n_tile * p.nchunks * b_bytes;
             int cc = 0;
             PROF_DECL
@@ -736,7 +736,7 @@ static int launch_conv(const ConvParams& p, const nunet_conv_plan_t& pl, cudaStr
     return e == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e;
 }
 
-int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, cudaStream_t stream);
+int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, const nunet::BnTail& tail, cudaStream_t stream);
 
 extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     if (!d || d->num_src < 1 || d->num_src > NUNET_MAX_SRC || !d->wpack || (!d->out && d->num_out_seg <= 0)) return NUNET_E_BADARG;
@@ -810,8 +810,8 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
         case MODE_GRAD: return launch_conv<MODE_GRAD>(p, pl, (cudaStream_t)stream);
         case MODE_ACT: {
             if (d->wpack_layout == 1) {
-                if (!nunet_conv3x3_c32_eligible(d->N, d->H, d->W, cin, d->Cout) || d->mask_y || d->num_out_seg) return NUNET_E_BADARG;
-                return nunet_conv_c32_launch(d, cin, pl.grid_m, (cudaStream_t)stream);
+                if (!nunet_conv3x3_c32_eligible(d->N, d->H, d->W, cin, d->Cout) || d->num_out_seg) return NUNET_E_BADARG;
+                return nunet_conv_c32_launch(d, cin, pl.grid_m, p.tail, (cudaStream_t)stream);
             }
             // tensor-load path: box = (32 ch, W+2 px, 1, 1) per padded row, needs W+2 <= 256 and the CK=32 tiling
             static const bool no_tma = getenv("NUNET_NO_TMA") != nullptr;

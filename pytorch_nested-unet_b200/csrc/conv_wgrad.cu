@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv3x3_wgrad_kernel(const Wgrad
             }
         }
     } else if (warp == kWProducerWarps) {
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             const uint32_t idesc = umma_idesc_bf16(128, TRIPLE ? 96 : 32, kMajorMN, kMajorMN);
             const uint32_t a_hi = umma_desc_hi((uint32_t)p.KP * 16u), b_hi = umma_desc_hi((uint32_t)p.Pg2 * 16u);
             const int ksteps = p.KP >> 4;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv3x3_wgrad_tma_kernel(const _
 
     if (warp == 9) {
         // =============================== TMA issuer
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             for (int si = 0; si < p.num_src; ++si) tma_prefetch_desc(&p.xmap[si]);
             tma_prefetch_desc(&p.gmap);
             int bsrc[4], bch[4];  // (source, channel) of each 32-channel block of this M tile
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv3x3_wgrad_tma_kernel(const _
         __syncwarp();
     } else if (warp == 8) {
         // =============================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the compiler then knows ONE thread runs this (no per-instruction convergence loop around tcgen05 / TMA ops)
             const uint32_t idesc = umma_idesc_bf16(128, 96, kMajorMN, kMajorMN);
             const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B (8 positions), version 1, SWIZZLE_64B
             const uint32_t a_lbo = p.stacked ? (row_bytes >> 4) : ((uint32_t)p.x_block_bytes >> 4);

@@ -231,7 +231,8 @@ class _State(object):
             cinp = _cin_pad(s, packed_input)
             modes = [(L.PACK_FWD_C32 if _stacked(s, N, h, w, cinp) else L.PACK_FWD, ops.conv_plan(N, h, w, cinp, s.cout))]
             if want_dgrad and s.sources[0][0] >= 0:
-                modes.append((L.PACK_DGRAD, ops.conv_plan(N, h, w, s.cout, s.cin_pad)))
+                dstack = (s.which == 2 and FUSE_BLOCK_ROUTER and s.cin_pad == 32 and _tma_width(w) and ops.c32_eligible(N, h, w, s.cout, s.cin_pad))
+                modes.append((L.PACK_DGRAD_C32 if dstack else L.PACK_DGRAD, ops.conv_plan(N, h, w, s.cout, s.cin_pad)))
             wt = s.conv.weight
             if wt.dtype != torch.float32 or not wt.is_contiguous():
                 continue   # the per-layer path converts
@@ -554,7 +555,9 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                 ready.append((s.conv.bias, galloc(s.conv.bias) if (buckets is not None or grad_alloc is not None) else torch.zeros_like(s.conv.bias)))
             if s.sources[0][0] >= 0:
                 plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
-                wpd = st.pack(s, plan, L.PACK_DGRAD)
+                # a dgrad that produces 32 channels (level-0 second convs) runs on the stacked kernel too
+                dstack = (s.which == 2 and FUSE_BLOCK_ROUTER and s.cin_pad == 32 and _tma_width(w) and ops.c32_eligible(N, h, w, s.cout, s.cin_pad))
+                wpd = st.pack(s, plan, L.PACK_DGRAD_C32 if dstack else L.PACK_DGRAD)
                 gsrc = [ops.Source(L.SRC_ACT, gy, s.cout)]
                 if s.which == 2 and FUSE_BLOCK_ROUTER:
                     # the block's first conv has exactly one consumer (this conv): its gradient router — ReLU mask, g_z, the two
@@ -570,7 +573,7 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
                     else:
                         sums1 = torch.empty((2, sp.cout), dtype=torch.float64, device=dev)
                         bt = ops.bn_bwd_tail(st.counter(sp, True), count, None, None, None, None, None, None, None, None, sums_out=sums1)
-                    gz1, _ = ops.conv3x3(N, h, w, gsrc, s.cin_pad, wpd, cls="conv_dgrad", mask=msk, bwd_tail=bt)
+                    gz1, _ = ops.conv3x3(N, h, w, gsrc, s.cin_pad, wpd, cls="conv_dgrad", mask=msk, bwd_tail=bt, stacked=dstack)
                     pre[sp.idx] = (gz1, dg1, db1, kk[0], kk[1], kk[2], sums1)
                 else:
                     dxs[s.idx], _ = ops.conv3x3(N, h, w, gsrc, s.cin_pad, wpd, cls="conv_dgrad", out_segs=[c for _, _, c in s.sources])

@@ -14,13 +14,21 @@ def timeit(fn):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 8
 res = []
-for H, cin, cout, kind in [(96, 32, 32, "stats"), (96, 32, 32, "plain"), (96, 32, 32, "mask"), (96, 32, 96, "plain"), (96, 32, 192, "plain"), (96, 32, 192, "segs"), (48, 64, 64, "stats"), (48, 64, 320, "plain")]:
+for H, cin, cout, kind in [(96, 32, 32, "c32stats"), (96, 32, 32, "c32plain"), (96, 32, 32, "c32mask"), (96, 192, 32, "c32stats"), (96, 96, 32, "c32stats"),(96, 32, 32, "stats"), (96, 32, 32, "plain"), (96, 32, 32, "mask"), (96, 32, 96, "plain"), (96, 32, 192, "plain"), (96, 32, 192, "segs"), (48, 64, 64, "stats"), (48, 64, 320, "plain")]:
     a = torch.rand(N, H, H, cin, generator=g, device=dev).to(torch.bfloat16)
     w = torch.randn(cout, cin, 3, 3, generator=g, device=dev) * 0.05
     plan = ops.conv_plan(N, H, H, cin, cout)
     wp = ops.pack_weights(w, L.PACK_FWD, plan)
     src = [ops.Source(L.SRC_ACT, a, cin)]
-    if kind == "stats": fn = lambda: ops.conv3x3(N, H, H, src, cout, wp, want_stats=True)
+    if kind.startswith("c32"):
+        wpc = ops.pack_weights(w, L.PACK_FWD_C32, plan)
+        if kind == "c32stats": fn = lambda: ops.conv3x3(N, H, H, src, cout, wpc, want_stats=True, stacked=True)
+        elif kind == "c32plain": fn = lambda: ops.conv3x3(N, H, H, src, cout, wpc, stacked=True)
+        else:
+            y1 = torch.randn(N, H, H, cout, generator=g, device=dev).to(torch.bfloat16)
+            sc, sh, mu, rs = (torch.rand(cout, generator=g, device=dev) + 0.5 for _ in range(4))
+            fn = lambda: ops.conv3x3(N, H, H, src, cout, wpc, mask=ops.Mask(y1, sc, sh, mu, rs), stacked=True)
+    elif kind == "stats": fn = lambda: ops.conv3x3(N, H, H, src, cout, wp, want_stats=True)
     elif kind == "plain": fn = lambda: ops.conv3x3(N, H, H, src, cout, wp)
     elif kind == "segs": fn = lambda: ops.conv3x3(N, H, H, src, cout, wp, out_segs=[32] * 4 + [64])
     else:
