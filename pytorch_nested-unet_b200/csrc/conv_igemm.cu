@@ -37,6 +37,7 @@ constexpr int kProducerWarps = 8;
 #define NUNET_DBG_SKIP 0      // experiment builds only (tools/ab_epilogue.sh): 1 no epilogue stores, 2 no MMAs, 4 no activation tensor loads
 #endif
 constexpr int kEpiSlot = 32 * 80;                 // bytes of transpose scratch per epilogue warp
+constexpr uint32_t kStatBytes = 8192;             // per-thread-owned statistic slots
 
 // Shared-memory carve-up, identical on host (sizing) and device.
 struct SmemLayout {
@@ -52,10 +53,9 @@ __host__ __device__ inline SmemLayout conv_smem_layout(bool tma, int T, int NT, 
     L.off_coef = o;    o += tma ? 0u : (uint32_t)cin_pad * 12u;        // per-input-channel loader coefficients
     L.off_mask = o;    o += 2u * NT * 4u;                              // ReLU-mask coefficients of the fused-router epilogue
     L.off_seg = o;     o += 24u * 16u;                                 // output segment of each 32-channel slab {pointer, pitch}
-    // a launch runs either the plain epilogue (transpose scratch) or a statistics epilogue (per-thread-owned slots [<= 8 rows][2][NT])
-    const uint32_t stat_b = 8u * 2u * NT * 4u, epi_b = (uint32_t)epi_warps * kEpiSlot;
-    L.off_stat = o;
-    L.off_epi = o;     o += stat_b > epi_b ? stat_b : epi_b;
+    // statistic slots [4 * TG rows][2][NT] floats, TG = tile groups per lane quadrant (<= 8 KB), then the transpose scratch
+    L.off_stat = o;    o += kStatBytes;
+    L.off_epi = o;     o += (uint32_t)epi_warps * kEpiSlot;
     L.off_bar = o;     o += (2u * S + 6u) * 8u + 16u;
     L.total = o + 128u;
     return L;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                 cbase += cpad;
             }
         }
-        for (int i = threadIdx.x; i < 16 * p.NT; i += kThreads) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < (int)(kStatBytes / 4); i += kThreads) s_stat[i] = 0.f;
         if (p.mask_y)
             for (int c = threadIdx.x; c < p.NT; c += kThreads) {
                 s_mask[c] = p.mask_scale[n_tile * p.NT + c];
@@ -241,33 +241,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
         const bool want_stats = p.stat_part != nullptr;
         const bool masked = p.mask_y != nullptr;         // fused block-internal gradient router (dgrad of a block's second conv)
         const __nv_bfloat16* mask_y = reinterpret_cast<const __nv_bfloat16*>(p.mask_y);
-        // statistic paths: 16-column slabs; a warp owns slab group sg (of G) and tile group tsel (of TG)
-        const int nslab = p.NT >> 4;
-        const int G = nslab < kParts ? nslab : kParts, TG = kParts / G;
+        // statistic paths: 32-column slabs; a warp owns slab group sg (of G) and tile group tsel (of TG)
+        const int nslab32 = p.NT >> 5;
+        int G = kParts;
+        while (G > nslab32) G >>= 1;                     // a divisor of kParts (a power of two)
+        const int TG = kParts / G;
         const int sg = part % G, tsel = part / G;
         float* my_stat = s_stat + (size_t)((lq * TG + tsel) * 2) * p.NT;   // slots written by this warp only (deterministic)
-        int it = 0;
-        PROF_DECL
-        for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
-            const int b = it & 1;
-            const uint32_t k = (uint32_t)(it >> 1);
-            const PixInfo* tab = pixtab + (size_t)b * p.P;
-            const int q0 = tg * group_positions + lq * 32 + lane;   // this lane's output position in tile 0 of the group
+        const int chunk = lane & 3, rsub = lane >> 2;
+        // the tile-group loop is written twice (EPI_GROUP_BEGIN / _END): the statistics path keeps its sums in registers across all
+        // groups, which must not cost the plain path registers
 #ifdef NUNET_POLL1
-            if (lane == 0) { if constexpr (!kTma) mbar_wait(&tab_full[b], k & 1); mbar_wait(&acc_full[b], k & 1); }
-            __syncwarp();
+#define EPI_GROUP_WAIT if (lane == 0) { if constexpr (!kTma) mbar_wait(&tab_full[b], k & 1); mbar_wait(&acc_full[b], k & 1); } __syncwarp();
 #else
-            if constexpr (!kTma) mbar_wait(&tab_full[b], k & 1);
-            mbar_wait(&acc_full[b], k & 1);
+#define EPI_GROUP_WAIT if constexpr (!kTma) mbar_wait(&tab_full[b], k & 1); mbar_wait(&acc_full[b], k & 1);
 #endif
-            PROF_MARK(0)
-            tc_fence_after();
-            const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);
-            if (!want_stats) {
+#define EPI_GROUP_BEGIN                                                                                                   \
+        int it = 0;                                                                                                       \
+        PROF_DECL                                                                                                         \
+        for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {                                                    \
+            const int b = it & 1;                                                                                         \
+            const uint32_t k = (uint32_t)(it >> 1);                                                                       \
+            const PixInfo* tab = pixtab + (size_t)b * p.P;                                                                \
+            const int q0 = tg * group_positions + lq * 32 + lane; /* this lane's output position in tile 0 of the group */ \
+            EPI_GROUP_WAIT                                                                                                \
+            PROF_MARK(0)                                                                                                  \
+            tc_fence_after();                                                                                             \
+            const uint32_t acc = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * p.T * p.NT);                    \
+            (void)tab;
+#define EPI_GROUP_END                                                                                                     \
+            tc_fence_before();                                                                                            \
+            __syncwarp();                                                                                                 \
+            if (lane == 0) mbar_arrive(&acc_empty[b]);                                                                    \
+            PROF_MARK(1)                                                                                                  \
+        }                                                                                                                 \
+        if (eidx == 0 && lane == 0) PROF_FLUSH(4)
+        if (!want_stats) {
+            EPI_GROUP_BEGIN
                 // plain store path (dgrad, eval): 32 columns per TMEM load = 64 bytes per pixel row.  A lane owns a ROW, so a direct
                 // store would touch 32 different 128-byte lines per instruction; the 32x64 B tile is transposed through a padded
                 // per-warp smem scratch so that four lanes write one row's 64 contiguous bytes (8 lines per store instruction).
-                const int nslab32 = p.NT >> 5;
                 uint8_t* scratch = s_epi + (size_t)eidx * kEpiSlot;
                 for (int wi = part; wi < p.T * nslab32; wi += kParts) {
                     const int t = wi / nslab32, cs = wi - t * nslab32;
@@ -298,92 +311,120 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                     }
                     __syncwarp();
                 }
-            } else {
-                for (int cs = sg; cs < nslab; cs += G) {
-                    float ssum[16], ssq[16];
+            EPI_GROUP_END
+        } else {
+            // a lane owns 8 channels (chunk) of every 8th row (rsub) of a 32x32 slab; its sums stay in registers across ALL tile groups
+            // when the warp owns one slab (NT <= 128 with sixteen epilogue warps), else they are flushed after every group
+            // (a second register set would spill: 113 registers per thread at 576 threads)
+            constexpr int kAccSets = 1;
+            const bool hoist = nslab32 <= kAccSets * G;
+            float s1[kAccSets][8], s2[kAccSets][8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
-                    const int gc = n_tile * p.NT + cs * 16;
-                    for (int t = tsel; t < p.T; t += TG) {
-                        int pix;
-                        if constexpr (kTma) pix = decode_position(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q).pix;
-                        else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
-                        uint32_t v[16];
-                        tmem_ld16(acc + (uint32_t)(t * p.NT + cs * 16), v);
-                        uint4 ym[2];
-                        if (masked && pix >= 0) {
-                            const uint4* ysrc = reinterpret_cast<const uint4*>(mask_y + (size_t)pix * p.Cout + gc);
-                            ym[0] = __ldg(ysrc);
-                            ym[1] = __ldg(ysrc + 1);
-                        }
-                        tmem_ld_wait();
-                        if (pix >= 0) {
-                            float f[16];
+            for (int sl = 0; sl < kAccSets; ++sl)
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                            if (masked) {
-                                // g_z = dX * [scale*y + shift > 0]; sums: S1 = sum g_z, S2' = sum g_z*y (combined with mean / invstd at the end)
-                                float yv[16];
-                                unpack8(ym[0], *reinterpret_cast<float(*)[8]>(&yv[0]));
-                                unpack8(ym[1], *reinterpret_cast<float(*)[8]>(&yv[8]));
+                for (int e = 0; e < 8; ++e) { s1[sl][e] = 0.f; s2[sl][e] = 0.f; }
+            auto flush_stats = [&](int cs0) {
+                // fold the eight lanes that hold the same channel chunk (fixed order); one writer per slot
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const float z = fmaf(yv[i], s_mask[cs * 16 + i], s_mask[p.NT + cs * 16 + i]);
-                                    f[i] = (z > 0.f) ? f[i] : 0.f;
-                                    ssum[i] += f[i];
-                                    ssq[i] = fmaf(f[i], yv[i], ssq[i]);
-                                }
-                            } else {
+                for (int sl = 0; sl < kAccSets; ++sl) {
+                    const int cs = cs0 + sl * G;
+                    if (cs >= nslab32) break;
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    ssum[i] += f[i];
-                                    ssq[i] = fmaf(f[i], f[i], ssq[i]);
-                                }
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pix * p.Cout + gc);
+                    for (int e = 0; e < 8; ++e) {
 #pragma unroll
-                            for (int j = 0; j < ((NUNET_DBG_SKIP & 1) ? 0 : 2); ++j) {
-                                uint4 o;
-                                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                                dst[j] = o;
-                            }
+                        for (int off = 4; off <= 16; off <<= 1) {
+                            s1[sl][e] += __shfl_xor_sync(0xffffffffu, s1[sl][e], off);
+                            s2[sl][e] += __shfl_xor_sync(0xffffffffu, s2[sl][e], off);
                         }
                     }
-                    // fold the two half-warps, then a transposing butterfly: lane L ends with the total of channel L & 15
+                    if (rsub == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], 16);
-                        ssq[i] += __shfl_xor_sync(0xffffffffu, ssq[i], 16);
-                    }
-#pragma unroll
-                    for (int off = 8; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float sa = up ? ssum[i] : ssum[i + off];
-                            const float ka = up ? ssum[i + off] : ssum[i];
-                            ssum[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
-                            const float sb = up ? ssq[i] : ssq[i + off];
-                            const float kb = up ? ssq[i + off] : ssq[i];
-                            ssq[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+                        for (int e = 0; e < 8; ++e) {
+                            my_stat[cs * 32 + chunk * 8 + e] += s1[sl][e];
+                            my_stat[p.NT + cs * 32 + chunk * 8 + e] += s2[sl][e];
                         }
                     }
-                    if (lane < 16) {  // this thread is the only writer of these two slots, groups are visited in a fixed order
-                        my_stat[cs * 16 + lane] += ssum[0];
-                        my_stat[p.NT + cs * 16 + lane] += ssq[0];
-                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { s1[sl][e] = 0.f; s2[sl][e] = 0.f; }
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[b]);
-            PROF_MARK(1)
-        }
-        if (eidx == 0 && lane == 0) PROF_FLUSH(4)
-        if (want_stats) {
+            };
+            EPI_GROUP_BEGIN
+                // statistics epilogues (training forward / fused block-internal router): the same transposed 64-byte-per-row store
+                // as the plain path (round 1 stored 32 bytes per lane: 32 cache lines per instruction).  The per-channel sums are
+                // taken in the transposed domain, from the bf16 values that are actually stored: a lane owns 8 channels of every 8th
+                // row; the eight lanes of a channel chunk are folded by three shuffles per slab.
+                uint8_t* scratch = s_epi + (size_t)eidx * kEpiSlot;
+                for (int cs0 = sg; cs0 < nslab32; cs0 += kAccSets * G) {
+#pragma unroll
+                    for (int sl = 0; sl < kAccSets; ++sl) {
+                        const int cs = cs0 + sl * G;
+                        if (cs >= nslab32) break;
+                        const int gc = n_tile * p.NT + cs * 32 + chunk * 8;
+                        for (int t = tsel; t < p.T; t += TG) {
+                            int pix;
+                            if constexpr (kTma) pix = decode_position(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q).pix;
+                            else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
+                            uint32_t v[32];
+                            tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
+                            int rpix[4];
+                            uint4 ym[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                rpix[i] = __shfl_sync(0xffffffffu, pix, i * 8 + rsub);
+                                if (masked && rpix[i] >= 0) ym[i] = __ldg(reinterpret_cast<const uint4*>(mask_y + (size_t)rpix[i] * p.Cout + gc));
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                                o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                                o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                                o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                                *reinterpret_cast<uint4*>(scratch + lane * 80 + j * 16) = o;
+                            }
+                            __syncwarp();
+                            float msc[8], msh[8];
+                            if (masked) {
+                                *reinterpret_cast<float4*>(&msc[0]) = *reinterpret_cast<const float4*>(&s_mask[cs * 32 + chunk * 8]);
+                                *reinterpret_cast<float4*>(&msc[4]) = *reinterpret_cast<const float4*>(&s_mask[cs * 32 + chunk * 8 + 4]);
+                                *reinterpret_cast<float4*>(&msh[0]) = *reinterpret_cast<const float4*>(&s_mask[p.NT + cs * 32 + chunk * 8]);
+                                *reinterpret_cast<float4*>(&msh[4]) = *reinterpret_cast<const float4*>(&s_mask[p.NT + cs * 32 + chunk * 8 + 4]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (rpix[i] < 0) continue;
+                                uint4 o = *reinterpret_cast<const uint4*>(scratch + (i * 8 + rsub) * 80 + chunk * 16);
+                                float f[8];
+                                unpack8(o, f);
+                                if (masked) {
+                                    // g_z = dX * [scale*y + shift > 0]; sums: S1 = sum g_z, S2' = sum g_z*y (combined with mean / invstd at the end)
+                                    float yv[8];
+                                    unpack8(ym[i], yv);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float z = fmaf(yv[e], msc[e], msh[e]);
+                                        f[e] = (z > 0.f) ? f[e] : 0.f;
+                                        s1[sl][e] += f[e];
+                                        s2[sl][e] = fmaf(f[e], yv[e], s2[sl][e]);
+                                    }
+                                    o = pack8(f);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        s1[sl][e] += f[e];
+                                        s2[sl][e] = fmaf(f[e], f[e], s2[sl][e]);
+                                    }
+                                }
+                                *reinterpret_cast<uint4*>(out + (size_t)rpix[i] * p.Cout + gc) = o;
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    if (!hoist) flush_stats(cs0);
+                }
+            EPI_GROUP_END
+            if (hoist) flush_stats(sg);
             asm volatile("bar.sync 2, %0;" ::"r"(kEpi * 32) : "memory");  // the epilogue warps only
             const int tid_e = eidx * 32 + lane;
             float* dst = p.stat_part + (size_t)blockIdx.x * 2 * p.Cout + n_tile * p.NT;

@@ -26,6 +26,12 @@ def autocast_context(name):
     return load("steps_r02.pt")["_autocast_bf16"].get(name)
 
 
+def autocast_grads(name):
+    """{parameter: (relative deviation of the gradient norm, cosine)} of the unmodified reference's bf16-autocast training step against
+    its own fp32 gradients (tests/golden/make_autocast_grads.py), or None."""
+    return load("autocast_grads.pt").get(name)
+
+
 def synthetic(g, offset=0):
     from oracle.nunet_oracle import synthetic_batch
     return synthetic_batch(g["n"], g["h"], g["w"], g["num_classes"], 3, g["data_seed"] + offset, g["dist"])

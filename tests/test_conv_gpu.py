@@ -76,13 +76,17 @@ def test_conv_fwd_sources(case):
     err = (got - ref).abs()
     tol = 0.008 * ref.abs() + 2e-3 * ref.abs().max()
     assert bool((err <= tol).all()), "max err %g (ref max %g), T=%d NT=%d CK=%d S=%d" % (err.max(), ref.abs().max(), plan.T, plan.NT, plan.CK, plan.S)
-    # statistics come from the fp32 accumulators
+    # the statistics are those of the STORED bf16 values (what the BatchNorm that follows normalises): tight against the output itself,
+    # and within bf16 rounding of the fp32 reference's sums
     s = part[:, 0, :].double().sum(0)
     ss = part[:, 1, :].double().sum(0)
+    os_, oss = got.double().sum((0, 2, 3)), (got.double() ** 2).sum((0, 2, 3))
+    assert torch.allclose(s, os_, rtol=1e-4, atol=1e-4 * float(oss.max().sqrt())), (s - os_).abs().max()
+    assert torch.allclose(ss, oss, rtol=1e-4), ((ss - oss) / oss).abs().max()
     rs = ref.double().sum((0, 2, 3))
     rss = (ref.double() ** 2).sum((0, 2, 3))
-    assert torch.allclose(s, rs, rtol=2e-3, atol=2e-3 * float(rss.max().sqrt())), (s - rs).abs().max()
-    assert torch.allclose(ss, rss, rtol=2e-3), ((ss - rss) / rss).abs().max()
+    assert torch.allclose(s, rs, rtol=4e-3, atol=4e-3 * float(rss.max().sqrt())), (s - rs).abs().max()
+    assert torch.allclose(ss, rss, rtol=4e-3), ((ss - rss) / rss).abs().max()
 
 
 @pytest.mark.parametrize("cin_real", [3, 1, 4])

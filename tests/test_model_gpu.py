@@ -112,6 +112,7 @@ def test_train_step_and_eval_against_reference_golden(name):
     assert iou == (I + 1e-5) / (U + 1e-5)
     # gradients
     named = dict(model.named_parameters())
+    acg = goldens.autocast_grads(name)
     worst = 0.0
     for k, n_ref in g["grad_norms"].items():
         gr = named[k].grad
@@ -122,7 +123,11 @@ def test_train_step_and_eval_against_reference_golden(name):
             continue
         rel = abs(float(gr.norm()) - n_ref) / max(n_ref, 1e-12)
         worst = max(worst, rel)
-        assert rel <= 0.20, (k, float(gr.norm()), n_ref)
+        # 20 %, or twice what the reference's OWN bf16-autocast step loses on this parameter; where the reference's bf16 gradient is
+        # barely correlated with its fp32 one (cancelling BatchNorm sums of the loader-distribution cases: cosine down to 0.06) only
+        # the order of magnitude is held
+        dev_ref, cos_ref = acg.get(k, (0.0, 1.0)) if acg else (0.0, 1.0)
+        assert rel <= max(0.20 if cos_ref >= 0.9 else 1.0, 2 * dev_ref), (k, float(gr.norm()), n_ref, dev_ref, cos_ref)
     for k, g_ref in g["grads"].items():
         if k.endswith("conv1.bias") or k.endswith("conv2.bias"):
             continue

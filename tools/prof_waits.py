@@ -10,7 +10,7 @@ rd.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_ulonglong * 16)()
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
-CASES = [("fwd", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 96, 96, [("act", 32)], 192),
+CASES = [("fwd", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 96, 96, [("act", 32)], 32), ("mask", 256, 96, 96, [("act", 32)], 32), ("mask", 256, 48, 48, [("act", 64)], 64), ("dgrad", 256, 96, 96, [("act", 32)], 192),
          ("dgrad", 256, 96, 96, [("act", 32)], 96), ("fwd", 256, 48, 48, [("act", 64)], 64)]
 for kind, N, H, W, srcs, Cout in CASES:
     sources = []
@@ -29,7 +29,11 @@ for kind, N, H, W, srcs, Cout in CASES:
     for it in range(2):
         torch.cuda.synchronize(); rd(buf, 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ops.conv3x3(N, H, W, sources, Cout, wp, want_stats=(kind == "fwd")); e1.record()
+        mk = None
+        if kind == "mask":
+            y1 = torch.randn(N, H, W, Cout, generator=g, device=dev).to(torch.bfloat16)
+            mk = ops.Mask(y1, *(torch.rand(Cout, generator=g, device=dev) + 0.5 for _ in range(4)))
+        e0.record(); ops.conv3x3(N, H, W, sources, Cout, wp, want_stats=(kind == "fwd"), mask=mk); e1.record()
         torch.cuda.synchronize(); rd(buf, 0)
     v = [x / (plan.grid_m * plan.n_tiles) / 1e3 for x in buf]   # kcycles per CTA
     ms = e0.elapsed_time(e1)
