@@ -72,7 +72,13 @@ __device__ unsigned long long g_wait_prof[16];
 #define PROF_DECL long long prof_t = clock64(); long long prof_acc[4] = {0, 0, 0, 0};
 #define PROF_MARK(slot) { long long now_ = clock64(); prof_acc[slot] += now_ - prof_t; prof_t = now_; }
 #define PROF_FLUSH(base) { for (int i_ = 0; i_ < 4; ++i_) atomicAdd(&g_wait_prof[(base) + i_], (unsigned long long)prof_acc[i_]); }
+#define PROF_ENTRY const long long prof_entry = clock64();
+#define PROF_PROLOGUE(slot) prof_acc[slot] += prof_t - prof_entry;                 /* kernel entry -> role loop start */
+#define PROF_MAX_SINCE(idx) atomicMax(&g_wait_prof[idx], (unsigned long long)(clock64() - prof_t));   /* slowest CTA: the BatchNorm tail */
 #else
+#define PROF_ENTRY
+#define PROF_PROLOGUE(slot)
+#define PROF_MAX_SINCE(idx)
 #define PROF_DECL
 #define PROF_MARK(slot) {}
 #define PROF_FLUSH(base) {}
@@ -84,6 +90,7 @@ __device__ unsigned long long g_wait_prof[16];
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    PROF_ENTRY
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cgs = p.CK >> 3;
     constexpr bool kTma = (MODE == MODE_ACT_TMA);
@@ -440,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             }
             // BatchNorm finalisation by the last CTA of the grid (all operand stages are idle by now: sA is free scratch)
             if (p.tail.counter && tid_e < 256) bn_tail_run(p.tail, p.stat_part, (int)gridDim.x, p.Cout, gridDim.x * gridDim.y, tid_e, 3, sA);
+            if (tid_e == 0) { PROF_MAX_SINCE(6) }
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer
@@ -454,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
             for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.Wp + (tap % 3));
             int cc = 0, it = 0;
             PROF_DECL
+            PROF_PROLOGUE(3)
             for (int tg = blockIdx.x; tg < p.ntg; tg += gridDim.x, ++it) {
                 const int b = it & 1;
                 const uint32_t k = (uint32_t)(it >> 1);
@@ -700,6 +709,9 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
         return NUNET_E_UNSUPPORTED;
     const int NT = pick_nt(Cout);
     if (NT == 0) return NUNET_E_UNSUPPORTED;
+    // (256-wide tiles only fit shared memory with 16-channel chunks, i.e. on the cp.async loader path; two 128-wide tiles on tensor
+    // loads were measured 1.5-2.8x SLOWER at 12x12 / 6x6 — 256->256: 0.088 vs 0.058 ms, 512->512: 0.183 vs 0.066 ms — the weight
+    // stream per position doubles; profiles/r02_summary.md)
     const int n_tiles = Cout / NT;
     const size_t budget = 220 * 1024;
     int bestT = 0, bestCK = 0, bestS = 0;

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256, 4) up_transpose_kernel(const UpTParams p)
 // running row accumulators suffice and a row is written out the moment y0 moves past it.  10 16-byte loads per output item
 // (L1 serves the overlap between neighbouring threads), no shared memory, no barriers: HBM-bound instead of issue-bound.
 constexpr int kRB = 16;   // source rows per CTA (3 extra output rows are re-read per CTA)
+constexpr int kRBBulk = 24; // bulk-copy variant: issue-bound, so fewer re-read rows win (0.091 ms at 16, 0.086 ms at 24 for 48x48x64; profiles/r02_summary.md)
 
 __global__ void __launch_bounds__(128) up_transpose_stream_kernel(const UpTParams p) {
     const int cgs = p.C >> 3;
@@ -254,6 +255,164 @@ __global__ void __launch_bounds__(128) up_transpose_stream_kernel(const UpTParam
     }
 }
 
+// ---- bulk-copy variant (default when a dX row is contiguous and w * C / 8 <= 992).  The streaming kernel above is latency-bound:
+// five 16-byte loads in flight per thread, 88 % of its stall samples on the load scoreboard, 2.6 TB/s (profiles/r02_summary.md).
+// Here one elected thread of a producer warp streams whole dX rows (W2 * C bf16, 12 KB at every level of the 96x96 step) into a
+// ring of shared-memory stages with cp.async.bulk (up to 72 KB in flight per CTA, no registers spent on it); the consumer threads
+// run the same per-thread walk as the streaming kernel, reading their five taps from the stage.
+struct UpTBulkParams {
+    const __nv_bfloat16* dx;
+    int N, h, w, C, rb, S;
+    __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(1024) up_transpose_bulk_kernel(const UpTBulkParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int cgs = p.C >> 3, items = p.w * cgs;
+    const int cwarps = (items + 31) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H2 = 2 * p.h, W2 = 2 * p.w;
+    const uint32_t row_bytes = (uint32_t)W2 * (uint32_t)p.C * 2u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.S * row_bytes);
+    uint64_t* empty = full + p.S;
+    const int rblocks = (p.h + p.rb - 1) / p.rb;
+    const int n = blockIdx.x / rblocks, ys = (blockIdx.x - n * rblocks) * p.rb;
+    const int ye = min(p.h, ys + p.rb);
+    const float ry = (float)(p.h - 1) / (float)(H2 - 1), rx = (float)(p.w - 1) / (float)(W2 - 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], (uint32_t)cwarps);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+    const int Ystart = max(0, 2 * ys - 4);
+    if (warp == cwarps) {
+        // ---- producer: rows Ystart .. (last row whose upper source row is below ye), one bulk copy each
+        if (elect_one()) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.dx) + (size_t)n * H2 * row_bytes;
+            int s = 0;
+            uint32_t ph = 1;
+            for (int Y = Ystart; Y < H2; ++Y) {
+                if ((int)(ry * (float)Y) >= ye) break;
+                mbar_wait(&empty[s], ph);
+                mbar_arrive_expect_tx(&full[s], row_bytes);
+                bulk_g2s(smem + (size_t)s * row_bytes, src + (size_t)Y * row_bytes, row_bytes, &full[s]);
+                if (++s == p.S) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    const int item = threadIdx.x;
+    const bool active = item < items;
+    const int cg = active ? item % cgs : 0, x = active ? item / cgs : 0;
+    // the <= kTaps consecutive output columns that read source column x (as in the streaming kernel)
+    float wx[kTaps];
+    int X0 = 0;
+    {
+        float wk[8];
+        int k0 = 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int D = 2 * x - 3 + k;
+            wk[k] = (D >= 0 && D < W2) ? upw(D, x, p.w, rx) : 0.f;
+            if (wk[k] != 0.f && k0 == 8) k0 = k;
+        }
+        if (k0 > 8 - kTaps) k0 = 8 - kTaps;
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k == k0 + j) v = wk[k];
+            wx[j] = v;
+        }
+        X0 = 2 * x - 3 + k0;
+#pragma unroll
+        for (int sft = 0; sft < 3; ++sft)
+            if (X0 < 0) {
+#pragma unroll
+                for (int j = 0; j < kTaps - 1; ++j) wx[j] = wx[j + 1];
+                wx[kTaps - 1] = 0.f;
+                ++X0;
+            }
+        // taps past the right edge carry zero weight by construction: point them at the last column instead of predicating the loads
+    }
+    uint32_t toff[kTaps];
+#pragma unroll
+    for (int j = 0; j < kTaps; ++j) toff[j] = (uint32_t)(min(X0 + j, W2 - 1) * p.C + cg * 8) * 2u;
+    __nv_bfloat16* dst = p.out + (size_t)n * p.h * p.w * p.C + (size_t)x * p.C + cg * 8;
+    float acc_a[8], acc_b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc_a[e] = 0.f; acc_b[e] = 0.f; }
+    int cur = (int)(ry * (float)Ystart);
+    int s = 0;
+    uint32_t ph = 0;
+    const uint8_t* stage = smem;
+    for (int Y = Ystart; Y < H2; ++Y) {
+        const float sy = ry * (float)Y;
+        const int y0 = (int)sy;
+        if (y0 >= ye) break;
+        const int y1 = y0 + (y0 < p.h - 1);
+        const float ly = sy - (float)y0;
+        mbar_wait(&full[s], ph);
+        uint4 r[kTaps];
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) r[j] = *reinterpret_cast<const uint4*>(stage + toff[j]);
+        float xr[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xr[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTaps; ++j) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&r[j]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                xr[2 * e] = fmaf(wx[j], f.x, xr[2 * e]);
+                xr[2 * e + 1] = fmaf(wx[j], f.y, xr[2 * e + 1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);      // the stage has been read into registers by this warp
+        stage += row_bytes;
+        if (++s == p.S) { s = 0; ph ^= 1u; stage = smem; }
+        if (y0 > cur) {   // row `cur` is complete
+            if (cur >= ys && active) {
+                uint4 o;
+                __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) q[e] = __floats2bfloat162_rn(acc_a[2 * e], acc_a[2 * e + 1]);
+                *reinterpret_cast<uint4*>(dst + (size_t)cur * p.w * p.C) = o;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { acc_a[e] = acc_b[e]; acc_b[e] = 0.f; }
+            cur = y0;
+        }
+        const float w0 = 1.f - ly;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc_a[e] = fmaf(w0, xr[e], acc_a[e]);
+        if (y1 == y0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc_a[e] = fmaf(ly, xr[e], acc_a[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc_b[e] = fmaf(ly, xr[e], acc_b[e]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int row = cur + t;
+        if (row >= ys && row < ye && active) {
+            uint4 o;
+            __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q[e] = t == 0 ? __floats2bfloat162_rn(acc_a[2 * e], acc_a[2 * e + 1]) : __floats2bfloat162_rn(acc_b[2 * e], acc_b[2 * e + 1]);
+            *reinterpret_cast<uint4*>(dst + (size_t)row * p.w * p.C) = o;
+        }
+    }
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -265,6 +424,27 @@ extern "C" int nunet_up_transpose(const void* dx, int32_t pitch, int32_t coff, i
     if (tiles >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
     UpTParams p{(const __nv_bfloat16*)dx, pitch, coff, N, h, w, C, (__nv_bfloat16*)out};
     static const bool tiled = getenv("NUNET_UPT_TILED") != nullptr;
+    static const bool no_bulk = getenv("NUNET_UPT_NO_BULK") != nullptr;
+    static const int rb_env = getenv("NUNET_UPT_RB") ? atoi(getenv("NUNET_UPT_RB")) : 0;
+    const long long row_bytes = 2LL * w * C * 2;
+    if (!tiled && !no_bulk && pitch == C && coff == 0 && w * (C / 8) <= 992 && row_bytes <= 24 * 1024 && ((uintptr_t)dx & 15) == 0) {
+        UpTBulkParams b{(const __nv_bfloat16*)dx, N, h, w, C, rb_env > 0 ? rb_env : kRBBulk, 0, (__nv_bfloat16*)out};
+        b.S = (int)(72 * 1024 / row_bytes);
+        if (b.S > 8) b.S = 8;
+        const long long bx = (long long)N * ((h + b.rb - 1) / b.rb);
+        if (bx >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
+        const size_t smem = (size_t)b.S * row_bytes + 2 * b.S * 8;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(up_transpose_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+            attr_done = true;
+        }
+        const int threads = ((w * (C / 8) + 31) / 32) * 32 + 32;
+        up_transpose_bulk_kernel<<<(unsigned)bx, threads, smem, (cudaStream_t)stream>>>(b);
+        cudaError_t e0 = cudaGetLastError();
+        return e0 == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e0;
+    }
     if (!tiled) {
         const long long bx = (long long)N * ((h + kRB - 1) / kRB);
         if (bx >= (1LL << 31)) return NUNET_E_UNSUPPORTED;

@@ -66,7 +66,10 @@ def test_grad_router(N, H, W, Cc, kinds):
 
 
 @pytest.mark.parametrize("N,h,w,Cc,pitch,coff", [(2, 8, 8, 64, 64, 0), (3, 6, 10, 128, 192, 64), (2, 3, 5, 512, 768, 256), (4, 24, 24, 32, 96, 32),
-                                                    (2, 48, 48, 64, 192, 128)])
+                                                    (2, 48, 48, 64, 192, 128),
+                                                    # dense rows: the bulk-copy pipelined kernel (ring of whole-row stages)
+                                                    (3, 48, 48, 64, 64, 0), (2, 24, 24, 128, 128, 0), (2, 6, 6, 512, 512, 0), (2, 17, 9, 32, 32, 0),
+                                                    (1, 1, 1, 64, 64, 0), (2, 35, 3, 8, 8, 0), (1, 5, 124, 64, 64, 0), (1, 4, 200, 64, 64, 0)])
 def test_up_transpose(N, h, w, Cc, pitch, coff):
     import ops
     gen = torch.Generator(device=DEV).manual_seed(17 + h)

@@ -11,7 +11,7 @@ buf = (C.c_ulonglong * 16)()
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(0)
 CASES = [("fwd", 256, 96, 96, [("act", 32)], 32), ("dgrad", 256, 96, 96, [("act", 32)], 32), ("mask", 256, 96, 96, [("act", 32)], 32), ("mask", 256, 48, 48, [("act", 64)], 64), ("dgrad", 256, 96, 96, [("act", 32)], 192),
-         ("dgrad", 256, 96, 96, [("act", 32)], 96), ("fwd", 256, 48, 48, [("act", 64)], 64)]
+         ("dgrad", 256, 96, 96, [("act", 32)], 96), ("fwd", 256, 48, 48, [("act", 64)], 64), ("fwd", 256, 24, 24, [("act", 128)], 128), ("fwd", 256, 12, 12, [("act", 256)], 256), ("dgrad", 256, 48, 48, [("act", 64)], 320)]
 for kind, N, H, W, srcs, Cout in CASES:
     sources = []
     for k, Cc in srcs:
@@ -33,11 +33,18 @@ for kind, N, H, W, srcs, Cout in CASES:
         if kind == "mask":
             y1 = torch.randn(N, H, W, Cout, generator=g, device=dev).to(torch.bfloat16)
             mk = ops.Mask(y1, *(torch.rand(Cout, generator=g, device=dev) + 0.5 for _ in range(4)))
-        e0.record(); ops.conv3x3(N, H, W, sources, Cout, wp, want_stats=(kind == "fwd"), mask=mk); e1.record()
+        tail = None
+        if kind == "fwd":
+            f32 = lambda: torch.zeros(Cout, device=dev)
+            counter = torch.zeros(1, dtype=torch.int32, device=dev)
+            tail = ops.bn_tail(counter, float(N * H * W), f32() + 1, f32(), f32(), f32(), f32() + 1, 0.1, 1e-5, f32(), f32(), f32(), f32())
+        e0.record(); ops.conv3x3(N, H, W, sources, Cout, wp, want_stats=(kind == "fwd"), mask=mk, tail=tail); e1.record()
         torch.cuda.synchronize(); rd(buf, 0)
     v = [x / (plan.grid_m * plan.n_tiles) / 1e3 for x in buf]   # kcycles per CTA
     ms = e0.elapsed_time(e1)
+    raw = list(buf)
     fl = 2.0 * N * H * W * cin * Cout * 9
     print("%s %dx%d cin %d cout %d: %.3f ms %.0f TF/s | T=%d NT=%d CK=%d S=%d chunks=%d groups/cta=%.1f" % (kind, H, W, cin, Cout, ms, fl / ms / 1e9, plan.T, plan.NT, plan.CK, plan.S, plan.nchunks, plan.ntg / plan.grid_m))
     print("   kcycles/CTA  producer: wait_acc %.0f table %.0f wait_empty %.0f stage %.0f | epilogue: wait %.0f work %.0f | mma: wait_acc %.0f wait_full %.0f issue %.0f | fetch: wait_empty %.0f issue %.0f"
           % (v[0], v[1], v[2], v[3], v[4], v[5], v[8], v[9], v[10], v[12], v[13]))
+    print("   mma prologue (entry -> first wait) %.1f kcycles/CTA | epilogue after the last group, slowest CTA (statistics + BatchNorm tail) %.1f kcycles" % (v[11], raw[6] / 1e3))
