@@ -503,6 +503,189 @@ __global__ void __launch_bounds__(256, POOL ? (NS >= 3 ? 1 : 2) : 3) grad_router
     }
 }
 
+// ---- bulk-copy variant for same-resolution consumers with dense rows (every router of the level-0 heads and the decoder nodes).
+// The register kernels above are latency-bound at few consumers: 768 threads x (NS + 1) x U 16-byte loads is all an SM has in
+// flight (x0_4's router: 24 KB, 2.6 TB/s).  Here a producer warp streams 4 KB chunks of y, of every consumer's dX and of dlogits
+// into a ring of shared-memory stages with cp.async.bulk (up to 96 KB in flight per CTA, two CTAs per SM); a consumer thread owns
+// one 16-byte item of every stream per chunk — its channel group is fixed (256 % (C/8) == 0), so the sums stay in registers.
+constexpr uint32_t kRChunk = 4096;
+
+template <int NS, bool HEAD>
+__global__ void __launch_bounds__(288, 2) grad_router_bulk_kernel(const RouterParams p, int S, int rows_total) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ float red[256][9];
+    const int cgs = p.C >> 3;
+    const int cg_shift = 31 - __clz(cgs);
+    const int PIX = 256 >> cg_shift;                       // pixels per chunk
+    const int npix = p.N * p.H * p.W;
+    const int nchunks = (npix + PIX - 1) / PIX;
+    constexpr uint32_t kStreams = NS + 1;
+    constexpr uint32_t stage_bytes = kStreams * kRChunk + (HEAD ? 256u : 0u);   // + dlogits: <= 64 floats
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* empty = full + S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 1;
+            for (int ck = blockIdx.x; ck < nchunks; ck += gridDim.x) {
+                const int p0 = ck * PIX;
+                const int np = min(PIX, npix - p0);
+                const uint32_t bytes = (uint32_t)np * (uint32_t)p.C * 2u;
+                const size_t goff = (size_t)p0 * p.C * 2;
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                mbar_wait(&empty[s], ph);
+                mbar_arrive_expect_tx(&full[s], bytes * kStreams + (HEAD ? (uint32_t)np * 4u : 0u));
+                bulk_g2s(st, reinterpret_cast<const uint8_t*>(p.y) + goff, bytes, &full[s]);
+#pragma unroll
+                for (int ci = 0; ci < NS; ++ci)
+                    bulk_g2s(st + (ci + 1) * kRChunk, reinterpret_cast<const uint8_t*>(p.cons[ci].dx) + goff, bytes, &full[s]);
+                if (HEAD) bulk_g2s(st + kStreams * kRChunk, p.dlogits + p0, (uint32_t)np * 4u, &full[s]);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    const int cg = tid & (cgs - 1), lp = tid >> cg_shift;
+    const int ch = cg * 8;
+    float sc[8], sh[8], acc1[8], acc2[8], wh8[8], accw[8], accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = p.scale[ch + i];
+        sh[i] = p.shift[ch + i];
+        acc1[i] = 0.f;
+        acc2[i] = 0.f;
+        wh8[i] = HEAD ? p.wh[ch + i] : 0.f;
+        accw[i] = 0.f;
+    }
+    {
+        int s = 0;
+        uint32_t ph = 0;
+        const uint8_t* st = smem;
+        for (int ck = blockIdx.x; ck < nchunks; ck += gridDim.x) {
+            const int p0 = ck * PIX;
+            const int np = min(PIX, npix - p0);
+            mbar_wait(&full[s], ph);
+            const uint4 ry = *reinterpret_cast<const uint4*>(st + tid * 16);
+            uint4 rd[NS > 0 ? NS : 1];
+#pragma unroll
+            for (int ci = 0; ci < NS; ++ci) rd[ci] = *reinterpret_cast<const uint4*>(st + (ci + 1) * kRChunk + tid * 16);
+            float dl = 0.f;
+            if (HEAD) dl = *reinterpret_cast<const float*>(st + kStreams * kRChunk + lp * 4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);          // this warp holds its items in registers
+            st += stage_bytes;
+            if (++s == S) { s = 0; ph ^= 1u; st = smem; }
+            if (lp < np) {
+                float yv[8], g[8];
+                unpack8f(ry, yv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < NS; ++ci) add8(g, rd[ci], 1.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float z = fmaf(yv[i], sc[i], sh[i]);
+                    if (HEAD) {
+                        g[i] = fmaf(dl, wh8[i], g[i]);
+                        accw[i] = fmaf(dl, fmaxf(z, 0.f), accw[i]);
+                    }
+                    const float gz = (z > 0.f) ? g[i] : 0.f;
+                    g[i] = gz;
+                    acc1[i] += gz;
+                    acc2[i] = fmaf(gz, yv[i], acc2[i]);
+                }
+                if (HEAD && cg == 0) accb += dl;
+                *reinterpret_cast<uint4*>(p.gz + (size_t)(p0 + lp) * p.C + ch) = pack8(g);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc2[i] = p.invstd[ch + i] * (acc2[i] - p.mean[ch + i] * acc1[i]);
+    // block reduction over the 256 consumer threads (named barrier 1: the producer warp has left)
+    for (int pass = 0; pass < (HEAD ? 3 : 2); ++pass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[tid][i] = pass == 0 ? acc1[i] : (pass == 1 ? acc2[i] : accw[i]);
+        if (pass == 2) red[tid][8] = accb;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = tid; c < p.C + (pass == 2 ? 1 : 0); c += 256) {
+            float sum = 0.f;
+            if (c < p.C) {
+                const int g8 = c >> 3, e = c & 7;
+                for (int t = g8; t < 256; t += cgs) sum += red[t][e];
+            } else {
+                for (int t = 0; t < 256; t += cgs) sum += red[t][8];
+            }
+            if (pass < 2) p.part[((size_t)blockIdx.x * 2 + pass) * p.C + c] = sum;
+            else p.hpart[(size_t)blockIdx.x * 33 + c] = sum;
+            // the caller's buffers hold nunet_grad_router_rows() rows (sized for the register kernels' grids): the rest is zero
+            for (int r = blockIdx.x + gridDim.x; r < rows_total; r += gridDim.x) {
+                if (pass < 2) p.part[((size_t)r * 2 + pass) * p.C + c] = 0.f;
+                else p.hpart[(size_t)r * 33 + c] = 0.f;
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    if (p.tail.counter) {
+        const bool last = bn_tail_run(p.tail, p.part, (int)gridDim.x, p.C, gridDim.x, tid, 1, &red[0][0]);
+        if (HEAD && last) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            double* shd = reinterpret_cast<double*>(&red[0][0]);   // [7][33]
+            const int col = tid % 33, rl = tid / 33;
+            if (rl < 7) {
+                double a = 0.0;
+                for (int r0 = rl; r0 < (int)gridDim.x; r0 += 7 * 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int r = r0 + u * 7;
+                        v[u] = (r < (int)gridDim.x) ? __ldcg(p.hpart + (size_t)r * 33 + col) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a += (double)v[u];
+                }
+                shd[rl * 33 + col] = a;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < 33) {
+                double a = 0.0;
+                for (int l = 0; l < 7; ++l) a += shd[l * 33 + tid];
+                if (tid < 32) p.dwh[tid] = (float)a;
+                else if (p.dbh) p.dbh[0] = (float)a;
+            }
+        }
+    }
+}
+
+template <int NS, bool HEAD>
+static int launch_router_bulk(const RouterParams& p, int rows, cudaStream_t st) {
+    constexpr uint32_t stage_bytes = (NS + 1) * kRChunk + (HEAD ? 256u : 0u);
+    int S = (int)(96u * 1024u / stage_bytes);
+    if (S > 8) S = 8;
+    const size_t smem = (size_t)S * stage_bytes + 2 * S * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(grad_router_bulk_kernel<NS, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return NUNET_E_CUDA + (int)e;
+        attr_done = true;
+    }
+    const int cgs = p.C >> 3, PIX = 256 / cgs;
+    const long long nchunks = ((long long)p.N * p.H * p.W + PIX - 1) / PIX;
+    int grid = rows < 2 * 148 ? rows : 2 * 148;
+    if (nchunks < grid) grid = (int)nchunks;
+    grad_router_bulk_kernel<NS, HEAD><<<grid, 288, smem, st>>>(p, S, rows);
+    cudaError_t e0 = cudaGetLastError();
+    return e0 == cudaSuccess ? NUNET_OK : NUNET_E_CUDA + (int)e0;
+}
+
 }  // namespace nunet
 
 using namespace nunet;
@@ -562,6 +745,18 @@ extern "C" int nunet_grad_router(const nunet_router_desc_t* d, void* stream) {
     const bool fused_head = d->head_part != nullptr;
     if (fused_head && (!hh || d->K != 1 || d->C != 32 || !d->dwh || !d->bn.counter || hu || hp)) return NUNET_E_BADARG;
     p.hpart = d->head_part; p.dwh = d->dwh; p.dbh = d->dbh;
+    // bulk-copy streaming kernel: same-resolution consumers only, dense rows, no head or the fused K == 1 head
+    static const bool no_bulk = getenv("NUNET_ROUTER_NO_BULK") != nullptr;
+    if (!no_bulk && !no_fast && !hu && !hp && (!hh || fused_head) && ((uintptr_t)d->y & 15) == 0) {
+        bool dense = true;
+        for (int i = 0; i < n_same; ++i) dense = dense && p.cons[i].pitch == d->C && p.cons[i].coff == 0 && ((uintptr_t)p.cons[i].dx & 15) == 0;
+        if (hh) dense = dense && ((long long)d->N * d->H * d->W) % 4 == 0 && ((uintptr_t)d->dlogits & 15) == 0;
+        if (dense) {
+#define NUNET_BULK_CASE(NS_) if (n_same == NS_) return hh ? launch_router_bulk<NS_, true>(p, rows, st) : launch_router_bulk<NS_, false>(p, rows, st)
+            NUNET_BULK_CASE(0); NUNET_BULK_CASE(1); NUNET_BULK_CASE(2); NUNET_BULK_CASE(3); NUNET_BULK_CASE(4);
+#undef NUNET_BULK_CASE
+        }
+    }
     // v2 where it wins: a POOL consumer (window per thread) or the fused head; plain same-resolution sums stay on the 64-register kernel
     if (!hu && !no_fast && !no_v2 && (hp || fused_head) && !(hp && hh)) {
 #define NUNET_V2_CASE(NS_, P_, H_) if (n_same == NS_ && hp == P_ && hh == H_) grad_router_v2_kernel<NS_, P_, H_><<<rows, 256, 0, st>>>(p)
