@@ -63,32 +63,59 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 
 // BatchNorm backward (nn.BatchNorm2d, train): dbeta = S1, dgamma = S2,
 //   g_y = gamma*r*(g_z - S1/M - yhat*S2/M),  yhat = (y-mean)*r   =>   g_y = k1*g_z + k2*y + k3.
-__device__ __forceinline__ void bn_backward_channel(const BnFinalizeArgs& a, int c, double S1, double S2) {
-    const double g = a.gamma[c], r = a.save_invstd[c], mu = a.save_mean[c], M = a.count;
-    a.dbeta[c] = (float)(S1 * a.grad_scale);
-    a.dgamma[c] = (float)(S2 * a.grad_scale);
-    a.k1[c] = (float)(g * r);
-    a.k2[c] = (float)(-g * r * r * S2 / M);
-    a.k3[c] = (float)(-g * r * S1 / M + g * r * r * mu * S2 / M);
+// The per-channel parameters a finalisation reads.  Loaded up front (bn_prefetch), before any of the result stores: the outputs are
+// plain float* that may alias the inputs as far as the compiler knows, so loads placed after the first store were issued one by
+// one — five dependent global-memory latencies (~9 k cycles of a forward tail, tools/prof_waits.py).
+struct BnPre {
+    float gamma, a, b, c, d;   // forward: a = beta, b = conv bias, c = running mean, d = running var ; backward: a = invstd, b = mean
+};
+__device__ __forceinline__ BnPre bn_prefetch(const BnFinalizeArgs& f, int ch) {
+    BnPre q;
+    q.gamma = f.gamma[ch];
+    if (f.mode == 1) {
+        q.a = f.save_invstd[ch];
+        q.b = f.save_mean[ch];
+        q.c = 0.f;
+        q.d = 0.f;
+    } else {
+        q.a = f.beta[ch];
+        q.b = f.conv_bias ? f.conv_bias[ch] : 0.f;
+        q.c = f.running_mean ? f.running_mean[ch] : 0.f;
+        q.d = f.running_mean ? f.running_var[ch] : 0.f;
+    }
+    return q;
 }
 
-__device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS) {
-    if (a.mode == 1) { bn_backward_channel(a, c, S, SS); return; }
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS, const BnPre& q) {
+    if (a.mode == 1) {
+        // S = S1 = sum g_z, SS = S2 = sum g_z*yhat (header comment above)
+        const double g = q.gamma, r = q.a, mu = q.b, M = a.count;
+        a.dbeta[c] = (float)(S * a.grad_scale);
+        a.dgamma[c] = (float)(SS * a.grad_scale);
+        a.k1[c] = (float)(g * r);
+        a.k2[c] = (float)(-g * r * r * SS / M);
+        a.k3[c] = (float)(-g * r * S / M + g * r * r * mu * SS / M);
+        return;
+    }
     const double mean = S / a.count;
     double var = SS / a.count - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    const float sc = a.gamma[c] * invstd;
+    const float sc = q.gamma * invstd;
     a.scale[c] = sc;
-    a.shift[c] = a.beta[c] - (float)mean * sc;
+    a.shift[c] = q.a - (float)mean * sc;
     if (a.save_mean) a.save_mean[c] = (float)mean;
     if (a.save_invstd) a.save_invstd[c] = invstd;
     if (a.running_mean) {
-        const double b = a.conv_bias ? (double)a.conv_bias[c] : 0.0;  // the dropped conv bias only shifts the mean
-        a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * (mean + b));
+        const double b = (double)q.b;  // the dropped conv bias only shifts the mean
+        a.running_mean[c] = (float)((1.0 - a.momentum) * q.c + a.momentum * (mean + b));
         const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
-        a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
+        a.running_var[c] = (float)((1.0 - a.momentum) * q.d + a.momentum * unbiased);
     }
+}
+
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalizeArgs& a, int c, double S, double SS) {
+    bn_finalize_channel(a, c, S, SS, bn_prefetch(a, c));
 }
 
 // Executed by the 256 threads `tid` = 0..255 of a CTA that share named barrier `bar_id`, AFTER they have written the CTA's own
@@ -107,6 +134,10 @@ __device__ __forceinline__ bool bn_tail_run(const BnTail& t, const float* part, 
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
     if (!*flag) return false;
     __threadfence();
+    BnPre pre[2];                           // channels tid and tid + 256 (C <= 512): in flight under the partial-row loads below
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (t.fin.gamma && tid + k * 256 < C) pre[k] = bn_prefetch(t.fin, tid + k * 256);
     const int groups = C >> 1;              // 16-byte column groups per row (2C floats)
     const int L = 256 / groups;             // row lanes: 16 (C = 32) ... 1 (C = 512)
     const int g = tid % groups, lane = tid / groups;
@@ -150,7 +181,10 @@ __device__ __forceinline__ bool bn_tail_run(const BnTail& t, const float* part, 
         }
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
     }
-    for (int c = tid; c < C; c += 256) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int c = tid + k * 256;
+        if (c >= C) break;
         double S = 0.0, SS = 0.0;
         if (exchange) {
             for (int q = 0; q < t.xch.world; ++q) {          // rank order: bitwise identical totals on every rank
@@ -162,7 +196,7 @@ __device__ __forceinline__ bool bn_tail_run(const BnTail& t, const float* part, 
             for (int l = 0; l < L; ++l) { S += sh[(size_t)l * 2 * C + c]; SS += sh[(size_t)l * 2 * C + C + c]; }
         }
         if (t.sums_out) { t.sums_out[c] = S; t.sums_out[C + c] = SS; }
-        if (t.fin.gamma) bn_finalize_channel(t.fin, c, S, SS);
+        if (t.fin.gamma) bn_finalize_channel(t.fin, c, S, SS, pre[k]);
     }
     if (tid == 0) {
         *t.counter = 0;   // self-resetting for the next launch

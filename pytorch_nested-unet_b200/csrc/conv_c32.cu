@@ -36,6 +36,7 @@ namespace nunet {
 struct C32Params {
     CUtensorMap xmap[NUNET_MAX_SRC];
     int N, H, W, PW;
+    uint32_t pw_magic;           // ceil(2^32 / PW): u / PW == __umulhi(u, pw_magic) for the u < 2^16 of a group
     int ry, gpi, groups_total;   // rows per group, groups per image
     int box_rows, S, nch, num_src;
 #ifdef NUNET_EXPERIMENT
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
             const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
             const int rows = min(p.ry, p.H - y0);
             const int ntile = (rows * p.PW + 125) / 126;
+            const int img_row0 = (n * p.H + y0) * p.W;
             for (int t = 0; t < ntile; ++t) {
                 ++seq;
                 mbar_wait(&acc_full[t], (tile_phase >> t) & 1u);
@@ -235,9 +237,9 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                 }
                 // this lane's output position inside the group (index u holds pixel u % PW - 1 of row u / PW)
                 const int u = t * 126 + m;
-                const int row = u / p.PW, px = u - row * p.PW - 1;
+                const int row = (int)__umulhi((uint32_t)u, p.pw_magic), px = u - row * p.PW - 1;
                 const bool valid = (m >= 1) && (m <= 126) && (row < rows) && (px >= 0) && (px < p.W);
-                const size_t pix = ((size_t)n * p.H + (y0 + row)) * p.W + px;
+                const size_t pix = (size_t)(uint32_t)(img_row0 + row * p.W + px);       // N*H*W < 2^31 (plan check)
                 uint4 ym = make_uint4(0, 0, 0, 0);
                 if (masked && valid) ym = __ldg(reinterpret_cast<const uint4*>(p.mask_y + pix * 32 + cq * 8));
                 float y[8];
@@ -381,7 +383,7 @@ int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, const B
     C32Tiling t;
     if (!c32_tiling(d->H, d->W, cin / 32, &t)) return NUNET_E_UNSUPPORTED;
     C32Params p{};
-    p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.pw_magic = (uint32_t)(((1ULL << 32) + (uint64_t)t.PW - 1) / (uint64_t)t.PW); p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
     p.box_rows = t.box_rows; p.S = t.S; p.res_b = t.res_b; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
     p.wpack = d->wpack; p.out = (__nv_bfloat16*)d->out; p.stat_part = d->stat_part;
     p.tail = tail;

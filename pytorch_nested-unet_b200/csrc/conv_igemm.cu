@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                 for (int wi = part; wi < p.T * nslab32; wi += kParts) {
                     const int t = wi / nslab32, cs = wi - t * nslab32;
                     int pix;
-                    if constexpr (kTma) pix = decode_position(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q).pix;
+                    if constexpr (kTma) pix = decode_pix_fast(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q, p.div_wp, p.div_hp1);
                     else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                         const int gc = n_tile * p.NT + cs * 32 + chunk * 8;
                         for (int t = tsel; t < p.T; t += TG) {
                             int pix;
-                            if constexpr (kTma) pix = decode_position(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q).pix;
+                            if constexpr (kTma) pix = decode_pix_fast(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q, p.div_wp, p.div_hp1);
                             else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
                             uint32_t v[32];
                             tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
@@ -813,6 +813,7 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     if (rc) return rc;
     ConvParams p{};
     p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
+    p.div_wp = make_fastdiv((uint32_t)p.Wp); p.div_hp1 = make_fastdiv((uint32_t)p.Hp1);
     p.Q = (d->N * (d->H + 1) + 1) * (d->W + 2);
     p.T = pl.T; p.NT = pl.NT; p.CK = pl.CK; p.S = pl.S; p.P = pl.P; p.nchunks = pl.nchunks;
     p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src; p.tmem_cols = pl.tmem_cols; p.ntg = pl.ntg;

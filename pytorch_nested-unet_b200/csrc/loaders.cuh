@@ -316,4 +316,11 @@ __device__ __forceinline__ PixInfo decode_position(int q, int N, int H, int W, i
     return pi;
 }
 
+__device__ __forceinline__ int decode_pix_fast(int q, int N, int H, int W, int Wp, int Hp1, int Q, const FastDiv& dWp, const FastDiv& dHp1) {
+    if (q < 0 || q >= Q) return -1;
+    const int R = (int)fastdiv((uint32_t)q, dWp), c = q - R * Wp;
+    const int n = (int)fastdiv((uint32_t)R, dHp1), rr = R - n * Hp1;
+    return (c >= 1 && c <= W && rr >= 1 && n < N) ? (n * H + (rr - 1)) * W + (c - 1) : -1;
+}
+
 }  // namespace nunet
