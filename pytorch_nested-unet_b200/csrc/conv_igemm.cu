@@ -707,14 +707,18 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     const long long Q = ((long long)N * (H + 1) + 1) * (W + 2);
     if (Q + 4LL * 128 + 2 * (W + 2) + 2 >= (1LL << 31) || (long long)N * H * W * (Cout > cin_pad ? Cout : cin_pad) >= (1LL << 40))
         return NUNET_E_UNSUPPORTED;
-    const int NT = pick_nt(Cout);
+    int NT = pick_nt(Cout);
     if (NT == 0) return NUNET_E_UNSUPPORTED;
+#ifdef NUNET_EXPERIMENT
+    if (const char* e = getenv("NUNET_CONV_NT")) { const int v = atoi(e); if (v >= 32 && v % 32 == 0 && Cout % v == 0 && v < NT) NT = v; }
+#endif
     // (256-wide tiles only fit shared memory with 16-channel chunks, i.e. on the cp.async loader path; two 128-wide tiles on tensor
     // loads were measured 1.5-2.8x SLOWER at 12x12 / 6x6 — 256->256: 0.088 vs 0.058 ms, 512->512: 0.183 vs 0.066 ms — the weight
     // stream per position doubles; profiles/r02_summary.md)
-    const int n_tiles = Cout / NT;
     const size_t budget = 220 * 1024;
-    int bestT = 0, bestCK = 0, bestS = 0;
+    int n_tiles = 0, bestT = 0, bestCK = 0, bestS = 0;
+    auto search = [&](int NT) {
+    n_tiles = Cout / NT; bestT = 0; bestCK = 0; bestS = 0;
     // prefer: large T (halo amortisation) while keeping >= 2 waves of CTAs, CK=32, 2 stages
     for (int minS = 2; minS >= 1 && !bestT; --minS)
     for (int T = (256 / NT < 4 ? 256 / NT : 4); T >= 1 && !bestT; --T) {
@@ -736,6 +740,22 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
                 bestT = T; bestCK = CK; bestS = S;
                 break;
             }
+        }
+    }
+    };
+    search(NT);
+    // Wide outputs whose 160..256-column weight stage only fits with 16-channel chunks fall off the tensor-load path (cp.async
+    // loaders, eight epilogue warps).  Where the layer is large enough for the weight stream not to matter, narrower tiles on tensor
+    // loads win: 64-wide at >= 3000 tiles (48x48: 64->320 0.313 -> 0.226 ms, 64->192 0.171 -> 0.134), 128-wide at >= 1000 tiles
+    // (24x24: 128->384 0.149 -> 0.123); at 12x12 / 6x6 the default stays (256->768: 0.128 vs 0.197 / 0.334 ms).
+    if (bestCK != 32 && W + 2 <= 256 && cin_pad % 32 == 0) {
+        const long long tiles = (Q + 127) / 128;
+        const int alt = (tiles >= 3000 && Cout % 64 == 0 && NT > 64) ? 64 : ((tiles >= 1000 && Cout % 128 == 0 && NT > 128) ? 128 : 0);
+        if (alt) {
+            const int keepT = bestT, keepCK = bestCK, keepS = bestS;
+            search(alt);
+            if (bestT && bestCK == 32) NT = alt;
+            else { n_tiles = Cout / NT; bestT = keepT; bestCK = keepCK; bestS = keepS; }
         }
     }
     if (!bestT) return NUNET_E_SMEM;

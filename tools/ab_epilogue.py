@@ -14,7 +14,7 @@ def timeit(fn):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 8
 res = []
-for H, cin, cout, kind in [(12, 256, 256, "stats"), (12, 256, 256, "mask"), (12, 768, 256, "stats"), (12, 128, 256, "stats"), (6, 512, 512, "stats"), (6, 256, 512, "stats"), (12, 256, 768, "plain"), (6, 512, 512, "mask"), (96, 192, 32, "c32stats"), (96, 96, 32, "c32stats"), (96, 192, 32, "c32plain"), (96, 96, 32, "c32plain"), (96, 64, 32, "c32plain"),(96, 32, 32, "stats"), (96, 32, 32, "plain"), (96, 32, 32, "mask"), (96, 32, 96, "plain"), (96, 32, 192, "plain"), (96, 32, 192, "segs"), (48, 64, 64, "stats"), (48, 64, 320, "plain")]:
+for H, cin, cout, kind in [(48, 64, 320, "plain"), (48, 64, 256, "plain"), (48, 64, 192, "plain"), (24, 128, 512, "plain"), (24, 128, 384, "plain"), (24, 128, 256, "plain"), (12, 256, 768, "plain"), (12, 256, 512, "plain"), (12, 256, 256, "stats"), (12, 256, 256, "mask"), (12, 768, 256, "stats"), (12, 128, 256, "stats"), (6, 512, 512, "stats"), (6, 256, 512, "stats"), (12, 256, 768, "plain"), (6, 512, 512, "mask"), (96, 192, 32, "c32stats"), (96, 96, 32, "c32stats"), (96, 192, 32, "c32plain"), (96, 96, 32, "c32plain"), (96, 64, 32, "c32plain"),(96, 32, 32, "stats"), (96, 32, 32, "plain"), (96, 32, 32, "mask"), (96, 32, 96, "plain"), (96, 32, 192, "plain"), (96, 32, 192, "segs"), (48, 64, 64, "stats"), (48, 64, 320, "plain")]:
     a = torch.rand(N, H, H, cin, generator=g, device=dev).to(torch.bfloat16)
     w = torch.randn(cout, cin, 3, 3, generator=g, device=dev) * 0.05
     plan = ops.conv_plan(N, H, H, cin, cout)
