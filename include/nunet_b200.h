@@ -90,8 +90,10 @@ typedef struct {
  * (zero padding applied AFTER the per-source transform, as torch.cat + nn.Conv2d(padding=1) does).
  * Replaces, for one VGGBlock conv: nn.Conv2d (finished/archs1.py:18,20,24,28) and — via the source kinds — the
  * preceding nn.BatchNorm2d + ReLU apply (:25-26,29-30), nn.MaxPool2d (:82), nn.Upsample (:83) and torch.cat (:117-132).
- * With stat_part != NULL the epilogue also emits per-CTA per-channel [sum, sum of squares] of the fp32 accumulators
- * (the batch statistics nn.BatchNorm2d computes in train mode).  The same entry point runs dgrad (source kind GRAD,
+ * With stat_part != NULL the epilogue also emits per-CTA per-channel [sum, sum of squares] of the conv output (the batch
+ * statistics nn.BatchNorm2d computes in train mode): of the bf16 values it stores — what the following BatchNorm normalises —
+ * in the generic kernel, of the fp32 accumulators in the stacked Cout = 32 kernel (wpack_layout 1); both are summed in fp32 per
+ * thread and in fp64 across CTAs, in a fixed order.  The same entry point runs dgrad (source kind GRAD,
  * weights packed with NUNET_PACK_DGRAD). */
 typedef struct {
     int32_t N, H, W; /* output resolution */
