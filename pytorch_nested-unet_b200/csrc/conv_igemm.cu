@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                         // A rows are positions (64 B each, 64B swizzle, 8-row atoms of 512 B); the stage holds whole padded rows
                         // starting at row R_lo, so position (q0 - Wp - 1) sits `woff` rows into it.  Address-field units are 16 B.
                         const int qb = tg * group_positions - p.Wp - 1;
-                        const int R_lo = (qb >= 0) ? qb / p.Wp : -((-qb + p.Wp - 1) / p.Wp);
+                        const int R_lo = (qb >= 0) ? (int)fastdiv((uint32_t)qb, p.div_wp) : -((-qb + p.Wp - 1) / p.Wp);
                         const uint32_t woff = (uint32_t)(qb - R_lo * p.Wp);
                         const uint32_t a_hi_sw = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512 B, version 1, SWIZZLE_64B
                         const uint32_t a_base = ((smem_u32(sA + (size_t)s * a_bytes) >> 4) & 0x3FFFu) | (1u << 16);
@@ -540,9 +540,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                 int si = 0, src_c0 = 0;
                 // TMA mode: the padded rows [R_lo, R_lo + nrows) cover positions [q0 - Wp - 1, q0 + 128T + Wp + 1)
                 const int qb = tg * group_positions - p.Wp - 1;
-                const int R_lo = (qb >= 0) ? qb / p.Wp : -((-qb + p.Wp - 1) / p.Wp);
+                const int R_lo = (qb >= 0) ? (int)fastdiv((uint32_t)qb, p.div_wp) : -((-qb + p.Wp - 1) / p.Wp);
                 const int nrows = (qb - R_lo * p.Wp + p.P + p.Wp - 1) / p.Wp;
                 const uint32_t row_bytes = (uint32_t)p.Wp * 64u;
+                // image / row of padded row R_lo (R = n*(H+1) + 1 + y); the row loop below advances them without dividing
+                const int n_lo = (R_lo >= 0) ? (int)fastdiv((uint32_t)R_lo, p.div_hp1) : -1;
+                const int y_lo = (R_lo >= 0) ? R_lo - n_lo * p.Hp1 - 1 : -1;
                 for (int chunk = 0; chunk < p.nchunks; ++chunk, ++cc) {
                     const int s = cc % p.S;
                     const uint32_t ph = (uint32_t)(cc / p.S) & 1;
@@ -555,12 +558,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                         mbar_arrive_expect_tx(&full[s], (fetch_b ? b_bytes : 0u) + ((NUNET_DBG_SKIP & 4) ? 0u : (uint32_t)nrows * row_bytes));
                         if (fetch_b) bulk_g2s(sB + (size_t)s * b_stride, wsrc + (size_t)chunk * b_bytes, b_bytes, &full[s]);
                         uint8_t* dstA = sA + (size_t)s * a_bytes;
+                        int n = n_lo, y = y_lo, R = R_lo;
                         for (int r = 0; r < ((NUNET_DBG_SKIP & 4) ? 0 : nrows); ++r) {
-                            const int R = R_lo + r;
-                            // padded row R = n*(H+1) + 1 + y ; separator rows (y = -1) and rows outside the batch are out of bounds -> zeros
-                            const int n = (R >= 0) ? R / p.Hp1 : -1;
-                            const int y = (R >= 0) ? R - n * p.Hp1 - 1 : 0;
+                            // separator rows (y = -1) and rows outside the batch (n = -1 or n >= N) are out of bounds -> zeros
                             tma_load_4d(dstA + (size_t)r * row_bytes, &p.tmap[si], cglob - src_c0, -1, y, n, &full[s]);
+                            ++R;
+                            if (R <= 0) { n = (R == 0) ? 0 : -1; y = -1; }
+                            else if (++y == p.H) { y = -1; ++n; }
                         }
                     } else {
                         if (!res_b || cc == 0) {
