@@ -127,7 +127,11 @@ typedef struct {
     int32_t nchunks, n_tiles, grid_m, cin_pad; /* grid_m = CTAs along x = rows of stat_part (persistent kernel) */
     int32_t smem_bytes, tmem_cols, ntg;       /* ntg = tile groups of 128*T positions */
     int32_t tma_a_stage_bytes, tma_smem_bytes; /* > 0: the TMA tensor-load variant of this tiling fits (copy-mode sources) */
-    int32_t tma_epi_warps, pad_;               /* warps draining TMEM in the TMA variant (16 or 8) */
+    int32_t tma_epi_warps;                     /* warps draining TMEM in the TMA variant (16 or 8) */
+    int32_t strips;                            /* > 1: rows wider than a tensor-load box (W + 2 > 256): the plan describes the batch as
+                                                  N*strips images of ceil(W/strips) columns whose halo columns are the neighbouring
+                                                  strips' pixels (the box simply starts one pixel to the left of the strip); tensor-load
+                                                  sources only — the transforming loader kinds return NUNET_E_UNSUPPORTED there */
     int64_t wpack_elems; /* bf16 elements the packed weights occupy */
 } nunet_conv_plan_t;
 

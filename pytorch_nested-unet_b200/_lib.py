@@ -48,7 +48,7 @@ class ConvPlan(C.Structure):
     _fields_ = [("T", C.c_int32), ("NT", C.c_int32), ("CK", C.c_int32), ("S", C.c_int32), ("P", C.c_int32),
                 ("nchunks", C.c_int32), ("n_tiles", C.c_int32), ("grid_m", C.c_int32), ("cin_pad", C.c_int32),
                 ("smem_bytes", C.c_int32), ("tmem_cols", C.c_int32), ("ntg", C.c_int32), ("tma_a_stage_bytes", C.c_int32),
-                ("tma_smem_bytes", C.c_int32), ("tma_epi_warps", C.c_int32), ("pad_", C.c_int32), ("wpack_elems", C.c_int64)]
+                ("tma_smem_bytes", C.c_int32), ("tma_epi_warps", C.c_int32), ("strips", C.c_int32), ("wpack_elems", C.c_int64)]
 
 
 class GradCons(C.Structure):

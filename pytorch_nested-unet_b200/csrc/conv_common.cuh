@@ -40,6 +40,8 @@ struct ConvParams {
     int N, H, W;
     int Wp, Hp1;  // W+2, H+1
     FastDiv div_wp, div_hp1;   // position decode in the TMA-mode epilogue
+    int strips, Wreal;         // strips > 1: N / W above describe N*strips column strips of the Wreal-pixel rows (TMA mode only)
+    FastDiv div_strips;
     int Q;        // padded positions: (N*(H+1)+1)*(W+2)
     int T, NT, CK, S, P, nchunks, cin_pad, Cout, num_src, tmem_cols, ntg;
     int res_b;          // 1: single K chunk, the weight block is fetched once per CTA and stays resident

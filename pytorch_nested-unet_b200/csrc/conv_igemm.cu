@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
         const bool want_stats = p.stat_part != nullptr;
         const bool masked = p.mask_y != nullptr;         // fused block-internal gradient router (dgrad of a block's second conv)
         const __nv_bfloat16* mask_y = reinterpret_cast<const __nv_bfloat16*>(p.mask_y);
+        auto epi_pix = [&](int q) {   // output pixel of flattened position q (-1: padding / halo)
+            return p.strips > 1 ? decode_pix_strips(q, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q, p.div_wp, p.div_hp1, p.strips, p.Wreal, p.div_strips)
+                                : decode_pix_fast(q, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q, p.div_wp, p.div_hp1);
+        };
         // statistic paths: 32-column slabs; a warp owns slab group sg (of G) and tile group tsel (of TG)
         const int nslab32 = p.NT >> 5;
         int G = kParts;
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                 for (int wi = part; wi < p.T * nslab32; wi += kParts) {
                     const int t = wi / nslab32, cs = wi - t * nslab32;
                     int pix;
-                    if constexpr (kTma) pix = decode_pix_fast(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q, p.div_wp, p.div_hp1);
+                    if constexpr (kTma) pix = epi_pix(q0 + t * 128);
                     else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                         const int gc = n_tile * p.NT + cs * 32 + chunk * 8;
                         for (int t = tsel; t < p.T; t += TG) {
                             int pix;
-                            if constexpr (kTma) pix = decode_pix_fast(q0 + t * 128, p.N, p.H, p.W, p.Wp, p.Hp1, p.Q, p.div_wp, p.div_hp1);
+                            if constexpr (kTma) pix = epi_pix(q0 + t * 128);
                             else pix = tab[t * 128 + lq * 32 + lane + p.Wp + 1].pix;
                             uint32_t v[32];
                             tmem_ld32(acc + (uint32_t)(t * p.NT + cs * 32), v);
@@ -561,7 +565,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_igemm_kernel(const __grid
                         int n = n_lo, y = y_lo, R = R_lo;
                         for (int r = 0; r < ((NUNET_DBG_SKIP & 4) ? 0 : nrows); ++r) {
                             // separator rows (y = -1) and rows outside the batch (n = -1 or n >= N) are out of bounds -> zeros
-                            tma_load_4d(dstA + (size_t)r * row_bytes, &p.tmap[si], cglob - src_c0, -1, y, n, &full[s]);
+                            if (p.strips > 1) {
+                                // "image" n is strip n % strips of image n / strips: the box starts one pixel left of the strip, so its
+                                // halo columns are the neighbouring strips' pixels (zeros only at the image border)
+                                const int img = (n >= 0) ? (int)fastdiv((uint32_t)n, p.div_strips) : -1;
+                                const int st = (n >= 0) ? n - img * p.strips : 0;
+                                tma_load_4d(dstA + (size_t)r * row_bytes, &p.tmap[si], cglob - src_c0, st * p.W - 1, y, img, &full[s]);
+                            } else {
+                                tma_load_4d(dstA + (size_t)r * row_bytes, &p.tmap[si], cglob - src_c0, -1, y, n, &full[s]);
+                            }
                             ++R;
                             if (R <= 0) { n = (R == 0) ? 0 : -1; y = -1; }
                             else if (++y == p.H) { y = -1; ++n; }
@@ -708,9 +720,19 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     if (H >= 65536 || W >= 65536) return NUNET_E_UNSUPPORTED;
     const int cin_pad = (cin_total <= 16) ? 16 : cin_total;
     if (cin_pad % 16 != 0) return NUNET_E_UNSUPPORTED;
+    if ((long long)N * H * W * (Cout > cin_pad ? Cout : cin_pad) >= (1LL << 40)) return NUNET_E_UNSUPPORTED;
+    // Rows wider than a tensor-load box (W + 2 > 256 positions): the batch is described as N*strips images of ceil(W/strips) columns;
+    // the box of a strip row starts one pixel to its left, so the halo columns hold the neighbouring strips' pixels.  Needs 32-channel
+    // chunks (tensor loads); falls back to the whole-row geometry (cp.async / transforming loaders) when no such tiling fits.
+    const int real_N = N, real_W = W;
+    static const bool no_strips = getenv("NUNET_NO_STRIPS") != nullptr;
+    int strips = (W + 2 > 256 && cin_pad % 32 == 0 && !no_strips) ? (W + 253) / 254 : 1;
+retry_geometry:
+    N = real_N * strips;
+    W = (real_W + strips - 1) / strips;
+    if (strips > 1) W += W & 1;      // even strip width: every row of a stage starts 128-byte aligned (tensor-load destination)
     const long long Q = ((long long)N * (H + 1) + 1) * (W + 2);
-    if (Q + 4LL * 128 + 2 * (W + 2) + 2 >= (1LL << 31) || (long long)N * H * W * (Cout > cin_pad ? Cout : cin_pad) >= (1LL << 40))
-        return NUNET_E_UNSUPPORTED;
+    if (Q + 4LL * 128 + 2 * (W + 2) + 2 >= (1LL << 31)) return NUNET_E_UNSUPPORTED;
     int NT = pick_nt(Cout);
     if (NT == 0) return NUNET_E_UNSUPPORTED;
 #ifdef NUNET_EXPERIMENT
@@ -737,7 +759,7 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
             // deeper rings measured 35-50 % SLOWER (32->192 at 96x96: S=2 0.264 ms, S=3 0.399 ms; profiles/r02_conv_tiling_sweep.log)
             for (int S = ((nch == 1 && resident_weights(NT)) ? 2 : 3); S >= minS; --S) {
                 if ((size_t)P * 16 >= (1u << 18)) continue;
-                if (conv_smem_bytes(T, NT, CK, S, P, cin_pad) > budget) continue;
+                if (strips > 1 ? CK != 32 : conv_smem_bytes(T, NT, CK, S, P, cin_pad) > budget) continue;   // strips: only the TMA layout (below) is ever launched
                 // rows that fit a tensor-load box: the same (T, S) must also fit the TMA variant's larger stages (copy-mode sources
                 // then run on tensor loads with sixteen epilogue warps; a deeper ring that only fits the cp.async layout is slower)
                 if (CK == 32 && W + 2 <= 256 && conv_tma_smem_bytes(T, NT, S, P, W, cin_pad, 8) > 227 * 1024) continue;
@@ -752,15 +774,19 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     // loaders, eight epilogue warps).  Where the layer is large enough for the weight stream not to matter, narrower tiles on tensor
     // loads win: 64-wide at >= 3000 tiles (48x48: 64->320 0.313 -> 0.226 ms, 64->192 0.171 -> 0.134), 128-wide at >= 1000 tiles
     // (24x24: 128->384 0.149 -> 0.123); at 12x12 / 6x6 the default stays (256->768: 0.128 vs 0.197 / 0.334 ms).
-    if (bestCK != 32 && W + 2 <= 256 && cin_pad % 32 == 0) {
+    if ((bestCK != 32 || bestS < 2) && W + 2 <= 256 && cin_pad % 32 == 0) {
         const long long tiles = (Q + 127) / 128;
         const int alt = (tiles >= 3000 && Cout % 64 == 0 && NT > 64) ? 64 : ((tiles >= 1000 && Cout % 128 == 0 && NT > 128) ? 128 : 0);
         if (alt) {
             const int keepT = bestT, keepCK = bestCK, keepS = bestS;
             search(alt);
-            if (bestT && bestCK == 32) NT = alt;
+            if (bestT && bestCK == 32 && bestS >= 2) NT = alt;
             else { n_tiles = Cout / NT; bestT = keepT; bestCK = keepCK; bestS = keepS; }
         }
+    }
+    if (strips > 1 && (!bestT || bestCK != 32 || conv_tma_smem_bytes(bestT, NT, bestS, 128 * bestT + 2 * (W + 2) + 2, W, cin_pad, 8) > 227 * 1024)) {
+        strips = 1;
+        goto retry_geometry;
     }
     if (!bestT) return NUNET_E_SMEM;
 #ifdef NUNET_EXPERIMENT
@@ -790,13 +816,15 @@ extern "C" int nunet_conv3x3_plan(int32_t N, int32_t H, int32_t W, int32_t cin_t
     pl->tma_a_stage_bytes = 0;
     pl->tma_smem_bytes = 0;
     pl->tma_epi_warps = 0;
-    if (bestCK == 32) {
+    pl->strips = strips;
+    if (bestCK == 32 && W + 2 <= 256) {
         const size_t a_tma = conv_tma_a_stage(pl->P, W);
         for (int ew = 16; ew >= 8 && !pl->tma_smem_bytes; ew -= 8) {
             const size_t total = conv_tma_smem_bytes(bestT, NT, bestS, pl->P, W, cin_pad, ew);
             if (total <= 227 * 1024) { pl->tma_a_stage_bytes = (int)a_tma; pl->tma_smem_bytes = (int)total; pl->tma_epi_warps = ew; }
         }
     }
+    if (strips > 1) pl->smem_bytes = pl->tma_smem_bytes;   // the only layout a strip plan is launched with
     int cols = 2 * bestT * NT, tc = 32;
     while (tc < cols) tc <<= 1;
     pl->tmem_cols = tc;
@@ -836,9 +864,13 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     int rc = nunet_conv3x3_plan(d->N, d->H, d->W, cin, d->Cout, &pl);
     if (rc) return rc;
     ConvParams p{};
-    p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
+    const int strips = pl.strips > 1 ? pl.strips : 1;
+    p.strips = strips; p.Wreal = d->W; p.div_strips = make_fastdiv((uint32_t)(strips > 1 ? strips : 2));
+    p.N = d->N * strips; p.H = d->H; p.W = (d->W + strips - 1) / strips; p.Hp1 = d->H + 1;
+    if (strips > 1) p.W += p.W & 1;
+    p.Wp = p.W + 2;
     p.div_wp = make_fastdiv((uint32_t)p.Wp); p.div_hp1 = make_fastdiv((uint32_t)p.Hp1);
-    p.Q = (d->N * (d->H + 1) + 1) * (d->W + 2);
+    p.Q = (p.N * (d->H + 1) + 1) * (p.W + 2);
     p.T = pl.T; p.NT = pl.NT; p.CK = pl.CK; p.S = pl.S; p.P = pl.P; p.nchunks = pl.nchunks;
     p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src; p.tmem_cols = pl.tmem_cols; p.ntg = pl.ntg;
     for (int i = 0; i < d->num_src; ++i) {
@@ -880,6 +912,7 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
     for (int i = 0; i < d->num_src; ++i) kinds[i] = d->src[i].kind;
     const int mode = sources_mode(kinds, d->num_src);
     if (d->wpack_layout != 0 && (d->wpack_layout != 1 || mode != MODE_ACT)) return NUNET_E_BADARG;
+    if (strips > 1 && mode != MODE_ACT) return NUNET_E_UNSUPPORTED;   // column strips: tensor-load sources only (see nunet_conv_plan_t.strips)
     switch (mode) {
         case MODE_INPUT: return launch_conv<MODE_INPUT>(p, pl, (cudaStream_t)stream);
         case MODE_SAME: return launch_conv<MODE_SAME>(p, pl, (cudaStream_t)stream);
@@ -893,10 +926,10 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
             }
             // tensor-load path: box = (32 ch, W+2 px, 1, 1) per padded row, needs W+2 <= 256 and the CK=32 tiling
             static const bool no_tma = getenv("NUNET_NO_TMA") != nullptr;
-            if (!no_tma && pl.CK == 32 && d->W + 2 <= 256 && pl.tma_smem_bytes > 0) {
+            if (!no_tma && pl.CK == 32 && p.W + 2 <= 256 && (p.W & 1) == 0 && pl.tma_smem_bytes > 0) {   // odd rows: 64-byte-aligned stage rows, not a TMA destination
                 bool ok = true;
-                for (int i = 0; i < d->num_src && ok; ++i)
-                    ok = encode_nhwc_map(&p.tmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, d->W + 2, 64) == 0;
+                for (int i = 0; i < d->num_src && ok; ++i)   // maps over the REAL tensors; the box is one (strip) row + its two halo columns
+                    ok = encode_nhwc_map(&p.tmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, p.W + 2, 64) == 0;
                 if (ok) {
                     nunet_conv_plan_t pt = pl;
                     pt.smem_bytes = pl.tma_smem_bytes;
@@ -905,6 +938,7 @@ extern "C" int nunet_conv3x3_fwd(const nunet_conv_desc_t* d, void* stream) {
                     return launch_conv<MODE_ACT_TMA>(p, pt, (cudaStream_t)stream);
                 }
             }
+            if (strips > 1) return NUNET_E_UNSUPPORTED;   // the strip geometry exists on tensor loads only
             return launch_conv<MODE_ACT>(p, pl, (cudaStream_t)stream);
         }
         case MODE_POOL_ACT: return launch_conv<MODE_POOL_ACT>(p, pl, (cudaStream_t)stream);

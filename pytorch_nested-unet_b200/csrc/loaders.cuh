@@ -322,5 +322,15 @@ __device__ __forceinline__ int decode_pix_fast(int q, int N, int H, int W, int W
     const int n = (int)fastdiv((uint32_t)R, dHp1), rr = R - n * Hp1;
     return (c >= 1 && c <= W && rr >= 1 && n < N) ? (n * H + (rr - 1)) * W + (c - 1) : -1;
 }
+// Column strips (rows wider than a tensor-load box): "image" v of the flattened geometry is strip v % strips of image v / strips.
+__device__ __forceinline__ int decode_pix_strips(int q, int Nv, int H, int Ws, int Wp, int Hp1, int Q, const FastDiv& dWp, const FastDiv& dHp1,
+                                                 int strips, int Wreal, const FastDiv& dStrips) {
+    if (q < 0 || q >= Q) return -1;
+    const int R = (int)fastdiv((uint32_t)q, dWp), c = q - R * Wp;
+    const int v = (int)fastdiv((uint32_t)R, dHp1), rr = R - v * Hp1;
+    const int n = (int)fastdiv((uint32_t)v, dStrips), s = v - n * strips;
+    const int x = s * Ws + c - 1;
+    return (c >= 1 && c <= Ws && x < Wreal && rr >= 1 && v < Nv) ? (n * H + (rr - 1)) * Wreal + x : -1;
+}
 
 }  // namespace nunet

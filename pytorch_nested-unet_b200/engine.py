@@ -151,8 +151,18 @@ _NOCTX = _NoCtx()
 
 
 def _tma_width(w):
-    """The TMA-fed kernels take rows of up to 254 pixels (box dimension limit 256 incl. padding)."""
+    """The stacked Cout = 32 kernel and the TMA weight-gradient kernel take rows of up to 254 pixels (box dimension limit 256 incl.
+    padding)."""
     return w + 2 <= 256
+
+
+STRIPS = _os.environ.get("NUNET_NO_STRIPS") is None
+
+
+def _mat_width(w):
+    """Operands are materialised (and fed by tensor loads) at this row width: always, since the forward / dgrad kernel describes wider
+    rows as column strips (nunet_conv_plan_t.strips); NUNET_NO_STRIPS=1 restores the transforming-loader path for rows > 254 px."""
+    return STRIPS or _tma_width(w)
 
 
 def _stacked(s, N, h, w, cin_pad):
@@ -336,9 +346,9 @@ def _forward_layer(s, recs, x, x32, N, H, W, train, dp, ws, dev, st):
     # only worth materialising where the TMA-fed kernels take them.)
     r.logits = None
     kinds = [c[2] for c in s.consumers]
-    mat = (s.which == 2 or (MATERIALIZE_ALL and _tma_width(w))) and MATERIALIZE_NODE_OUTPUTS and bool(kinds)
+    mat = (s.which == 2 or (MATERIALIZE_ALL and _mat_width(w))) and MATERIALIZE_NODE_OUTPUTS and bool(kinds)
     want_up = mat and MATERIALIZE_UPSAMPLED and L.SRC_UP in kinds
-    want_pool = mat and MATERIALIZE_POOLED and _tma_width(w // 2) and L.SRC_POOL in kinds
+    want_pool = mat and MATERIALIZE_POOLED and _mat_width(w // 2) and L.SRC_POOL in kinds
     want_a = mat and (L.SRC_SAME in kinds or (L.SRC_UP in kinds and not want_up) or (L.SRC_POOL in kinds and not want_pool))
     head = None
     if s.head is not None and s.cout == 32 and s.head.out_channels <= 8 and not (want_up or want_pool):
@@ -376,7 +386,7 @@ def _forward(model, x, train, want_dgrad=False):
     ws = st.workspace(dev)
     dp = _world(model)
     recs = []
-    packed_input = PACK_INPUT and _tma_width(W)
+    packed_input = PACK_INPUT and _mat_width(W)
     st.pack_all(N, H, W, want_dgrad, packed_input)
     norm = model.__dict__.get("_nunet_input_norm") or {}
     if x32 is not None:

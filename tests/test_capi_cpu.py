@@ -47,7 +47,14 @@ def test_plans_cover_all_baseline_layer_shapes(size, N):
         assert lib.nunet_conv3x3_plan(n, h, w, cin, cout, C.byref(pl)) == 0, (n, h, w, cin, cout)
         assert pl.smem_bytes <= 227 * 1024 and pl.T * pl.NT * 2 <= 512 and pl.tmem_cols <= 512
         assert pl.NT * pl.n_tiles == cout and pl.nchunks * pl.CK == pl.cin_pad and 1 <= pl.S <= 3  # the stage ring spans tile groups
-        assert pl.P == 128 * pl.T + 2 * (w + 2) + 2 and pl.P * 16 < (1 << 18)
+        # rows wider than a tensor-load box are planned as column strips (tensor-load sources, 32-channel chunks)
+        strips = max(pl.strips, 1)
+        ws = (w + strips - 1) // strips
+        ws += (ws & 1) if strips > 1 else 0
+        if strips > 1:
+            assert w + 2 > 256 and cin % 32 == 0 and ws + 2 <= 256
+            assert pl.CK == 32 and 0 < pl.tma_smem_bytes <= 227 * 1024
+        assert pl.P == 128 * pl.T + 2 * (ws + 2) + 2 and pl.P * 16 < (1 << 18)
         assert pl.grid_m * pl.n_tiles <= 148 and pl.grid_m <= pl.ntg
         if cin >= 32:  # dgrad runs the same kernel with the roles of cin / cout swapped
             pd = L.ConvPlan()

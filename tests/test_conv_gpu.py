@@ -48,6 +48,12 @@ CASES = [
     (3, 12, 20, [("same_act", 256), ("up_act", 512)], 256),
     (16, 96, 96, [("same_act", 32), ("up_act", 64)], 32),
     (2, 6, 6, [("up_act", 512)], 256),
+    # rows wider than a tensor-load box: column strips (2, 3 and 4 strips; widths that do not divide evenly)
+    (2, 5, 301, [("same_act", 32)], 32),
+    (1, 4, 520, [("same_act", 64), ("same_act", 32)], 64),
+    (2, 3, 256, [("same_act", 32)], 96),
+    (1, 2, 1000, [("same_act", 32)], 32),
+    (2, 7, 21, [("same_act", 32)], 32),     # odd width: stage rows are only 64-byte aligned -> cp.async copy mode
 ]
 
 
