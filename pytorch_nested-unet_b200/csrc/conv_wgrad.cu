@@ -293,7 +293,14 @@ extern "C" int nunet_conv3x3_wgrad_plan(int32_t N, int32_t H, int32_t W, int32_t
                 if (wgrad_smem_bytes(kp, s, Pg, tr ? 3 : 1, Pg2, cin_pad) <= budget) { KP = kp; S = s; triple = tr; break; }
         }
     }
-    if (!KP) return NUNET_E_SMEM;
+    if (!KP) {
+        // the cp.async variant does not fit (rows of >= ~600 pixels): the layer exists on the TMA variant (column strips) only
+        pl->KP = 0; pl->S = 0; pl->Pg = 0; pl->cpc = 0; pl->nchunks_total = 0; pl->splits = 0; pl->m_tiles = (cin_pad + 127) / 128;
+        pl->n_tiles = Cout / 32; pl->cin_pad = cin_pad; pl->triple = 0; pl->smem_bytes = 0; pl->part_elems = 0;
+        if (nunet_wgrad_tma_plan(N, H, W, cin_pad, Cout, pl) != 0) return NUNET_E_SMEM;
+        pl->part_elems = (int64_t)pl->tma_splits * 9 * cin_pad * Cout;
+        return NUNET_OK;
+    }
     const int nchunks_total = (int)((Q + KP - 1) / KP);
     const int m_tiles = (cin_pad + 127) / 128, n_tiles = Cout / 32;
     // enough CTAs for ~2 waves, but at least 4 chunks per CTA to amortise prologue + epilogue
@@ -359,6 +366,7 @@ extern "C" int nunet_conv3x3_wgrad(const nunet_wgrad_desc_t* d, void* stream) {
             if (trc >= 0) return trc;   // < 0: tensor-map encoding unavailable -> cp.async kernel below
         }
     }
+    if (!pl.KP) return NUNET_E_SMEM;   // no cp.async tiling for this shape (plan: TMA variant only)
     WgradParams p{};
     p.N = d->N; p.H = d->H; p.W = d->W; p.Wp = d->W + 2; p.Hp1 = d->H + 1;
     p.Q = ((long long)d->N * (d->H + 1) + 1) * (d->W + 2);

@@ -37,6 +37,8 @@ struct WgradTmaParams {
     int x_box_rows, g_box_rows;
     int chunks_total, cpc, S, ksteps;
     int stacked;  // 1: cin_pad == 32, kernel rows stacked on the A operand
+    int strips, Ws;   // strips > 1: rows wider than a tensor-load box — "image" v is column strip v % strips (Ws pixels) of image v / strips
+    FastDiv div_strips;
     int cin_pad, Cout, num_src;
     int srcC[NUNET_MAX_SRC];
     int x_block_bytes, x_stage_bytes, g_stage_bytes;
@@ -115,10 +117,23 @@ __global__ void __launch_bounds__(kTThreads, 1) conv3x3_wgrad_tma_kernel(const _
                 else { n = c / p.cpi; y0 = (c - n * p.cpi) * p.ry - 1; }
                 const int xy = (!p.kimg && p.stacked) ? y0 - 1 : y0, gyy = (!p.kimg && !p.stacked) ? y0 - 1 : y0;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], tx);
                 uint8_t* dx = sX + (size_t)s * x_bytes + x_off;
-                for (int b = 0; b < xblocks; ++b) tma_load_4d(dx + (size_t)b * p.x_block_bytes, &p.xmap[bsrc[b]], bch[b], 0, xy, n, &full[s]);
-                tma_load_4d(sG + (size_t)s * g_bytes + g_off, &p.gmap, n_tile * 32, -1, gyy, n, &full[s]);
+                if (p.strips > 1) {
+                    // Column strips (rows mode only).  The sum over a row splits into strips if X is RESTRICTED to the strip's own
+                    // pixels while gy keeps one real halo pixel on either side: X goes row by row through a (32 ch x Ws px) box into
+                    // the PW-pitch rows — positions Ws .. PW-1 of every row are never written and stay zero from the prologue — and
+                    // the gy box simply starts one pixel to the left of the strip.
+                    const int img = (int)fastdiv((uint32_t)n, p.div_strips), st = n - img * p.strips;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(p.x_box_rows * xblocks) * (uint32_t)p.Ws * 64u + (uint32_t)p.g_box_rows * row_bytes);
+                    for (int b = 0; b < xblocks; ++b)
+                        for (int r = 0; r < p.x_box_rows; ++r)
+                            tma_load_4d(dx + (size_t)b * p.x_block_bytes + (size_t)r * row_bytes, &p.xmap[bsrc[b]], bch[b], st * p.Ws, xy + r, img, &full[s]);
+                    tma_load_4d(sG + (size_t)s * g_bytes + g_off, &p.gmap, n_tile * 32, st * p.Ws - 1, gyy, img, &full[s]);
+                } else {
+                    mbar_arrive_expect_tx(&full[s], tx);
+                    for (int b = 0; b < xblocks; ++b) tma_load_4d(dx + (size_t)b * p.x_block_bytes, &p.xmap[bsrc[b]], bch[b], 0, xy, n, &full[s]);
+                    tma_load_4d(sG + (size_t)s * g_bytes + g_off, &p.gmap, n_tile * 32, -1, gyy, n, &full[s]);
+                }
             }
         }
         __syncwarp();
@@ -223,7 +238,21 @@ struct TmaTiling {
 
 // Picks the chunk shape (rows of one image, or whole images) that minimises the number of 16-position K steps of the whole
 // layer (+1 per chunk for the pipeline hand-off) among those that leave at least two pipeline stages.
+// Rows wider than a tensor-load box: N*strips column strips of Ws (even) pixels, as in nunet_conv3x3_plan.
+static int wgrad_strips(int W, int* Ws) {
+    static const bool no_strips = getenv("NUNET_NO_STRIPS") != nullptr;
+    int strips = (W + 2 > 256 && !no_strips) ? (W + 253) / 254 : 1;
+    int w = (W + strips - 1) / strips;
+    if (strips > 1) w += w & 1;
+    *Ws = w;
+    return strips;
+}
+
 static bool tma_tiling(int N, int H, int W, int cin_pad, TmaTiling* t) {
+    int Ws;
+    const int strips = wgrad_strips(W, &Ws);
+    N *= strips;
+    W = Ws;
     const int PW = (W + 2 + 1) & ~1;          // even: every padded row starts 128-byte aligned
     const int Hp1 = H + 1;
     if (PW > 256) return false;               // TMA box dimension limit
@@ -233,7 +262,7 @@ static bool tma_tiling(int N, int H, int W, int cin_pad, TmaTiling* t) {
     const int halo = 2 * PW + 3;
     for (int pass = 0; pass < 2; ++pass) {
         const int lim = pass == 0 ? (Hp1 < 254 ? Hp1 : 254) : (N < 256 ? N : 256);
-        if (pass == 1 && Hp1 > 256) break;
+        if (pass == 1 && (Hp1 > 256 || strips > 1)) break;   // whole-image chunks need consecutive images in the batch dimension
         for (int q = 1; q <= lim; ++q) {
             const int rows = pass == 0 ? q : q * Hp1;
             const int ksteps = (rows * PW + 15) / 16, kpos = ksteps * 16;
@@ -292,6 +321,8 @@ int nunet_wgrad_tma_launch(const nunet_wgrad_desc_t* d, const nunet_wgrad_plan_t
     p.PW = t.PW; p.ry = t.ry; p.cpi = t.cpi; p.kimg = t.kimg; p.x_box_rows = t.x_box_rows; p.g_box_rows = t.g_box_rows;
     p.chunks_total = pl.tma_chunks; p.cpc = pl.tma_cpc; p.S = pl.tma_S; p.ksteps = t.ksteps;
     p.stacked = t.stacked;
+    p.strips = wgrad_strips(d->W, &p.Ws);
+    p.div_strips = make_fastdiv((uint32_t)(p.strips > 1 ? p.strips : 2));
     p.cin_pad = pl.cin_pad; p.Cout = d->Cout; p.num_src = d->num_src;
     p.x_block_bytes = t.x_block_bytes; p.x_stage_bytes = t.x_stage_bytes; p.g_stage_bytes = t.g_stage_bytes;
     p.part = d->part;
@@ -299,7 +330,8 @@ int nunet_wgrad_tma_launch(const nunet_wgrad_desc_t* d, const nunet_wgrad_plan_t
     const int gbh = t.kimg ? p.Hp1 : t.g_box_rows, gbn = t.kimg ? t.kimg : 1;
     for (int i = 0; i < d->num_src; ++i) {
         p.srcC[i] = d->src[i].C;
-        if (encode_nhwc_map(&p.xmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, p.PW, 64, xbh, xbn) != 0) return -1;
+        if (p.strips > 1 ? encode_nhwc_map(&p.xmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, p.Ws, 64, 1, 1) != 0
+                         : encode_nhwc_map(&p.xmap[i], d->src[i].data, d->N, d->H, d->W, d->src[i].C, 32, p.PW, 64, xbh, xbn) != 0) return -1;
     }
     if (encode_nhwc_map(&p.gmap, d->gy, d->N, d->H, d->W, d->Cout, 32, p.PW, 64, gbh, gbn) != 0) return -1;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.tma_smem_bytes);

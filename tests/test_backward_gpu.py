@@ -168,6 +168,11 @@ WG_CASES = [
     (3, 12, 20, [("same_act", 256), ("same_act", 512)], 256),
     (2, 6, 6, [("same_act", 512)], 512),
     (5, 6, 6, [("same_act", 256)], 512),
+    # rows wider than a tensor-load box: column strips (X restricted to the strip row by row, gy with its real halo columns)
+    (2, 5, 300, [("same_act", 64)], 32),
+    (1, 4, 520, [("same_act", 32)], 64),              # Cin = 32: kernel rows stacked on the A side, 3 strips
+    (2, 9, 301, [("same_act", 32), ("same_act", 128)], 64),
+    (1, 3, 1000, [("same_act", 64)], 32),
 ]
 
 

@@ -93,20 +93,24 @@ def test_tma_weight_gradient_and_stacked_conv_tilings(size, N):
     for (n, h, w, cin, cout) in _layers(size, N):
         pw = L.WgradPlan()
         assert lib.nunet_conv3x3_wgrad_plan(n, h, w, cin, cout, C.byref(pw)) == 0
-        want_tma = cin % 32 == 0 and w + 2 <= 256
+        want_tma = cin % 32 == 0          # rows wider than 254 px: column strips (rows mode only)
         assert bool(pw.tma) == want_tma, (n, h, w, cin, cout)
+        strips = (w + 253) // 254 if w + 2 > 256 else 1
+        ws = (w + strips - 1) // strips
+        ws += (ws & 1) if strips > 1 else 0
+        nv, wv = n * strips, ws               # the tiling below is that of the strip geometry
         if pw.tma:
             assert pw.tma_smem_bytes <= 227 * 1024 and 1 <= pw.tma_S <= 4
-            assert pw.tma_PW >= w + 2 and pw.tma_PW % 2 == 0
+            assert pw.tma_PW >= wv + 2 and pw.tma_PW % 2 == 0 and pw.tma_PW <= 256 and (strips == 1 or pw.tma_r > 0)
             assert pw.tma_splits * pw.tma_cpc >= pw.tma_chunks and (pw.tma_splits - 1) * pw.tma_cpc < pw.tma_chunks
             assert pw.tma_G == (1 if cin == 32 else 3) and pw.tma_Nt == 32
             assert pw.part_elems >= pw.tma_splits * 9 * cin * cout
             # chunk enumeration covers every padded row exactly once: ry rows of one image, or kimg whole images
             if pw.tma_r > 0:
-                assert pw.tma_chunks == n * ((h + 1 + pw.tma_r - 1) // pw.tma_r)
+                assert pw.tma_chunks == nv * ((h + 1 + pw.tma_r - 1) // pw.tma_r)
                 assert -(-(pw.tma_r * pw.tma_PW) // 16) * 16 <= 1024
             else:
-                assert pw.tma_chunks == (n + (-pw.tma_r) - 1) // (-pw.tma_r) and (-pw.tma_r) * (h + 1) <= 256
+                assert pw.tma_chunks == (nv + (-pw.tma_r) - 1) // (-pw.tma_r) and (-pw.tma_r) * (h + 1) <= 256
             m_tiles = (cin + 127) // 128
             assert pw.tma_splits * m_tiles * (cout // 32) <= 148 or pw.tma_splits == 1     # one wave of CTAs
         want_c32 = cout == 32 and cin >= 64 and cin % 32 == 0 and w + 2 <= 256
