@@ -37,6 +37,8 @@ struct C32Params {
     CUtensorMap xmap[NUNET_MAX_SRC];
     int N, H, W, PW;
     uint32_t pw_magic;           // ceil(2^32 / PW): u / PW == __umulhi(u, pw_magic) for the u < 2^16 of a group
+    int strips, Wreal;           // strips > 1: N / W describe N*strips column strips of the Wreal-pixel rows (see nunet_conv_plan_t.strips)
+    FastDiv div_strips;
     int ry, gpi, groups_total;   // rows per group, groups per image
     int box_rows, S, nch, num_src;
 #ifdef NUNET_EXPERIMENT
@@ -130,7 +132,14 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                     while (cglob >= c0 + p.srcC[si]) { c0 += p.srcC[si]; ++si; }
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], (C32_DBG(1) ? 0u : a_box_bytes) + (p.res_b ? 0u : kC32BBytes));
-                    if (!C32_DBG(1)) tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, -1, y0 - 1, n, &full[s]);
+                    if (!C32_DBG(1)) {
+                        if (p.strips > 1) {   // "image" n = strip n % strips of image n / strips; the box starts one pixel left of the strip
+                            const int img = (int)fastdiv((uint32_t)n, p.div_strips), st = n - img * p.strips;
+                            tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, st * p.W - 1, y0 - 1, img, &full[s]);
+                        } else {
+                            tma_load_4d(sA + (size_t)s * p.a_stage_bytes, &p.xmap[si], cglob - c0, -1, y0 - 1, n, &full[s]);
+                        }
+                    }
                     if (!p.res_b) bulk_g2s(sB + (size_t)s * kC32BBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kC32BBytes, kC32BBytes, &full[s]);
                 }
             }
@@ -204,7 +213,13 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
             const int n = g / p.gpi, y0 = (g - n * p.gpi) * p.ry;
             const int rows = min(p.ry, p.H - y0);
             const int ntile = (rows * p.PW + 125) / 126;
-            const int img_row0 = (n * p.H + y0) * p.W;
+            int img_row0 = (n * p.H + y0) * p.W, row_pitch = p.W, col_lim = p.W;
+            if (p.strips > 1) {
+                const int img = (int)fastdiv((uint32_t)n, p.div_strips), st = n - img * p.strips;
+                img_row0 = (img * p.H + y0) * p.Wreal + st * p.W;
+                row_pitch = p.Wreal;
+                col_lim = min(p.W, p.Wreal - st * p.W);      // the last strip may be narrower
+            }
             for (int t = 0; t < ntile; ++t) {
                 ++seq;
                 mbar_wait(&acc_full[t], (tile_phase >> t) & 1u);
@@ -238,8 +253,8 @@ __global__ void __launch_bounds__(kC32Threads, 1) conv3x3_c32_kernel(const __gri
                 // this lane's output position inside the group (index u holds pixel u % PW - 1 of row u / PW)
                 const int u = t * 126 + m;
                 const int row = (int)__umulhi((uint32_t)u, p.pw_magic), px = u - row * p.PW - 1;
-                const bool valid = (m >= 1) && (m <= 126) && (row < rows) && (px >= 0) && (px < p.W);
-                const size_t pix = (size_t)(uint32_t)(img_row0 + row * p.W + px);       // N*H*W < 2^31 (plan check)
+                const bool valid = (m >= 1) && (m <= 126) && (row < rows) && (px >= 0) && (px < col_lim);
+                const size_t pix = (size_t)(uint32_t)(img_row0 + row * row_pitch + px);       // N*H*W < 2^31 (plan check)
                 uint4 ym = make_uint4(0, 0, 0, 0);
                 if (masked && valid) ym = __ldg(reinterpret_cast<const uint4*>(p.mask_y + pix * 32 + cq * 8));
                 float y[8];
@@ -329,7 +344,18 @@ struct C32Tiling {
     int PW, ry, gpi, box_rows, S, res_b, a_stage_bytes, smem_bytes;
 };
 
+// Rows wider than a tensor-load box: N*strips column strips of Ws (even) pixels, exactly as nunet_conv3x3_plan describes them.
+static int c32_strips(int W, int* Ws) {
+    static const bool no_strips = getenv("NUNET_NO_STRIPS") != nullptr;
+    int strips = (W + 2 > 256 && !no_strips) ? (W + 253) / 254 : 1;
+    int w = (W + strips - 1) / strips;
+    if (strips > 1) w += w & 1;
+    *Ws = w;
+    return strips;
+}
+
 static bool c32_tiling(int H, int W, int nch, C32Tiling* t) {
+    { int Ws; c32_strips(W, &Ws); W = Ws; }
     const int PW = (W + 2 + 1) & ~1;
     if (PW > 256) return false;
     const int budget = 226 * 1024;
@@ -383,7 +409,10 @@ int nunet_conv_c32_launch(const nunet_conv_desc_t* d, int cin, int grid, const B
     C32Tiling t;
     if (!c32_tiling(d->H, d->W, cin / 32, &t)) return NUNET_E_UNSUPPORTED;
     C32Params p{};
-    p.N = d->N; p.H = d->H; p.W = d->W; p.PW = t.PW; p.pw_magic = (uint32_t)(((1ULL << 32) + (uint64_t)t.PW - 1) / (uint64_t)t.PW); p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * t.gpi;
+    int Ws;
+    const int strips = c32_strips(d->W, &Ws);
+    p.strips = strips; p.Wreal = d->W; p.div_strips = make_fastdiv((uint32_t)(strips > 1 ? strips : 2));
+    p.N = d->N * strips; p.H = d->H; p.W = Ws; p.PW = t.PW; p.pw_magic = (uint32_t)(((1ULL << 32) + (uint64_t)t.PW - 1) / (uint64_t)t.PW); p.ry = t.ry; p.gpi = t.gpi; p.groups_total = d->N * strips * t.gpi;
     p.box_rows = t.box_rows; p.S = t.S; p.res_b = t.res_b; p.nch = cin / 32; p.num_src = d->num_src; p.a_stage_bytes = t.a_stage_bytes;
     p.wpack = d->wpack; p.out = (__nv_bfloat16*)d->out; p.stat_part = d->stat_part;
     p.tail = tail;

@@ -168,7 +168,7 @@ def _mat_width(w):
 def _stacked(s, N, h, w, cin_pad):
     """True if this layer's forward conv runs on the stacked Cout = 32 kernel (conv_c32.cu): all its sources are materialised
     activations at this resolution (always the case where the TMA width limit holds) and the shape is eligible."""
-    if s.cout != 32 or not _tma_width(w) or not (MATERIALIZE_NODE_OUTPUTS and MATERIALIZE_UPSAMPLED and MATERIALIZE_ALL and MATERIALIZE_POOLED):
+    if s.cout != 32 or not _mat_width(w) or not (MATERIALIZE_NODE_OUTPUTS and MATERIALIZE_UPSAMPLED and MATERIALIZE_ALL and MATERIALIZE_POOLED):
         return False
     return ops.c32_eligible(N, h, w, cin_pad, s.cout)
 
@@ -241,7 +241,7 @@ class _State(object):
             cinp = _cin_pad(s, packed_input)
             modes = [(L.PACK_FWD_C32 if _stacked(s, N, h, w, cinp) else L.PACK_FWD, ops.conv_plan(N, h, w, cinp, s.cout))]
             if want_dgrad and s.sources[0][0] >= 0:
-                dstack = (s.which == 2 and FUSE_BLOCK_ROUTER and s.cin_pad == 32 and _tma_width(w) and ops.c32_eligible(N, h, w, s.cout, s.cin_pad))
+                dstack = (s.which == 2 and FUSE_BLOCK_ROUTER and s.cin_pad == 32 and _mat_width(w) and ops.c32_eligible(N, h, w, s.cout, s.cin_pad))
                 modes.append((L.PACK_DGRAD_C32 if dstack else L.PACK_DGRAD, ops.conv_plan(N, h, w, s.cout, s.cin_pad)))
             wt = s.conv.weight
             if wt.dtype != torch.float32 or not wt.is_contiguous():
@@ -566,7 +566,7 @@ def _backward(model, xs, recs, grad_logits, grad_alloc=None):
             if s.sources[0][0] >= 0:
                 plan = ops.conv_plan(N, h, w, s.cout, s.cin_pad)
                 # a dgrad that produces 32 channels (level-0 second convs) runs on the stacked kernel too
-                dstack = (s.which == 2 and FUSE_BLOCK_ROUTER and s.cin_pad == 32 and _tma_width(w) and ops.c32_eligible(N, h, w, s.cout, s.cin_pad))
+                dstack = (s.which == 2 and FUSE_BLOCK_ROUTER and s.cin_pad == 32 and _mat_width(w) and ops.c32_eligible(N, h, w, s.cout, s.cin_pad))
                 wpd = st.pack(s, plan, L.PACK_DGRAD_C32 if dstack else L.PACK_DGRAD)
                 gsrc = [ops.Source(L.SRC_ACT, gy, s.cout)]
                 if s.which == 2 and FUSE_BLOCK_ROUTER:

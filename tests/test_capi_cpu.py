@@ -113,5 +113,5 @@ def test_tma_weight_gradient_and_stacked_conv_tilings(size, N):
                 assert pw.tma_chunks == (nv + (-pw.tma_r) - 1) // (-pw.tma_r) and (-pw.tma_r) * (h + 1) <= 256
             m_tiles = (cin + 127) // 128
             assert pw.tma_splits * m_tiles * (cout // 32) <= 148 or pw.tma_splits == 1     # one wave of CTAs
-        want_c32 = cout == 32 and cin >= 64 and cin % 32 == 0 and w + 2 <= 256
+        want_c32 = cout == 32 and cin >= 64 and cin % 32 == 0      # any row width (column strips above 254 px)
         assert bool(lib.nunet_conv3x3_c32_eligible(n, h, w, cin, cout)) == want_c32, (n, h, w, cin, cout)

@@ -170,7 +170,8 @@ def test_upsample2x_matches_torch():
 
 
 C32_CASES = [(2, 16, 16, [64]), (2, 32, 32, [32, 64]), (3, 48, 80, [32, 32, 64]), (4, 96, 96, [32] * 4 + [64]), (2, 6, 6, [64]), (5, 96, 96, [32, 32]),
-             (1, 16, 240, [32, 32, 32])]
+             (1, 16, 240, [32, 32, 32]),
+             (2, 5, 300, [64]), (1, 4, 521, [32, 64])]      # column strips (2 and 3; last strip narrower)
 
 
 @pytest.mark.parametrize("case", C32_CASES, ids=lambda c: "N%d_%dx%d_cin%d" % (c[0], c[1], c[2], sum(c[3])))

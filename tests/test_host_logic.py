@@ -140,9 +140,9 @@ def test_kernel_selection_policy_for_materialised_operands():
     stacked = sorted((s.node, s.which, s.cin_pad) for s in specs
                      if engine._stacked(s, 4, 96 >> s.level, 96 >> s.level, engine._cin_pad(s, True)))
     assert stacked == [("0_1", 1, 96), ("0_2", 1, 128), ("0_3", 1, 160), ("0_4", 1, 192)]
-    # 256-pixel rows exceed the 254-pixel TMA box: nothing at level 0 is stacked / repacked there, level 1 (128 px) still is eligible
-    assert not any(engine._stacked(s, 4, 256, 256, engine._cin_pad(s, False)) for s in specs if s.level == 0)
-    assert engine._tma_width(254) and not engine._tma_width(255)
+    # 256-pixel rows exceed the 254-pixel tensor-load box: the kernels describe them as column strips, the same layers stay stacked
+    assert sorted(s.node for s in specs if s.level == 0 and engine._stacked(s, 4, 256, 256, engine._cin_pad(s, True))) == ["0_1", "0_2", "0_3", "0_4"]
+    assert engine._tma_width(254) and not engine._tma_width(255) and engine._mat_width(255) and engine._mat_width(512)
     stem = specs[0]
     assert engine._cin_pad(stem, True) == 32 and engine._cin_pad(stem, False) == 16
     u = archs.UNet(1, 3)
