@@ -1,9 +1,11 @@
-"""Throughput of the other BASELINE.json configurations (C1, C3, C4, C5) on one GPU; writes profiles/r01_configs.json."""
+"""Throughput of the other BASELINE.json configurations (C1, C3, C4, C5) on one GPU; writes gpurun_out/configs.json (copied to
+profiles/rNN_configs.json).  fp32 NCHW inputs as the reference loop feeds them; the package's fused SGD."""
 import json, os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "pytorch_nested-unet_b200"))
 import archs, losses, metrics, ops
+import optim as noptim
 
 dev = torch.device("cuda:0")
 
@@ -12,7 +14,7 @@ def train_rate(arch, classes, ds, n, size, steps=5, warm=3):   # warm >= 3: the 
     torch.manual_seed(0)
     model = getattr(archs, arch)(classes, 3, ds).to(dev)
     crit = losses.BCEDiceLoss()
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    opt = noptim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
     x = torch.randn(n, 3, size, size, device=dev) * 0.01
     t = (torch.rand(n, classes, size, size, device=dev) > 0.5).float()
 
