@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--size", type=int, default=96)
     ap.add_argument("--arch", default="NestedUNet")
     ap.add_argument("--no-ds", action="store_true")
+    ap.add_argument("--classes", type=int, default=1, help="num_classes (BASELINE config 4: 4); the CPU legs run the 1-class reference step only")
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="also write profiles/layers_latest.json")
@@ -226,7 +227,7 @@ def run_native(args):
     import ops
     ds = not args.no_ds
     torch.manual_seed(0)
-    model = getattr(archs, args.arch)(1, 3, ds).to(dev)
+    model = getattr(archs, args.arch)(args.classes, 3, ds).to(dev)
     crit = losses.BCEDiceLoss().to(dev)
     if world > 1:
         import dist as nunet_dist
@@ -239,7 +240,7 @@ def run_native(args):
     # HWC->CHW transposes (dataset.py:72-74) — runs on the GPU (ops.input_u8 / ops.mask_u8), so a step ships 4x fewer bytes.
     g = torch.Generator().manual_seed(1 + rank)
     x_host = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory()
-    t_host = ((torch.rand(B, S, S, 1, generator=g) > 0.5).to(torch.uint8) * 255).pin_memory()
+    t_host = ((torch.rand(B, S, S, args.classes, generator=g) > 0.5).to(torch.uint8) * 255).pin_memory()
     x_dev, t_dev = x_host.to(dev), ops.mask_u8(t_host.to(dev))
 
     def step(x, t):
@@ -348,7 +349,7 @@ def run_native(args):
         total_ms = sum(timing["by_class"].values())
         _, train_fl = conv_flops_per_image(args.arch, S)
         tflops = train_fl * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        net = network_roofline(args.arch, S, B, ds, pk)
+        net = network_roofline(args.arch, S, B, ds, pk, num_classes=args.classes)
         step_ms = ms / args.steps
         # the dominant kernel: the generic tcgen05 implicit-GEMM conv (forward of the non-stacked layers + every dgrad)
         dom = [r for r in timing["launches"] if r["class"] in ("conv_fwd", "conv_dgrad") and r["meta"] and r["meta"][-1] == "igemm"]
@@ -392,7 +393,7 @@ def run_native(args):
                 json.dump({"batch": B, "size": S, "arch": args.arch, "launches": layer_rows}, f, indent=1)
     cpu = None
     numerics = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.classes == 1:
         rate, med, cores, first = cpu_reference_step_rate(args.arch, ds, 16, S, 3, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle port of the reference train step, %s ds=%s batch 16 @%dx%d fp32, median of 3 steps (%.2f s/step)" % (args.arch, ds, S, S, med)}
@@ -412,8 +413,8 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_run": warm_run,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "%s(num_classes=1, input_channels=3, deep_supervision=%s) %dx%d, batch %d per GPU, full train step "
-                                   "(fwd + BCEDice + IoU + bwd + SGD)" % (args.arch, ds, S, S, B),
+            "config": {"workload": "%s(num_classes=%d, input_channels=3, deep_supervision=%s) %dx%d, batch %d per GPU, full train step "
+                                   "(fwd + BCEDice + IoU + bwd + SGD)" % (args.arch, args.classes, ds, S, S, B),
                        "global_batch": B * world, "parallelism": "dp%d%s" % (world, "" if world == 1 else ("+syncbn" if not args.no_sync_bn else "")),
                        "l2": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size() + t_host.numel() * t_host.element_size()) * world,
