@@ -10,6 +10,21 @@ import torch
 import ops
 
 
+def iou_counts_device(output, target):
+    """(intersection, union) as an int64[2] tensor ON THE DEVICE — no host synchronisation (utils.StepScalars reads it one step
+    late).  The counts BCEDiceLoss cached for this (output, target) pair are reused; otherwise one counting launch."""
+    cached = getattr(output, "__dict__", {}).get("_nunet_iou") if torch.is_tensor(output) else None
+    if cached is not None and torch.is_tensor(target) and cached[0] == target.data_ptr() and cached[1] == target._version \
+            and cached[2] == output._version:
+        return cached[3]
+    ops.require_cuda(output, "iou_counts_device output")
+    o = output.detach().to(dtype=torch.float32).contiguous()
+    t = target.detach().to(device=o.device, dtype=torch.float32).contiguous()
+    if o.shape != t.shape:
+        raise ValueError("output and target must have the same shape")
+    return ops.iou_counts(o, t)
+
+
 def iou_counts(output, target):
     """(intersection, union) as Python ints over the whole batch and all classes (metrics.py:13-16)."""
     cached = getattr(output, "__dict__", {}).get("_nunet_iou") if torch.is_tensor(output) else None

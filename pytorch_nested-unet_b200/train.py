@@ -23,8 +23,8 @@ from torch.optim import lr_scheduler
 
 import archs
 import losses
-from metrics import iou_score
-from utils import AverageMeter, device_target, str2bool
+from metrics import iou_counts_device, iou_score
+from utils import AverageMeter, DevicePrefetcher, StepScalars, device_target, str2bool
 
 ARCH_NAMES = archs.__all__
 LOSS_NAMES = losses.__all__ + ['BCEWithLogitsLoss']      # trains.py:27-28
@@ -99,35 +99,43 @@ def _global_mean(value, device):
     return value
 
 
-def _loss_and_iou(config, model, criterion, input, target):
-    """trains.py:117-127."""
+def _loss_and_iou(config, model, criterion, input, target, on_device=False):
+    """trains.py:117-127.  on_device: the IoU is returned as its two integer counts on the device (no host synchronisation)."""
+    iou_fn = iou_counts_device if on_device else _iou
     if config['deep_supervision']:
         outputs = model(input)
         loss = 0
         for output in outputs:
             loss += criterion(output, target)
         loss /= len(outputs)
-        iou = _iou(outputs[-1], target)
+        iou = iou_fn(outputs[-1], target)
     else:
         output = model(input)
         loss = criterion(output, target)
-        iou = _iou(output, target)
+        iou = iou_fn(output, target)
     return loss, iou
 
 
 def train(config, train_loader, model, criterion, optimizer):
-    """trains.py:106-147."""
+    """trains.py:106-147.  The scalars of a step (trains.py:124,133-134) are read through utils.StepScalars: their device->host copy is
+    issued before backward is enqueued and waited for after the optimizer step has been enqueued, so the CPU never waits for more than
+    the forward pass and the GPU never runs dry; the meters see the same values in the same iteration."""
     avg_meters = {'loss': AverageMeter(), 'iou': AverageMeter()}
     model.train()
-    for input, target, _ in train_loader:
+    scalars = StepScalars(reduce=True)
+    # DevicePrefetcher: the host->device copy of batch i+1 is issued on a copy stream when batch i is handed out (trains.py:113-114
+    # copies synchronously on the compute stream); the .cuda() calls below are then no-ops
+    for input, target, _ in DevicePrefetcher(train_loader):
         input = input.cuda(non_blocking=True)
         target = device_target(target.cuda(non_blocking=True))
-        loss, iou = _loss_and_iou(config, model, criterion, input, target)
+        loss, counts = _loss_and_iou(config, model, criterion, input, target, on_device=True)
+        scalars.submit(loss, counts)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
-        avg_meters['loss'].update(_global_mean(loss.item(), input.device), input.size(0))
-        avg_meters['iou'].update(iou, input.size(0))
+        for lv, i_, u_ in scalars.collect():
+            avg_meters['loss'].update(lv, input.size(0))
+            avg_meters['iou'].update((i_ + 1e-5) / (u_ + 1e-5), input.size(0))      # metrics.py:17-18
     return OrderedDict([('loss', avg_meters['loss'].avg), ('iou', avg_meters['iou'].avg)])
 
 

@@ -91,3 +91,38 @@ def test_eval_graphs_of_different_shapes_do_not_share_weight_images():
         m(xb)
         a3 = m(xa).clone()
     assert torch.equal(a1, a2) and torch.equal(a1, a3)
+
+
+def test_step_scalars_and_prefetcher_give_the_synchronous_loop_values():
+    """utils.StepScalars / utils.DevicePrefetcher (train.train's loop): the scalars collected after the step equal loss.item() and
+    metrics.iou_score of the same step, batches arrive unchanged and in order, keep=k leaves k submissions in flight."""
+    import archs
+    import losses
+    import metrics
+    import utils
+    torch.manual_seed(5)
+    model = archs.NestedUNet(1, 3, True).to(DEV).train()
+    crit = losses.BCEDiceLoss()
+    g = torch.Generator().manual_seed(2)
+    host = [((torch.randn(2, 3, 32, 32, generator=g) * 0.01).pin_memory(), (torch.rand(2, 1, 32, 32, generator=g) > 0.5).float().pin_memory(), {"i": k})
+            for k in range(4)]
+    scal = utils.StepScalars()
+    seen = []
+    for k, (x, t, meta) in enumerate(utils.DevicePrefetcher(iter(host), DEV)):
+        assert meta["i"] == k and x.is_cuda and torch.equal(x.cpu(), host[k][0]) and torch.equal(t.cpu(), host[k][1])
+        outs = model(x)
+        loss = sum(crit(o, t) for o in outs) / len(outs)
+        counts = metrics.iou_counts_device(outs[-1], t)
+        scal.submit(loss, counts)
+        loss.backward()
+        got = scal.collect(keep=1 if k < 2 else 0)
+        seen += got
+        ref_iou = metrics.iou_score(outs[-1], t)
+        if k == 3:
+            lv, i_, u_ = got[-1]
+            assert abs(lv - loss.item()) == 0.0 and abs((i_ + 1e-5) / (u_ + 1e-5) - ref_iou) == 0.0
+    assert len(seen) == 4 and not scal.slots
+    # counts without the loss cache: one counting launch, same integers
+    o = torch.randn(2, 1, 16, 16, device=DEV)
+    t = (torch.rand(2, 1, 16, 16, device=DEV) > 0.5).float()
+    assert tuple(metrics.iou_counts_device(o, t).tolist()) == metrics.iou_counts(o, t)
