@@ -219,6 +219,15 @@ int nunet_sigmoid_u8(const float* logits, long long total, uint8_t* out, void* s
 /* dlogits = (gscale ? *gscale : 1) * gmul * d(loss)/d(logits). */
 int nunet_loss_bwd(const float* logits, const float* target, const double* sums, const float* gscale, float gmul, int32_t N,
                    int32_t E, float* dlogits, void* stream);
+/* The deep-supervision loop (trains.py:120-123: `for output in outputs: loss += criterion(output, target)`) in ONE pass: nheads <= 4
+ * logit tensors of the same shape against the same target.  logits / gscale / dlogits are HOST arrays of nheads device pointers.
+ * part: [nheads][N][bps][4], cnt: [nheads][N][bps][2], sums: [nheads][N][3], loss: [nheads], counts: [nheads][2]; every head's
+ * results are bitwise those of nunet_loss_iou_fwd / nunet_loss_bwd on that head alone.  bwd: gscale[k] NULL = 1, dlogits[k] NULL =
+ * head k's loss received no gradient (nothing is written for it). */
+int nunet_loss_iou_fwd_multi(const float* const* logits, int32_t nheads, const float* target, int32_t N, int32_t E, float* part,
+                             int32_t* cnt, double* sums, float* loss, long long* counts, void* stream);
+int nunet_loss_bwd_multi(const float* const* logits, int32_t nheads, const float* target, const double* sums,
+                         const float* const* gscale, float gmul, int32_t N, int32_t E, float* const* dlogits, void* stream);
 /* LovaszHingeLoss (losses.py:49-96,120-129; csrc/lovasz.cu): logits / target [N][P] fp32 (P = C*H*W of one image, target in {0,1});
  * per image a descending sort of the hinge errors, the Jaccard gradient of the sorted labels, loss = mean_n dot(relu(e_sorted), grad).
  * coef [N][P]: d loss_image / d logit (kept for the backward pass); loss_img [N] fp64; loss: fp32 scalar.  scratch:

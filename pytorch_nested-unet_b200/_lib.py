@@ -107,6 +107,8 @@ _SIGS = {
     "nunet_loss_iou_fwd": ([C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6, C.c_int),
     "nunet_iou_counts": ([C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_loss_bwd": ([C.c_void_p] * 4 + [C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
+    "nunet_loss_iou_fwd_multi": ([C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6, C.c_int),
+    "nunet_loss_bwd_multi": ([C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p], C.c_int),
     "nunet_head_bwd_params_rows": ([], C.c_int),
     "nunet_head_bwd_params": ([C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p], C.c_int),
     "nunet_grad_router_rows": ([C.c_int32] * 4, C.c_int),

@@ -170,6 +170,137 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------- all deep-supervision heads at once
+// trains.py:120-123 calls the criterion once per head ON THE SAME TARGET: here the NH heads share one pass (the target is read once,
+// one launch instead of NH) with exactly the per-head thread -> element mapping and reduction order of the kernels above, so every
+// head's partial sums, loss, counts and gradient are bitwise those of the single-head launches.
+constexpr int kMaxHeads = 4;
+struct LossHeads {
+    const float* logits[kMaxHeads];
+    const float* gscale[kMaxHeads];   // backward: upstream gradient of head h's loss (device scalar) or nullptr (= 1)
+    float* dlogits[kMaxHeads];        // backward: nullptr = this head's loss received no gradient
+};
+
+// part: [NH][N][BPS][4], cnt: [NH][N][BPS][2]
+template <int NH>
+__global__ void __launch_bounds__(256) loss_iou_partial_multi_kernel(const LossHeads h, const float* __restrict__ target, int E,
+                                                                     float* __restrict__ part, int* __restrict__ cnt) {
+    const int n = blockIdx.y, N = gridDim.y;
+    const float* t = target + (size_t)n * E;
+    float bce[NH], pt[NH], ps[NH], ts[NH];
+    int I[NH], U[NH];
+#pragma unroll
+    for (int k = 0; k < NH; ++k) { bce[k] = 0.f; pt[k] = 0.f; ps[k] = 0.f; ts[k] = 0.f; I[k] = 0; U[k] = 0; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E; i += gridDim.x * blockDim.x) {
+        const float tv = t[i];
+        const bool t_ = tv > 0.5f;
+#pragma unroll
+        for (int k = 0; k < NH; ++k) {
+            const float xv = h.logits[k][(size_t)n * E + i];
+            const float p = sigmoid_f32(xv);
+            bce[k] += fmaxf(xv, 0.f) - xv * tv + log1pf(expf(-fabsf(xv)));
+            pt[k] = fmaf(p, tv, pt[k]);
+            ps[k] += p;
+            ts[k] += tv;
+            const bool o_ = p > 0.5f;
+            I[k] += (o_ && t_);
+            U[k] += (o_ || t_);
+        }
+    }
+    __shared__ float sf[NH][8][4];
+    __shared__ int si[NH][8][2];
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        const float a = warp_sum(bce[k]), b = warp_sum(pt[k]), c = warp_sum(ps[k]), d = warp_sum(ts[k]);
+        const int ii = warp_sum_i(I[k]), uu = warp_sum_i(U[k]);
+        if ((threadIdx.x & 31) == 0) { sf[k][w][0] = a; sf[k][w][1] = b; sf[k][w][2] = c; sf[k][w][3] = d; si[k][w][0] = ii; si[k][w][1] = uu; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 * NH) {
+        const int k = threadIdx.x / 6, j = threadIdx.x - 6 * k;
+        const size_t blk = ((size_t)k * N + n) * gridDim.x + blockIdx.x;
+        if (j < 4) {
+            float a = 0.f;
+            for (int i = 0; i < 8; ++i) a += sf[k][i][j];
+            part[blk * 4 + j] = a;
+        } else {
+            int a = 0;
+            for (int i = 0; i < 8; ++i) a += si[k][i][j - 4];
+            cnt[blk * 2 + j - 4] = a;
+        }
+    }
+}
+
+// block k finishes head k: sums [NH][N][3], loss [NH], counts [NH][2]
+__global__ void __launch_bounds__(256) loss_iou_finalize_multi_kernel(const float* __restrict__ part, const int* __restrict__ cnt, int N,
+                                                                      int BPS, int E, double* __restrict__ sums, float* __restrict__ loss,
+                                                                      long long* __restrict__ counts) {
+    const int k = blockIdx.x;
+    part += (size_t)k * N * BPS * 4;
+    cnt += (size_t)k * N * BPS * 2;
+    sums += (size_t)k * N * 3;
+    __shared__ double s_bce[256], s_dice[256];
+    __shared__ long long s_I[256], s_U[256];
+    double bce = 0.0, dice = 0.0;
+    long long I = 0, U = 0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        double b = 0, pt = 0, ps = 0, ts = 0;
+        for (int q_ = 0; q_ < BPS; ++q_) {
+            const float* q = part + ((size_t)n * BPS + q_) * 4;
+            b += q[0]; pt += q[1]; ps += q[2]; ts += q[3];
+            I += cnt[((size_t)n * BPS + q_) * 2];
+            U += cnt[((size_t)n * BPS + q_) * 2 + 1];
+        }
+        bce += b;
+        const double smooth = 1e-5;
+        dice += (2.0 * pt + smooth) / (ps + ts + smooth);
+        sums[n * 3 + 0] = pt; sums[n * 3 + 1] = ps; sums[n * 3 + 2] = ts;
+    }
+    s_bce[threadIdx.x] = bce; s_dice[threadIdx.x] = dice; s_I[threadIdx.x] = I; s_U[threadIdx.x] = U;
+    __syncthreads();
+    for (int o = 128; o >= 1; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_bce[threadIdx.x] += s_bce[threadIdx.x + o]; s_dice[threadIdx.x] += s_dice[threadIdx.x + o];
+            s_I[threadIdx.x] += s_I[threadIdx.x + o]; s_U[threadIdx.x] += s_U[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        loss[k] = (float)(0.5 * s_bce[0] / ((double)N * E) + (1.0 - s_dice[0] / N));
+        counts[2 * k] = s_I[0];
+        counts[2 * k + 1] = s_U[0];
+    }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(256) loss_bwd_multi_kernel(const LossHeads h, const float* __restrict__ target,
+                                                             const double* __restrict__ sums, float gmul, int N, int E) {
+    const int n = blockIdx.y;
+    const double smooth = 1e-5;
+    const float c_bce = 0.5f / ((float)N * (float)E);
+    float g[NH], a_t[NH], a_0[NH];
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        const double* sm = sums + ((size_t)k * N + n) * 3;
+        const double pt = sm[0], ps = sm[1], ts = sm[2];
+        const double den = ps + ts + smooth, num = 2.0 * pt + smooth;
+        g[k] = (h.gscale[k] ? *h.gscale[k] : 1.f) * gmul;
+        a_t[k] = (float)(-2.0 / (den * N));
+        a_0[k] = (float)(num / (den * den * N));
+    }
+    const float* t = target + (size_t)n * E;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E; i += gridDim.x * blockDim.x) {
+        const float tv = t[i];
+#pragma unroll
+        for (int k = 0; k < NH; ++k) {
+            if (h.dlogits[k] == nullptr) continue;
+            const float p = sigmoid_f32(h.logits[k][(size_t)n * E + i]);
+            h.dlogits[k][(size_t)n * E + i] = g[k] * (c_bce * (p - tv) + (a_t[k] * tv + a_0[k]) * p * (1.f - p));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- head parameter grads
 // dWh[k][c] = sum_pix dlogit[n,k,pix] * a[pix,c] ; dbh[k] = sum dlogit.  part: [gridDim.x][K][33]
 template <int KT>
@@ -320,6 +451,49 @@ extern "C" int nunet_loss_bwd(const float* logits, const float* target, const do
     if (!logits || !target || !sums || !dlogits || N < 1 || E < 1) return NUNET_E_BADARG;
     const int bps = nunet_loss_blocks_per_sample(N, E);
     loss_bwd_kernel<<<dim3(bps, N), 256, 0, (cudaStream_t)stream>>>(logits, target, sums, gscale, gmul, N, E, dlogits);
+    return cuda_rc();
+}
+
+extern "C" int nunet_loss_iou_fwd_multi(const float* const* logits, int32_t nheads, const float* target, int32_t N, int32_t E, float* part,
+                                        int32_t* cnt, double* sums, float* loss, long long* counts, void* stream) {
+    if (!logits || nheads < 1 || nheads > kMaxHeads || !target || !part || !cnt || !sums || !loss || !counts || N < 1 || E < 1) return NUNET_E_BADARG;
+    LossHeads h{};
+    for (int k = 0; k < nheads; ++k) {
+        if (!logits[k]) return NUNET_E_BADARG;
+        h.logits[k] = logits[k];
+    }
+    const int bps = nunet_loss_blocks_per_sample(N, E);
+    const dim3 grid(bps, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nheads) {
+        case 1: loss_iou_partial_multi_kernel<1><<<grid, 256, 0, st>>>(h, target, E, part, cnt); break;
+        case 2: loss_iou_partial_multi_kernel<2><<<grid, 256, 0, st>>>(h, target, E, part, cnt); break;
+        case 3: loss_iou_partial_multi_kernel<3><<<grid, 256, 0, st>>>(h, target, E, part, cnt); break;
+        default: loss_iou_partial_multi_kernel<4><<<grid, 256, 0, st>>>(h, target, E, part, cnt); break;
+    }
+    loss_iou_finalize_multi_kernel<<<nheads, 256, 0, st>>>(part, cnt, N, bps, E, sums, loss, counts);
+    return cuda_rc();
+}
+
+extern "C" int nunet_loss_bwd_multi(const float* const* logits, int32_t nheads, const float* target, const double* sums,
+                                    const float* const* gscale, float gmul, int32_t N, int32_t E, float* const* dlogits, void* stream) {
+    if (!logits || nheads < 1 || nheads > kMaxHeads || !target || !sums || !dlogits || N < 1 || E < 1) return NUNET_E_BADARG;
+    LossHeads h{};
+    for (int k = 0; k < nheads; ++k) {
+        if (!logits[k]) return NUNET_E_BADARG;
+        h.logits[k] = logits[k];
+        h.gscale[k] = gscale ? gscale[k] : nullptr;
+        h.dlogits[k] = dlogits[k];
+    }
+    const int bps = nunet_loss_blocks_per_sample(N, E);
+    const dim3 grid(bps, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nheads) {
+        case 1: loss_bwd_multi_kernel<1><<<grid, 256, 0, st>>>(h, target, sums, gmul, N, E); break;
+        case 2: loss_bwd_multi_kernel<2><<<grid, 256, 0, st>>>(h, target, sums, gmul, N, E); break;
+        case 3: loss_bwd_multi_kernel<3><<<grid, 256, 0, st>>>(h, target, sums, gmul, N, E); break;
+        default: loss_bwd_multi_kernel<4><<<grid, 256, 0, st>>>(h, target, sums, gmul, N, E); break;
+    }
     return cuda_rc();
 }
 

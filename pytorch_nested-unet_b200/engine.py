@@ -1116,7 +1116,7 @@ def run_model(model, x):
         else:
             with torch.no_grad():
                 outs, _ = _forward_check(model, x, model.training)
-        return list(outs) if model._returns_list else outs[0]
+        return list(outs) if model._returns_list else outs[0]     # check mode: the per-head loss launches (its own reference path)
     if need_grad:
         outs = _NetFunction.apply(model, x, *params)
     elif (GRAPH_EVAL and not model.training and torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.uint8)
@@ -1127,5 +1127,6 @@ def run_model(model, x):
             _, _, logits = _forward(model, x, model.training)
         outs = tuple(t for _, t in logits)
     if model._returns_list:
-        return list(outs)
+        import losses
+        return losses.mark_head_group(list(outs))     # BCEDiceLoss then evaluates all heads in one launch (losses._group_loss)
     return outs[0]

@@ -29,6 +29,62 @@ class _BCEDiceFunction(torch.autograd.Function):
         return ops.loss_bwd(logits, target, sums, g), None
 
 
+class _BCEDiceGroupFunction(torch.autograd.Function):
+    """The criterion of ALL deep-supervision heads against one target (trains.py:120-123) as one node: one reduction pass forward
+    (the target is read once), one launch backward for every head whose loss took part in the total."""
+
+    @staticmethod
+    def forward(ctx, target, *logits):
+        loss, sums, counts = ops.loss_iou_fwd_multi(list(logits), target)
+        ctx.save_for_backward(target, sums, *logits)
+        ctx.counts = counts
+        return tuple(loss[k] for k in range(len(logits)))
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        target, sums = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        logits = list(ctx.saved_tensors[2:])
+        gs = [None if g is None else g.contiguous().float() for g in grad_outs]
+        return (None,) + tuple(ops.loss_bwd_multi(logits, target, sums, gs))
+
+
+def mark_head_group(outputs):
+    """Called by the engine on the list of deep-supervision logits it returns: BCEDiceLoss evaluates the whole group on the first
+    head it is given (one launch for all of them) and hands the other heads their cached value when the loop reaches them."""
+    group = {"tensors": list(outputs), "key": None, "losses": None}
+    for k, o in enumerate(outputs):
+        o.__dict__["_nunet_head_group"] = (group, k)
+    return outputs
+
+
+def _group_loss(input, target, t):
+    """The cached / freshly evaluated group loss of `input`, or None when `input` is not a marked head or the group does not qualify."""
+    tag = input.__dict__.get("_nunet_head_group")
+    if tag is None:
+        return None
+    group, k = tag
+    heads = group["tensors"]
+    if not (1 < len(heads) <= ops.MAX_LOSS_HEADS) or heads[k] is not input:
+        return None
+    key = (target.data_ptr(), target._version, tuple(h._version for h in heads), torch.is_grad_enabled())
+    if group["key"] != key:
+        ref = heads[0]
+        if not all(h.is_cuda and h.dtype == torch.float32 and h.is_contiguous() and h.shape == ref.shape and h.requires_grad == ref.requires_grad
+                   for h in heads):
+            return None
+        if ref.requires_grad and torch.is_grad_enabled():
+            losses = _BCEDiceGroupFunction.apply(t, *heads)
+            counts = losses[0].grad_fn.counts if losses[0].grad_fn is not None and hasattr(losses[0].grad_fn, "counts") else None
+        else:
+            lv, _, counts = ops.loss_iou_fwd_multi([h.detach() for h in heads], t)
+            losses = tuple(lv[j] for j in range(len(heads)))
+        if counts is not None:
+            for j, h in enumerate(heads):
+                h.__dict__["_nunet_iou"] = (target.data_ptr(), target._version, h._version, counts[j])
+        group["key"], group["losses"] = key, losses
+    return group["losses"][k]
+
+
 class BCEDiceLoss(nn.Module):
     def __init__(self):
         super().__init__()
@@ -40,6 +96,10 @@ class BCEDiceLoss(nn.Module):
         x = input if (input.dtype == torch.float32 and input.is_contiguous()) else input.float().contiguous()
         t = target.detach()
         t = t if (t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda) else t.to(device=x.device, dtype=torch.float32).contiguous()
+        if x is input:
+            grouped = _group_loss(input, target, t)
+            if grouped is not None:
+                return grouped
         if x.requires_grad and torch.is_grad_enabled():
             fn_out = _BCEDiceFunction.apply(x, t)
             counts = fn_out.grad_fn.counts if fn_out.grad_fn is not None and hasattr(fn_out.grad_fn, "counts") else None

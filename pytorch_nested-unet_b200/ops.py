@@ -412,6 +412,50 @@ def loss_bwd(logits, target, sums, gscale, gmul=1.0, dlogits=None):
     return dlogits
 
 
+MAX_LOSS_HEADS = 4
+
+
+def _ptr_array(tensors):
+    """Host array of device pointers (None -> NULL) for the *_multi entry points."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def loss_iou_fwd_multi(logits_list, target):
+    """BCEDice + IoU counts of nheads <= 4 logit tensors against ONE target in one pass (two launches instead of 2 * nheads).
+    Returns (loss [nheads] fp32, sums [nheads,N,3] fp64, counts [nheads,2] int64); bitwise loss_iou_fwd per head."""
+    nh = len(logits_list)
+    N = logits_list[0].shape[0]
+    E = logits_list[0].numel() // N
+    bps = L.lib().nunet_loss_blocks_per_sample(N, E)
+    dev = logits_list[0].device
+    part = torch.empty((nh, N, bps, 4), dtype=torch.float32, device=dev)
+    cnt = torch.empty((nh, N, bps, 2), dtype=torch.int32, device=dev)
+    sums = torch.empty((nh, N, 3), dtype=torch.float64, device=dev)
+    loss = torch.empty(nh, dtype=torch.float32, device=dev)
+    counts = torch.empty((nh, 2), dtype=torch.int64, device=dev)
+    arr = _ptr_array(logits_list)
+    _call("loss_fwd", 2, None, "nunet_loss_iou_fwd_multi", L.lib().nunet_loss_iou_fwd_multi, arr, nh, _ptr(target), N, E, _ptr(part), _ptr(cnt), _ptr(sums),
+          _ptr(loss), _ptr(counts), _stream())
+    return loss, sums, counts
+
+
+def loss_bwd_multi(logits_list, target, sums, gscales, gmul=1.0):
+    """dlogits of every head whose loss received a gradient (gscales[k] is its 0-dim upstream gradient, None = no gradient) in one
+    launch; returns a list with None for the heads without gradient."""
+    nh = len(logits_list)
+    N = logits_list[0].shape[0]
+    E = logits_list[0].numel() // N
+    outs = [torch.empty_like(l) if g is not None else None for l, g in zip(logits_list, gscales)]
+    if all(o is None for o in outs):
+        return outs
+    la, ga, da = _ptr_array(logits_list), _ptr_array(gscales), _ptr_array(outs)
+    _call("loss_bwd", 1, None, "nunet_loss_bwd_multi", L.lib().nunet_loss_bwd_multi, la, nh, _ptr(target), _ptr(sums), ga, float(gmul), N, E, da, _stream())
+    return outs
+
+
 def head_bwd_params(y, scale, shift, dlogits, N, H, W, K, dwh=None, dbh=None):
     dev = y.device
     rows = L.lib().nunet_head_bwd_params_rows()

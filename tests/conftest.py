@@ -12,6 +12,11 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # GPU oracle settings: torch references in the tests are exact fp32 — no TF32 in cuDNN / cuBLAS, whatever order
+    # the test files run in
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -94,3 +94,60 @@ def test_lovasz_hinge_loss_matches_reference_golden(name):
     assert int(bad.sum()) <= 2, int(bad.sum())
     with torch.no_grad():
         assert abs(float(losses.LovaszHingeLoss()(x.detach(), t)) - g["loss"]) <= 2e-6 * max(1.0, abs(g["loss"]))
+
+
+@pytest.mark.parametrize("nh,K", [(4, 1), (2, 4), (3, 1)])
+def test_multi_head_loss_is_bitwise_the_per_head_launches(nh, K):
+    """nunet_loss_iou_fwd_multi / nunet_loss_bwd_multi (the deep-supervision loop of trains.py:120-123 in one pass) against
+    nunet_loss_iou_fwd / nunet_loss_bwd head by head: identical bits, including a head whose loss received no gradient."""
+    import ops
+    gen = torch.Generator(device=DEV).manual_seed(10 + nh)
+    xs = [torch.randn(5, K, 40, 56, generator=gen, device=DEV) * (1 + k) for k in range(nh)]
+    xs[0].view(-1)[::7] = 0.0
+    t = (torch.rand(5, K, 40, 56, generator=gen, device=DEV) > 0.5).float()
+    loss, sums, counts = ops.loss_iou_fwd_multi(xs, t)
+    gs = [torch.tensor(0.25 * (k + 1), device=DEV) for k in range(nh)]
+    gs[1] = None
+    dls = ops.loss_bwd_multi(xs, t, sums, gs, 0.5)
+    assert dls[1] is None
+    for k in range(nh):
+        l1, s1, c1 = ops.loss_iou_fwd(xs[k], t)
+        assert torch.equal(l1, loss[k]) and torch.equal(s1, sums[k]) and torch.equal(c1, counts[k])
+        if gs[k] is not None:
+            assert torch.equal(ops.loss_bwd(xs[k], t, s1, gs[k], 0.5), dls[k])
+
+
+def test_grouped_criterion_matches_the_per_head_criterion():
+    """losses.BCEDiceLoss on a marked group of heads (what NestedUNet(deep_supervision=True) returns): same losses, same cached IoU
+    counts, same input gradients as calling it head by head on unmarked tensors; a partial loop and a second target still work."""
+    import losses
+    import metrics
+    crit = losses.BCEDiceLoss()
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    base = [torch.randn(4, 1, 32, 32, generator=gen, device=DEV) for _ in range(4)]
+    t = (torch.rand(4, 1, 32, 32, generator=gen, device=DEV) > 0.5).float()
+    t2 = (torch.rand(4, 1, 32, 32, generator=gen, device=DEV) > 0.5).float()
+    a = [b.clone().requires_grad_(True) for b in base]
+    r = [b.clone().requires_grad_(True) for b in base]
+    heads = losses.mark_head_group([x * 1.0 for x in a])          # non-leaf tensors, as the engine's outputs are
+    la = [crit(h, t) for h in heads]
+    lr = [crit(x * 1.0, t) for x in r]
+    for k in range(4):
+        assert torch.equal(la[k].detach(), lr[k].detach())
+        assert metrics.iou_counts(heads[k], t) == metrics.iou_counts(r[k].detach(), t)
+    (sum(la) / 4).backward()
+    (sum(lr) / 4).backward()
+    for k in range(4):
+        assert torch.equal(a[k].grad, r[k].grad)
+    # only two of the heads enter the total; another target re-evaluates the group
+    for x in a:
+        x.grad = None
+    heads = losses.mark_head_group([x * 1.0 for x in a])
+    tot = crit(heads[0], t2) + crit(heads[3], t2)
+    tot.backward()
+    ref0 = base[0].clone().requires_grad_(True)
+    crit(ref0 * 1.0, t2).backward()
+    assert torch.equal(a[0].grad, ref0.grad) and float(a[1].grad.abs().max()) == 0.0 and float(a[3].grad.abs().max()) > 0.0
+    with torch.no_grad():
+        heads = losses.mark_head_group([b.clone() for b in base])
+        assert torch.equal(crit(heads[2], t), lr[2].detach())
