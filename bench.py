@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="also write profiles/layers_latest.json")
+    ap.add_argument("--e2e-loop", default="overlap", choices=["overlap", "sync"],
+                    help="overlap: train.train()'s loop (prefetcher + StepScalars); sync: copy on the compute stream and host reads after the step (A/B)")
     ap.add_argument("--kernels-only", action="store_true", help="profiler runs (ncu): only the warm-up and the timed device-resident steps")
     return ap.parse_args()
 
@@ -127,23 +129,61 @@ def network_roofline(arch, size, batch, ds, peaks_, num_classes=1, input_channel
     return out
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+class ClockSampler(object):
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md's clocks line): ONE `nvidia-smi -lms 200` process,
+    started by rank 0 only and before the warm-up, so that its start-up (NVML attaches to every GPU of the box under a driver-wide
+    lock) is over when the timing starts; its rows are filtered to the timed window by their own timestamps.  (Spawning a fresh
+    nvidia-smi every 200 ms from every rank, as this bench first did, cost the 2-GPU run an occasional 25 ms stall: 14.5 vs 15.8
+    ms/step between otherwise identical runs.)"""
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index, enabled=True):
+        self.proc, self.t0, self.t1, self.rows = None, None, None, []
+        if enabled:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                import tempfile
+                self.out = tempfile.TemporaryFile(mode="w+")
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=self.out, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def stop(self):
+        self.t1 = time.time()
+        if self.proc is None:
+            return
+        out = ""
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            try:
+                self.proc.kill()
             except Exception:
                 pass
-            time.sleep(0.2)
+        try:
+            self.out.seek(0)
+            out = self.out.read()
+            self.out.close()
+        except Exception:
+            pass
+        self.proc = None
+        import datetime
+        for line in out.splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            if self.t0 is not None and self.t0 <= ts <= self.t1:
+                self.rows.append(c[1:])
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -275,11 +315,14 @@ def run_native(args):
     model.train()
     # at least three untimed steps: the first runs eagerly, the second captures the CUDA graphs of the step, the third replays
     warm_run = max(args.warmup, 3)
+    sampler = ClockSampler(local, enabled=(rank == 0 and not os.environ.get("NUNET_NO_CLOCKS")))      # started before the warm-up, see the class
     for _ in range(warm_run):
         step(x_dev, t_dev)
+    import utils
+    if not os.environ.get("NUNET_NO_GC_FREEZE"):
+        utils.settle_gc()            # what train.train() does after its third step (a 70 ms generation-2 collection otherwise lands in a timed step)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_start()
     ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -290,8 +333,7 @@ def run_native(args):
     launches = ops.launch_count()
     ms = e0.elapsed_time(e1)
     if args.kernels_only:
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
+        sampler.stop()
         if rank == 0:
             print(json.dumps({"kernels_only": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
         if world > 1:
@@ -301,7 +343,6 @@ def run_native(args):
     #      memory through utils.DevicePrefetcher (the copy of batch i+1 is issued on a copy stream when batch i is handed out), and the
     #      step's loss and IoU counts are copied to the host every step and read there in the same iteration through
     #      utils.StepScalars (copy issued before backward is enqueued, waited for after the optimizer step is enqueued).
-    import utils
 
     class HostBatches(object):            # the loader: `n` pinned host batches per pass
         n = 4
@@ -313,21 +354,54 @@ def run_native(args):
     batches = HostBatches()
     loader = utils.DevicePrefetcher(batches, dev)
     scal = utils.StepScalars()
-    for xb, tb, _ in loader:              # untimed: the ring buffers, pinned result slots and events are created here
-        step(xb, ops.mask_u8(tb), scal)
-        scal.collect()
-    barrier()
-    batches.n = args.steps
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for xb, tb, _ in loader:
-        loss, counts = step(xb, ops.mask_u8(tb), scal)
-        (lv, i_, u_), = scal.collect()
-        iou = (i_ + 1e-5) / (u_ + 1e-5)
+    if not os.environ.get("NUNET_NO_GC_FREEZE"):
+        utils.settle_gc(again=True)
+    if args.e2e_loop == "sync":           # A/B: the reference's own placement (copy on the compute stream, host reads after the step)
+        for _ in range(2):
+            step(x_host.to(dev, non_blocking=True), ops.mask_u8(t_host.to(dev, non_blocking=True)))
+        barrier()
+        f0.record()
+        for _ in range(args.steps):
+            loss, counts = step(x_host.to(dev, non_blocking=True), ops.mask_u8(t_host.to(dev, non_blocking=True)))
+            lv = loss.item()
+            i_, u_ = counts.tolist()
+            iou = (i_ + 1e-5) / (u_ + 1e-5)
+    else:
+        for xb, tb, _ in loader:          # untimed: the ring buffers, pinned result slots and events are created here
+            step(xb, ops.mask_u8(tb), scal)
+            scal.collect()
+        barrier()
+        batches.n = args.steps
+        import gc
+        if os.environ.get("NUNET_E2E_TRACE"):
+            gc_t = {}
+
+            def gc_cb(phase, info):
+                if phase == "start":
+                    gc_t["t"] = time.perf_counter()
+                else:
+                    dt = (time.perf_counter() - gc_t.get("t", time.perf_counter())) * 1e3
+                    if dt > 1.0:
+                        print("rank %d gc gen%d %.1f ms collected %d" % (rank, info["generation"], dt, info["collected"]), file=sys.stderr)
+            gc.callbacks.append(gc_cb)
+        f0.record()
+        trace = [] if os.environ.get("NUNET_E2E_TRACE") else None
+        for xb, tb, _ in loader:
+            loss, counts = step(xb, ops.mask_u8(tb), scal)
+            if trace is not None:
+                trace.append(time.perf_counter())
+            (lv, i_, u_), = scal.collect()
+            if trace is not None:
+                trace.append(time.perf_counter())
+            iou = (i_ + 1e-5) / (u_ + 1e-5)
+        if trace:   # per iteration: enqueue time, wait time (ms) — where a slow end-to-end step spent its time on the host
+            it = [(round((trace[2 * k] - (trace[2 * k - 1] if k else trace[0])) * 1e3, 2), round((trace[2 * k + 1] - trace[2 * k]) * 1e3, 2))
+                  for k in range(len(trace) // 2)]
+            print("rank %d e2e trace (enqueue ms, wait ms): %s" % (rank, it), file=sys.stderr)
     f1.record()
     barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
     ms_e2e = f0.elapsed_time(f1)
     tm = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

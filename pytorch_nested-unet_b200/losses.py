@@ -5,6 +5,8 @@ trains.py:120-135.  Forward is ONE fused reduction over (logits, target): BCE-wi
 and — because metrics.iou_score is always called on the same pair right after (trains.py:124) — the integer
 intersection/union counts, which are cached on the logits tensor for metrics.iou_score to pick up.
 LovaszHingeLoss (losses.py:49-96,120-129) is a per-image sort + scan kernel (csrc/lovasz.cu)."""
+import os
+
 import torch
 from torch import nn
 
@@ -51,6 +53,8 @@ class _BCEDiceGroupFunction(torch.autograd.Function):
 def mark_head_group(outputs):
     """Called by the engine on the list of deep-supervision logits it returns: BCEDiceLoss evaluates the whole group on the first
     head it is given (one launch for all of them) and hands the other heads their cached value when the loop reaches them."""
+    if os.environ.get("NUNET_NO_HEAD_GROUP"):      # A/B switch: the per-head launches
+        return outputs
     group = {"tensors": list(outputs), "key": None, "losses": None}
     for k, o in enumerate(outputs):
         o.__dict__["_nunet_head_group"] = (group, k)

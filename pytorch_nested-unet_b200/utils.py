@@ -34,6 +34,20 @@ class AverageMeter(object):
         self.avg = self.sum / self.count
 
 
+def settle_gc(again=False):
+    """One full garbage collection, then gc.freeze(): everything alive now (torch, the model, the captured graphs, the optimizer
+    state) moves to the permanent generation and is never scanned again.  A training process has a large, static heap; a periodic
+    generation-2 collection over it took 70 ms here and landed inside a step every ~40 steps — with the GPU queue only one step
+    deep that is five idle steps, and under data parallelism every rank waits for the slowest one (measured: 2 GPUs, 20-step window,
+    16.3 vs 14.4 ms/step).  Objects created afterwards are collected as usual.  Idempotent unless again=True."""
+    import gc
+    if getattr(settle_gc, "done", False) and not again:
+        return
+    gc.collect()
+    gc.freeze()
+    settle_gc.done = True
+
+
 class DevicePrefetcher(object):
     """Wrapper of a loader of (tensor, ..., meta) host batches (train.train uses it): the host->device copy of batch i+1 is issued on
     a copy stream before batch i is handed out, so it overlaps batch i's step (the reference's loop copies synchronously on the
