@@ -45,8 +45,9 @@ def parse():
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="also write profiles/layers_latest.json")
-    ap.add_argument("--e2e-loop", default="overlap", choices=["overlap", "sync"],
-                    help="overlap: train.train()'s loop (prefetcher + StepScalars); sync: copy on the compute stream and host reads after the step (A/B)")
+    ap.add_argument("--e2e-loop", default="auto", choices=["auto", "overlap", "sync"],
+                    help="what train.train() does: overlap (prefetcher + scalars read before backward is waited for) on one GPU, sync (the reference's "
+                         "placement: copy on the compute stream, host reads after the step) under data parallelism; auto picks by world size")
     ap.add_argument("--kernels-only", action="store_true", help="profiler runs (ncu): only the warm-up and the timed device-resident steps")
     return ap.parse_args()
 
@@ -283,7 +284,11 @@ def run_native(args):
     t_host = ((torch.rand(B, S, S, args.classes, generator=g) > 0.5).to(torch.uint8) * 255).pin_memory()
     x_dev, t_dev = x_host.to(dev), ops.mask_u8(t_host.to(dev))
 
+    STAMPS = None
+
     def step(x, t, scalars=None):
+        if STAMPS is not None:
+            STAMPS.append(time.perf_counter())
         outputs = model(x)
         if isinstance(outputs, list):
             loss = 0
@@ -297,9 +302,15 @@ def run_native(args):
         counts = metrics_counts(last, t)
         if scalars is not None:
             scalars.submit(loss, counts)            # device->host copy of the step's scalars, issued before backward (utils.StepScalars)
+        if STAMPS is not None:
+            STAMPS.append(time.perf_counter())
         opt.zero_grad()
         loss.backward()
+        if STAMPS is not None:
+            STAMPS.append(time.perf_counter())
         opt.step()
+        if STAMPS is not None:
+            STAMPS.append(time.perf_counter())
         return loss, counts
 
     def metrics_counts(last, t):
@@ -357,7 +368,8 @@ def run_native(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if not os.environ.get("NUNET_NO_GC_FREEZE"):
         utils.settle_gc(again=True)
-    if args.e2e_loop == "sync":           # A/B: the reference's own placement (copy on the compute stream, host reads after the step)
+    e2e_loop = args.e2e_loop if args.e2e_loop != "auto" else ("overlap" if world == 1 else "sync")
+    if e2e_loop == "sync":                # the reference's own placement (copy on the compute stream, host reads after the step): train.train() under DP
         for _ in range(2):
             step(x_host.to(dev, non_blocking=True), ops.mask_u8(t_host.to(dev, non_blocking=True)))
         barrier()
@@ -367,6 +379,7 @@ def run_native(args):
             lv = loss.item()
             i_, u_ = counts.tolist()
             iou = (i_ + 1e-5) / (u_ + 1e-5)
+        f1.record()
     else:
         for xb, tb, _ in loader:          # untimed: the ring buffers, pinned result slots and events are created here
             step(xb, ops.mask_u8(tb), scal)
@@ -374,7 +387,7 @@ def run_native(args):
         barrier()
         batches.n = args.steps
         import gc
-        if os.environ.get("NUNET_E2E_TRACE"):
+        if True:    # always on: a collection that takes more than 1 ms inside the timed loop is reported on stderr
             gc_t = {}
 
             def gc_cb(phase, info):
@@ -386,20 +399,37 @@ def run_native(args):
                         print("rank %d gc gen%d %.1f ms collected %d" % (rank, info["generation"], dt, info["collected"]), file=sys.stderr)
             gc.callbacks.append(gc_cb)
         f0.record()
-        trace = [] if os.environ.get("NUNET_E2E_TRACE") else None
+        trace = True if os.environ.get("NUNET_E2E_TRACE") else None       # also print the phase medians when nothing was slow
+        variant = os.environ.get("NUNET_E2E_VARIANT", "")      # diagnosis only: "no_h2d" = the resident batch with the scalar read
+        STAMPS = []
+        iter_t = [time.perf_counter()]
         for xb, tb, _ in loader:
-            loss, counts = step(xb, ops.mask_u8(tb), scal)
-            if trace is not None:
-                trace.append(time.perf_counter())
+            if variant == "no_h2d":
+                loss, counts = step(x_dev, t_dev, scal)
+            else:
+                loss, counts = step(xb, ops.mask_u8(tb), scal)
             (lv, i_, u_), = scal.collect()
-            if trace is not None:
-                trace.append(time.perf_counter())
+            if STAMPS is not None:
+                STAMPS.append(time.perf_counter())
+            iter_t.append(time.perf_counter())
             iou = (i_ + 1e-5) / (u_ + 1e-5)
-        if trace:   # per iteration: enqueue time, wait time (ms) — where a slow end-to-end step spent its time on the host
-            it = [(round((trace[2 * k] - (trace[2 * k - 1] if k else trace[0])) * 1e3, 2), round((trace[2 * k + 1] - trace[2 * k]) * 1e3, 2))
-                  for k in range(len(trace) // 2)]
-            print("rank %d e2e trace (enqueue ms, wait ms): %s" % (rank, it), file=sys.stderr)
-    f1.record()
+        f1.record()
+        if len(iter_t) > 2:    # always: the three slowest host iterations (a stall shows up here with its position)
+            dt = sorted(((iter_t[k + 1] - iter_t[k]) * 1e3, k + 1) for k in range(len(iter_t) - 1))
+            print("rank %d e2e iterations: median %.2f ms, slowest %s" % (rank, dt[len(dt) // 2][0], [(k, round(v, 1)) for v, k in dt[-3:]]), file=sys.stderr)
+        if STAMPS:   # per iteration (ms): loader + forward + loss + submit | backward | optimizer | wait for the scalars
+            rows = []
+            for k in range(len(STAMPS) // 5):
+                a = STAMPS[5 * k:5 * k + 5]
+                prev = STAMPS[5 * k - 1] if k else a[0]
+                rows.append((round((a[0] - prev) * 1e3, 2), round((a[1] - a[0]) * 1e3, 2), round((a[2] - a[1]) * 1e3, 2), round((a[3] - a[2]) * 1e3, 2), round((a[4] - a[3]) * 1e3, 2)))
+            tot = [sum(r) for r in rows]
+            med = sorted(tot)[len(tot) // 2]
+            slow = [(k, rows[k]) for k in range(len(rows)) if tot[k] > 1.15 * med]
+            if slow or trace is not None:
+                print("rank %d e2e host trace: median iteration %.2f ms; median phases (loader, fwd+loss, bwd, opt, wait) %s; iterations over 1.15x median: %s" % (
+                    rank, med, [sorted(r[j] for r in rows)[len(rows) // 2] for j in range(5)], slow), file=sys.stderr)
+            STAMPS = None
     barrier()
     sampler.stop()
     ms_e2e = f0.elapsed_time(f1)
@@ -511,8 +541,11 @@ def run_native(args):
                        "l2": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size() + t_host.numel() * t_host.element_size()) * world,
                     "d2h_bytes_per_step": (4 + 16) * world, "ms_per_step": ms_e2e / args.steps,
-                    "how": "train.train()'s loop: pinned uint8 batch -> device every step (copy stream, one batch ahead), loss + IoU counts -> host "
-                           "every step and read in the same iteration (copy issued before backward is enqueued)"},
+                    "loop": e2e_loop,
+                    "how": ("train.train()'s loop: pinned uint8 batch -> device every step (copy stream, one batch ahead), loss + IoU counts -> host "
+                            "every step and read in the same iteration (copy issued before backward is enqueued)") if e2e_loop == "overlap" else
+                           ("train.train()'s loop under data parallelism: pinned uint8 batch -> device on the compute stream every step, loss + IoU "
+                            "counts read on the host after the step (the reference's placement, trains.py:113-134)")},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roof,

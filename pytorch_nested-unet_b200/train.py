@@ -117,23 +117,29 @@ def _loss_and_iou(config, model, criterion, input, target, on_device=False):
 
 
 def train(config, train_loader, model, criterion, optimizer):
-    """trains.py:106-147.  The scalars of a step (trains.py:124,133-134) are read through utils.StepScalars: their device->host copy is
-    issued before backward is enqueued and waited for after the optimizer step has been enqueued, so the CPU never waits for more than
-    the forward pass and the GPU never runs dry; the meters see the same values in the same iteration."""
+    """trains.py:106-147.  On one GPU the scalars of a step (trains.py:124,133-134) are read through utils.StepScalars — their
+    device->host copy is issued before backward is enqueued and waited for after the optimizer step has been enqueued, so the CPU
+    never waits for more than the forward pass and the GPU never runs dry — and batches arrive through utils.DevicePrefetcher (copy of
+    batch i+1 on a copy stream while step i runs); the meters see the same values in the same iteration.
+    Under data parallelism the loop keeps the reference's placement (copy on the compute stream, scalars read after the step): with
+    the overlapped placement loss.backward() occasionally blocked the host for 30-190 ms on both ranks (2 GPUs, 5 of 11 twenty-step
+    runs; not root-caused), which costs more than the 3 % the overlap gains."""
     avg_meters = {'loss': AverageMeter(), 'iou': AverageMeter()}
     model.train()
+    overlap = _world_size() == 1
     scalars = StepScalars(reduce=True)
     steps_done = 0
-    # DevicePrefetcher: the host->device copy of batch i+1 is issued on a copy stream when batch i is handed out (trains.py:113-114
-    # copies synchronously on the compute stream); the .cuda() calls below are then no-ops
-    for input, target, _ in DevicePrefetcher(train_loader):
+    for input, target, _ in (DevicePrefetcher(train_loader) if overlap else train_loader):
         input = input.cuda(non_blocking=True)
         target = device_target(target.cuda(non_blocking=True))
         loss, counts = _loss_and_iou(config, model, criterion, input, target, on_device=True)
-        scalars.submit(loss, counts)
+        if overlap:
+            scalars.submit(loss, counts)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
+        if not overlap:
+            scalars.submit(loss, counts)       # global mean loss / summed counts on the device, then one host read
         for lv, i_, u_ in scalars.collect():
             avg_meters['loss'].update(lv, input.size(0))
             avg_meters['iou'].update((i_ + 1e-5) / (u_ + 1e-5), input.size(0))      # metrics.py:17-18
