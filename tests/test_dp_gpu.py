@@ -113,8 +113,13 @@ def _worker(rank, world, port, q, backend, same_device):
     res["captured"] = sum(1 for tg in st.__dict__.get("train_graphs", {}).values() if tg.fwd is not None and tg.bwd is not None)
     gl = nd.global_mean(float(loss.detach()), xs.device)
     giou = nd.global_iou_score(out[-1], ts)
+    import metrics
+    import utils
+    scal = utils.StepScalars(reduce=True)        # train.train()'s read of the step's scalars under data parallelism
+    scal.submit(loss.detach(), metrics.iou_counts_device(out[-1], ts))
+    (sl, si, su), = scal.collect()
     torch.cuda.synchronize()
-    res.update({"loss": gl, "iou": giou, "logits": out[-1].detach().cpu(),
+    res.update({"loss": gl, "iou": giou, "scalars": [sl, (si + 1e-5) / (su + 1e-5)], "logits": out[-1].detach().cpu(),
                 "grads": {k: p.grad.detach().cpu() for k, p in model.module.named_parameters()},
                 "rm": model.module.conv2_0.bn1.running_mean.cpu(), "rv": model.module.conv0_4.bn2.running_var.cpu()})
     q.put(_to_numpy(res))        # by value: torch tensors travel as shared-memory handles that die with this process
@@ -173,6 +178,8 @@ def _compare(res):
     noise_logits = float((out_p[-1].detach()[inv] - out[-1].detach()).abs().max() / out[-1].abs().max())
     assert abs(res[0]["loss"] - float(loss.detach())) < max(2e-5, 3 * abs(float(loss_p.detach()) - float(loss.detach()))) and abs(res[1]["loss"] - res[0]["loss"]) < 1e-9
     I, U = counts
+    for r in res:      # utils.StepScalars(reduce=True): global mean loss and IoU over the summed counts, same on every rank
+        assert abs(r["scalars"][0] - r["loss"]) < 1e-6 and r["scalars"][1] == r["iou"]
     assert res[0]["iou"] == res[1]["iou"]
     assert abs(res[0]["iou"] - (I + 1e-5) / (U + 1e-5)) < 2e-3
     both = torch.cat([res[0]["logits"], res[1]["logits"]])
