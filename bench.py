@@ -302,6 +302,8 @@ def run_native(args):
         counts = metrics_counts(last, t)
         if scalars is not None:
             scalars.submit(loss, counts)            # device->host copy of the step's scalars, issued before backward (utils.StepScalars)
+            if not os.environ.get("NUNET_NO_BWD_FENCE"):
+                scalars.before_backward()           # the previous step has left the GPU before this backward graph is launched again
         if STAMPS is not None:
             STAMPS.append(time.perf_counter())
         opt.zero_grad()
@@ -356,7 +358,7 @@ def run_native(args):
     #      utils.StepScalars (copy issued before backward is enqueued, waited for after the optimizer step is enqueued).
 
     class HostBatches(object):            # the loader: `n` pinned host batches per pass
-        n = 4
+        n = 20                            # untimed pass (ring buffers, pinned result slots, events; the rare host stalls of the first second)
 
         def __iter__(self):
             for _ in range(self.n):

@@ -135,6 +135,7 @@ def train(config, train_loader, model, criterion, optimizer):
         loss, counts = _loss_and_iou(config, model, criterion, input, target, on_device=True)
         if overlap:
             scalars.submit(loss, counts)
+            scalars.before_backward()
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
