@@ -389,27 +389,22 @@ def run_native(args):
         barrier()
         batches.n = args.steps
         import gc
-        if True:    # always on: a collection that takes more than 1 ms inside the timed loop is reported on stderr
-            gc_t = {}
+        gc_t = {}
 
-            def gc_cb(phase, info):
-                if phase == "start":
-                    gc_t["t"] = time.perf_counter()
-                else:
-                    dt = (time.perf_counter() - gc_t.get("t", time.perf_counter())) * 1e3
-                    if dt > 1.0:
-                        print("rank %d gc gen%d %.1f ms collected %d" % (rank, info["generation"], dt, info["collected"]), file=sys.stderr)
-            gc.callbacks.append(gc_cb)
+        def gc_cb(phase, info):      # a collection that takes more than 1 ms inside the timed loop is reported on stderr
+            if phase == "start":
+                gc_t["t"] = time.perf_counter()
+            else:
+                dt = (time.perf_counter() - gc_t.get("t", time.perf_counter())) * 1e3
+                if dt > 1.0:
+                    print("rank %d gc gen%d %.1f ms collected %d" % (rank, info["generation"], dt, info["collected"]), file=sys.stderr)
+        gc.callbacks.append(gc_cb)
         f0.record()
         trace = True if os.environ.get("NUNET_E2E_TRACE") else None       # also print the phase medians when nothing was slow
-        variant = os.environ.get("NUNET_E2E_VARIANT", "")      # diagnosis only: "no_h2d" = the resident batch with the scalar read
         STAMPS = []
         iter_t = [time.perf_counter()]
         for xb, tb, _ in loader:
-            if variant == "no_h2d":
-                loss, counts = step(x_dev, t_dev, scal)
-            else:
-                loss, counts = step(xb, ops.mask_u8(tb), scal)
+            loss, counts = step(xb, ops.mask_u8(tb), scal)
             (lv, i_, u_), = scal.collect()
             if STAMPS is not None:
                 STAMPS.append(time.perf_counter())

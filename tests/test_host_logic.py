@@ -173,3 +173,65 @@ def test_checkpoint_layout_interchanges_with_the_reference():
         m2 = getattr(archs, arch)(k, 3, ds)
         m2.load_state_dict(torch.load(buf), strict=True)
         assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_loop_helpers_host_side(tmp_path):
+    """utils.settle_gc (collect + freeze once), bench.ClockSampler's timestamp window, and the grouped criterion's bookkeeping
+    (losses.mark_head_group / the NUNET_NO_HEAD_GROUP switch) — the parts of the loop around the step that need no GPU."""
+    import datetime
+    import gc
+    import importlib.util
+    import time
+    import utils
+    utils.settle_gc.done = False
+    before = gc.get_freeze_count()
+    utils.settle_gc()
+    frozen = gc.get_freeze_count()
+    assert frozen > before and utils.settle_gc.done
+    utils.settle_gc()                                   # idempotent ...
+    assert gc.get_freeze_count() == frozen
+    utils.settle_gc(again=True)                         # ... unless asked again (bench.py: before each timed loop)
+    assert gc.get_freeze_count() >= frozen
+    gc.unfreeze()
+    utils.settle_gc.done = False
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("nunet_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.ClockSampler(0, enabled=False)
+    assert c.summary() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    c.out = open(tmp_path / "smi.csv", "w+")
+    now = datetime.datetime.now()
+
+    def row(dt_ms, mhz, cap):
+        ts = (now + datetime.timedelta(milliseconds=dt_ms)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return "%s, %d, 1965, Not Active, Not Active, Not Active, %s\n" % (ts, mhz, cap)
+    c.out.write(row(-5000, 300, "Not Active"))          # before the timed window: ignored
+    c.out.write(row(50, 1740, "Active") + row(250, 1800, "Active") + row(450, 1710, "Not Active"))
+    c.out.write("garbage line\n")
+
+    class _Proc(object):
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+    c.proc = _Proc()
+    c.t0 = time.time() - 0.01
+    time.sleep(0.6)
+    c.stop()
+    assert c.summary() == {"sm_mhz": 1740, "sm_max_mhz": 1965, "reasons": ["sw_power_cap"], "samples": 3}
+
+    import losses
+    outs = [torch.zeros(2, 1, 4, 4) for _ in range(4)]
+    marked = losses.mark_head_group(outs)
+    assert marked is outs and all(o.__dict__["_nunet_head_group"][1] == k for k, o in enumerate(outs))
+    assert all(o.__dict__["_nunet_head_group"][0] is outs[0].__dict__["_nunet_head_group"][0] for o in outs)
+    os.environ["NUNET_NO_HEAD_GROUP"] = "1"
+    try:
+        plain = [torch.zeros(2, 1, 4, 4) for _ in range(4)]
+        losses.mark_head_group(plain)
+        assert all("_nunet_head_group" not in o.__dict__ for o in plain)
+    finally:
+        del os.environ["NUNET_NO_HEAD_GROUP"]
