@@ -6,6 +6,7 @@ and — because metrics.iou_score is always called on the same pair right after 
 intersection/union counts, which are cached on the logits tensor for metrics.iou_score to pick up.
 LovaszHingeLoss (losses.py:49-96,120-129) is a per-image sort + scan kernel (csrc/lovasz.cu)."""
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -52,28 +53,34 @@ class _BCEDiceGroupFunction(torch.autograd.Function):
 
 def mark_head_group(outputs):
     """Called by the engine on the list of deep-supervision logits it returns: BCEDiceLoss evaluates the whole group on the first
-    head it is given (one launch for all of them) and hands the other heads their cached value when the loop reaches them."""
+    head it is given (one launch for all of them) and hands the other heads their cached value when the loop reaches them.
+    The group only holds WEAK references to the logits, and forgets its cached losses once every head has been served: the logits
+    must not sit in a reference cycle (tensor -> group -> loss -> autograd node -> saved logits) that only the cyclic garbage
+    collector could free — 38 MB of device memory per step at the headline batch."""
     if os.environ.get("NUNET_NO_HEAD_GROUP"):      # A/B switch: the per-head launches
         return outputs
-    group = {"tensors": list(outputs), "key": None, "losses": None}
+    group = {"tensors": [weakref.ref(o) for o in outputs], "key": None, "losses": None, "served": set()}
     for k, o in enumerate(outputs):
         o.__dict__["_nunet_head_group"] = (group, k)
     return outputs
 
 
 def _group_loss(input, target, t):
-    """The cached / freshly evaluated group loss of `input`, or None when `input` is not a marked head or the group does not qualify."""
+    """The cached / freshly evaluated group loss of `input`, or None when `input` is not a marked head, the group does not qualify
+    or has been dissolved (every head served once: a further call takes the ordinary per-head path)."""
     tag = input.__dict__.get("_nunet_head_group")
     if tag is None:
         return None
     group, k = tag
-    heads = group["tensors"]
-    if not (1 < len(heads) <= ops.MAX_LOSS_HEADS) or heads[k] is not input:
+    if group["tensors"] is None:
+        return None
+    heads = [r() for r in group["tensors"]]
+    if any(h is None for h in heads) or not (1 < len(heads) <= ops.MAX_LOSS_HEADS) or heads[k] is not input:
         return None
     key = (target.data_ptr(), target._version, tuple(h._version for h in heads), torch.is_grad_enabled())
     if group["key"] != key:
         ref = heads[0]
-        if not all(h.is_cuda and h.dtype == torch.float32 and h.is_contiguous() and h.shape == ref.shape and h.requires_grad == ref.requires_grad
+        if not all(ops.is_device_tensor(h) and h.dtype == torch.float32 and h.is_contiguous() and h.shape == ref.shape and h.requires_grad == ref.requires_grad
                    for h in heads):
             return None
         if ref.requires_grad and torch.is_grad_enabled():
@@ -85,8 +92,12 @@ def _group_loss(input, target, t):
         if counts is not None:
             for j, h in enumerate(heads):
                 h.__dict__["_nunet_iou"] = (target.data_ptr(), target._version, h._version, counts[j])
-        group["key"], group["losses"] = key, losses
-    return group["losses"][k]
+        group["key"], group["losses"], group["served"] = key, losses, set()
+    out = group["losses"][k]
+    group["served"].add(k)
+    if len(group["served"]) == len(heads):      # the loop is through: nothing ties the logits to the autograd graph any more
+        group["tensors"], group["losses"], group["key"] = None, None, None
+    return out
 
 
 class BCEDiceLoss(nn.Module):

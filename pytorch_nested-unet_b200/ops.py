@@ -78,6 +78,10 @@ def require_cuda(t, what):
         raise L.NunetError("%s must be a CUDA tensor: the B200 path has no CPU fallback" % what)
 
 
+def is_device_tensor(t):
+    return t.is_cuda
+
+
 @functools.lru_cache(maxsize=None)
 def c32_eligible(N, H, W, cin_total, Cout):
     """True if a conv of this shape over pre-activated sources runs on the stacked Cout = 32 kernel (needs *_C32 weight packs)."""

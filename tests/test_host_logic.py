@@ -235,3 +235,128 @@ def test_loop_helpers_host_side(tmp_path):
         assert all("_nunet_head_group" not in o.__dict__ for o in plain)
     finally:
         del os.environ["NUNET_NO_HEAD_GROUP"]
+
+
+def _fake_loss_ops(monkeypatch):
+    """torch-CPU stand-ins for the loss entry points of ops.py (losses.py:107-117 restated), so that the bookkeeping of the grouped
+    criterion — which head is evaluated when, what is cached, what autograd receives, what keeps what alive — runs without a GPU.
+    The kernels themselves are compared with the reference on the GPU (tests/test_head_loss_gpu.py)."""
+    import ops
+    calls = {"multi_fwd": 0, "multi_bwd": 0, "single_fwd": 0, "single_bwd": 0}
+
+    def fwd(x, t):
+        n = x.shape[0]
+        p = torch.sigmoid(x).view(n, -1)
+        tt = t.view(n, -1)
+        sums = torch.stack([(p * tt).sum(1), p.sum(1), tt.sum(1)], 1).double()
+        bce = torch.nn.functional.binary_cross_entropy_with_logits(x, t)
+        dice = (2 * sums[:, 0] + 1e-5) / (sums[:, 1] + sums[:, 2] + 1e-5)
+        loss = (0.5 * bce.double() + 1 - dice.sum() / n).float()
+        o_, t_ = torch.sigmoid(x) > 0.5, t > 0.5
+        return loss, sums, torch.stack([(o_ & t_).sum(), (o_ | t_).sum()]).long()
+
+    def bwd(x, t, g, gmul):
+        with torch.enable_grad():      # called from inside a custom Function's backward, where grad mode is off
+            xr = x.detach().clone().requires_grad_(True)
+            fwd_loss = fwd(xr, t)[0]
+            (gx,) = torch.autograd.grad(fwd_loss, xr)
+        return gx * (float(g) if g is not None else 1.0) * gmul
+
+    def loss_iou_fwd(logits, target, want_counts=True):
+        calls["single_fwd"] += 1
+        return fwd(logits, target)
+
+    def loss_bwd(logits, target, sums, gscale, gmul=1.0, dlogits=None):
+        calls["single_bwd"] += 1
+        return bwd(logits, target, gscale, gmul)
+
+    def loss_iou_fwd_multi(logits_list, target):
+        calls["multi_fwd"] += 1
+        r = [fwd(x, target) for x in logits_list]
+        return torch.stack([a for a, _, _ in r]), torch.stack([b for _, b, _ in r]), torch.stack([c for _, _, c in r])
+
+    def loss_bwd_multi(logits_list, target, sums, gscales, gmul=1.0):
+        calls["multi_bwd"] += 1
+        return [bwd(x, target, g, gmul) if g is not None else None for x, g in zip(logits_list, gscales)]
+
+    for name, fn in (("loss_iou_fwd", loss_iou_fwd), ("loss_bwd", loss_bwd), ("loss_iou_fwd_multi", loss_iou_fwd_multi),
+                     ("loss_bwd_multi", loss_bwd_multi), ("require_cuda", lambda t, what: None), ("is_device_tensor", lambda t: True)):
+        monkeypatch.setattr(ops, name, fn)
+    return calls
+
+
+def test_grouped_criterion_bookkeeping(monkeypatch):
+    """losses.mark_head_group / BCEDiceLoss on the deep-supervision list (trains.py:120-123): one evaluation for the whole loop, the
+    per-head path's values and gradients, dissolution after the last head, a partial loop, another target, no-grad mode, and — the
+    point of the weak references — the logits die with their last reference, without the cyclic garbage collector."""
+    import gc
+    import weakref
+    import losses
+    calls = _fake_loss_ops(monkeypatch)
+    crit = losses.BCEDiceLoss()
+    g = torch.Generator().manual_seed(3)
+    base = [torch.randn(3, 1, 8, 8, generator=g) for _ in range(4)]
+    t = (torch.rand(3, 1, 8, 8, generator=g) > 0.5).float()
+    t2 = (torch.rand(3, 1, 8, 8, generator=g) > 0.5).float()
+    a = [b.clone().requires_grad_(True) for b in base]
+    r = [b.clone().requires_grad_(True) for b in base]
+    heads = losses.mark_head_group([x * 1.0 for x in a])
+    group = heads[0].__dict__["_nunet_head_group"][0]
+    la = [crit(h, t) for h in heads]
+    assert calls["multi_fwd"] == 1 and calls["single_fwd"] == 0          # ONE evaluation served the whole loop
+    assert group["tensors"] is None and group["losses"] is None          # ... and the group dissolved after the last head
+    lr = [crit(x * 1.0, t) for x in r]
+    assert calls["single_fwd"] == 4
+    for k in range(4):
+        assert torch.equal(la[k].detach(), lr[k].detach())
+        assert heads[k].__dict__["_nunet_iou"][3].tolist() == losses.ops.loss_iou_fwd(base[k], t)[2].tolist()
+    (sum(la) / 4).backward()
+    (sum(lr) / 4).backward()
+    assert calls["multi_bwd"] == 1
+    for k in range(4):
+        assert torch.allclose(a[k].grad, r[k].grad, rtol=0, atol=1e-7)
+    # a fifth call on a head of a dissolved group takes the ordinary path
+    n0 = calls["single_fwd"]
+    again = crit(heads[2], t)
+    assert calls["single_fwd"] == n0 + 1 and torch.equal(again.detach(), la[2].detach())
+
+    # no cycle: with the cyclic collector off, the logits are freed when their last reference goes
+    gc.collect()
+    gc.disable()
+    try:
+        heads = losses.mark_head_group([x * 1.0 for x in a])
+        refs = [weakref.ref(h) for h in heads]
+        total = sum(crit(h, t) for h in heads) / 4
+        total.backward()
+        del heads, total
+        assert all(rf() is None for rf in refs)
+        # a partial loop (two of four heads) and then backward: still no cycle once backward has released the saved tensors
+        for x in a:
+            x.grad = None
+        heads = losses.mark_head_group([x * 1.0 for x in a])
+        refs = [weakref.ref(h) for h in heads]
+        n_multi = calls["multi_fwd"]
+        tot = crit(heads[0], t2) + crit(heads[3], t2)
+        assert calls["multi_fwd"] == n_multi + 1 and heads[0].__dict__["_nunet_head_group"][0]["tensors"] is not None
+        tot.backward()
+        ref0 = base[0].clone().requires_grad_(True)
+        crit(ref0 * 1.0, t2).backward()
+        assert torch.allclose(a[0].grad, ref0.grad, rtol=0, atol=1e-7) and float(a[1].grad.abs().max()) == 0.0 and float(a[3].grad.abs().max()) > 0.0
+        del heads, tot
+        assert all(rf() is None for rf in refs)
+    finally:
+        gc.enable()
+
+    # another target re-evaluates the group; no-grad mode goes through the direct multi-head call
+    heads = losses.mark_head_group([x * 1.0 for x in a])
+    n_multi = calls["multi_fwd"]
+    l0, l0b = crit(heads[0], t), crit(heads[0], t2)
+    assert calls["multi_fwd"] == n_multi + 2 and not torch.equal(l0.detach(), l0b.detach())
+    with torch.no_grad():
+        heads = losses.mark_head_group([b.clone() for b in base])
+        assert torch.equal(crit(heads[2], t), lr[2].detach()) and crit(heads[2], t).grad_fn is None
+    # a list that does not qualify (mixed shapes) falls back to the per-head path
+    odd = losses.mark_head_group([torch.randn(3, 1, 8, 8), torch.randn(3, 1, 4, 4)])
+    n0 = calls["single_fwd"]
+    crit(odd[0], t)
+    assert calls["single_fwd"] == n0 + 1
