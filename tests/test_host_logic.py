@@ -360,3 +360,34 @@ def test_grouped_criterion_bookkeeping(monkeypatch):
     n0 = calls["single_fwd"]
     crit(odd[0], t)
     assert calls["single_fwd"] == n0 + 1
+
+
+def test_bench_roofline_model_matches_the_survey():
+    """bench.conv_flops_per_image / bench.network_roofline are the denominator of the headline `roofline.frac`: pin them to the
+    survey's numbers (9.7008 GF/img forward and 29.0866 GF/img training for NestedUNet-DS at 96x96, cross-checked there
+    against torch's flop counter on the reference; 8d: ~25.5 MB/img forward, ~91 MB/img training, 5.30 ms aggregate at batch 256)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("nunet_bench2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fwd, train = bench.conv_flops_per_image("NestedUNet", 96)
+    heads = 4 * 2.0 * 96 * 96 * 32                       # four 1x1 heads (0.15 GF/img each forward in the survey's table, batch 256)
+    assert abs((fwd + heads) / 1e9 - 9.7008) < 0.01
+    assert abs((train + 3 * heads) / 1e9 - 29.0866) < 0.03
+    # work scales with the pixel count; UNet is the encoder + the last anti-diagonal
+    f256, _ = bench.conv_flops_per_image("NestedUNet", 256)
+    assert abs(f256 / fwd - (256 / 96) ** 2) < 1e-9
+    fu, tu = bench.conv_flops_per_image("UNet", 96)
+    assert 0 < fu < fwd and 0 < tu < train
+    pk = {"hbm": 6541.1, "tc_burst": 1658.4, "tc_sustained": 1390.8}
+    net = bench.network_roofline("NestedUNet", 96, 256, True, pk)
+    assert abs(net["flops"] - train * 256) < 1e-3 * train * 256
+    assert 88e6 < net["bytes"] / 256 < 93e6                                  # survey: 91.0 MB per image-step
+    assert 5.2 < net["ms"]["burst"] < 5.4 and 5.9 < net["ms"]["sustained"] < 6.2      # survey 8d: 5.30 ms at the burst peak
+    assert 0.15 < net["hbm_bound_ms"]["sustained"] / net["ms"]["sustained"] < 0.35
+    # more bandwidth can only lower it; a 1-class and a 4-class head differ by the fp32 logits traffic only
+    fast = bench.network_roofline("NestedUNet", 96, 256, True, dict(pk, hbm=2 * pk["hbm"]))
+    assert fast["ms"]["sustained"] < net["ms"]["sustained"]
+    c4 = bench.network_roofline("NestedUNet", 96, 256, True, pk, num_classes=4)
+    assert abs((c4["bytes"] - net["bytes"]) - 4 * 256 * 96 * 96 * 20 * 3) < 1.0
