@@ -153,9 +153,10 @@ class StepScalars(object):
     def before_backward(self):
         """Call right before `loss.backward()`: waits until the PREVIOUS step has left the GPU.  The forward pass of this step is
         already queued behind it, so the GPU keeps working while the host waits, and backward + optimizer are then enqueued while the
-        GPU runs this step's forward.  Why: the captured backward graph is otherwise launched while its own previous launch is still
-        executing, and that launch occasionally blocked the host for 30-190 ms (bench.py's host trace: `bwd` phase 51 / 163 / 185 ms
-        instead of 1.3 ms, GPU idle afterwards) — never seen when the previous replay had finished."""
+        GPU runs this step's forward.  Why: without it the captured backward graph is launched while its own previous launch is still
+        executing, and `loss.backward()` then occasionally blocked the host for 50-190 ms (bench.py's host trace: `bwd` phase 51 / 163 /
+        185 ms instead of 1.3 ms, GPU idle afterwards).  With it the stalls are rarer and smaller (one of 27 ms in 1 380 iterations) but
+        not gone — their cause is open (profiles/r02_summary.md 6)."""
         if self.step_end is not None:
             self.step_end.synchronize()
 
